@@ -1,0 +1,178 @@
+/* rhccq.h — C ABI of the B200 hot path of the RHCCQ encoder.
+ *
+ * librhccq.so replaces the data-parallel core of the reference's hierarchical
+ * palette quantiser (Riccardoalfieri2003/ROIBasedImageCompression).  The
+ * reference is pure Python and has no FFI of its own; the functions below are
+ * what a ctypes binding inside the reference's encoder/compression modules
+ * would call in place of its Python/NumPy/scikit-learn loops.  Each entry
+ * names the reference lines it replaces (paths relative to the reference
+ * root).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with host_;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - functions return 0 on success and a negative value on failure;
+ *     rhccq_last_error() returns the text for the calling thread;
+ *   - nothing is allocated: outputs and workspaces are caller-owned, the
+ *     *_workspace_bytes functions say how much a call may use.  A working set
+ *     that fits in shared memory ignores the workspace (it may be NULL);
+ *   - per-problem result counters double as status: a negative count marks a
+ *     problem the kernel refused (capacity exceeded, unsupported branch) — it
+ *     never truncates or guesses;
+ *   - colours are 24-bit keys R<<16|G<<8|B in uint32 (ascending key order ==
+ *     lexicographic RGB order == np.unique(axis=0) order).
+ *
+ * Batches: problem p owns rows off[p] .. off[p] + cnt[p] of every per-row
+ * array of a call.
+ */
+#ifndef RHCCQ_H
+#define RHCCQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RHCCQ_ABI_VERSION 1
+
+/* status codes stored in per-problem counters */
+#define RHCCQ_ERR_CAPACITY (-1)      /* more rows/entries than the caller's max_* bound */
+#define RHCCQ_ERR_UPSTREAM (-2)      /* an input counter was already negative, or the random table is too short */
+#define RHCCQ_ERR_INDEX_WIDTH (-3)   /* more palette rows than the index type can address */
+#define RHCCQ_ERR_MINIBATCH (-4)     /* >= 10000 non-black colours: the reference switches to MiniBatchKMeans
+                                        (encoder/compression/clustering.py:207-218), not built yet */
+
+int rhccq_abi_version(void);
+const char* rhccq_last_error(void);
+/* 0 when a CUDA device of compute capability 10.x is usable by this process. */
+int rhccq_device_check(void);
+
+/* ------------------------------------------------------------------ host helpers (no GPU involved) */
+
+/* First `count` outputs of numpy.random.RandomState(42).random_sample — the stream every
+ * KMeans(random_state=42) of the reference consumes (clustering.py:751).  host_out: double[count]. */
+int rhccq_kmeans_rng_fill(double* host_out, int count);
+/* Doubles rhccq_palette_split may read for clusters of up to max_rows colours. */
+int rhccq_kmeans_rng_need(int max_rows);
+/* Slots of the cell table rhccq_palette_dbscan builds for a threshold and a row count. */
+int rhccq_palette_dbscan_slots(int thr, int n_rows);
+
+/* Per-problem working set of each op (bytes), and the size of the global workspace to pass for a
+ * batch of n_problems with that working set: 0 when it fits in shared memory. */
+size_t rhccq_workspace_total_bytes(size_t need, int n_problems);
+size_t rhccq_unique_index_workspace_bytes(int max_valid);
+size_t rhccq_palette_dbscan_workspace_bytes(int max_rows, int max_slots);
+size_t rhccq_palette_split_workspace_bytes(int max_rows);
+size_t rhccq_palette_finish_workspace_bytes(int max_rows);
+size_t rhccq_merge_level_workspace_bytes(int max_entries, int max_comps);
+
+/* ------------------------------------------------------------------ a1: unique colours of a segment
+ * Replaces get_all_unique_colors (encoder/compression/clustering.py:4-103) together with the crop /
+ * mask / black-repaint preparation of encoder/compression/subregions.py:315-421.
+ *
+ * img   uint8 [B,H,W,3]; seg int32 [B,H,W] label map or NULL; crops int32 [n_crops,6] =
+ * (image, row0, col0, height, width, segment id; id 0 = whole rectangle).  For crop p the sorted
+ * unique colours go to pal_keys[pal_off[p] ..] (capacity height*width), their number to pal_cnt[p],
+ * and the palette row of every pixel OF THE SEGMENT to index_plane at the pixel's image position
+ * (idx_bytes 2: uint16, 4: uint32; other pixels are left untouched — in the reference's crop they are
+ * black, row 0).  repaint_black != 0 applies subregions.py:395-421.  max_valid bounds the number of
+ * segment pixels of any crop. */
+int rhccq_unique_index(const uint8_t* img, const int32_t* seg, int B, int H, int W,
+                       const int32_t* crops, int n_crops, const int32_t* pal_off,
+                       uint32_t* pal_keys, int32_t* pal_cnt, void* index_plane, int idx_bytes,
+                       int repaint_black, int max_valid, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ a2: clustering parameters
+ * compute_clustering_params (clustering.py:108-135) for device-resident colour counts:
+ * max_cpc[p] = ceil(((1 - q/100) n + ... ) / q) exactly as the Python expression evaluates, 0 -> 1.
+ * quality: double [n] on the device; n_colors: int32 [n] (negative counts give max_cpc 1). */
+int rhccq_cluster_params(const int32_t* n_colors, const double* quality, int n, int32_t* max_cpc, void* stream);
+
+/* ------------------------------------------------------------------ a3': DBSCAN(min_samples=1) on palettes
+ * Replaces DBSCAN(eps/255, min_samples=1).fit_predict(palette/255.0) at clustering.py:204-205,233-235
+ * (scikit-learn: sklearn/cluster/_dbscan.py:397-470).  Rows equal to black take no part (label -2,
+ * clustering.py:185-192); the others get the number of their connected component of the eps-graph,
+ * components numbered by their lowest row.  Predicate: d2 <= thr[p]; with tie[p] != 0 a pair at
+ * d2 == thr[p] is evaluated in float64 on colours/255 against (eps[p]/255)^2 like the KD-tree does.
+ * n_clusters[p] receives the number of components.  */
+int rhccq_palette_dbscan(const uint32_t* pal_keys, const int32_t* pal_off, const int32_t* pal_cnt,
+                         const int32_t* thr, const int32_t* tie, const double* eps, int n_problems,
+                         int32_t* labels, int32_t* n_clusters, int max_rows, int max_slots,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ a3/a4: cluster -> new palette rows
+ * Replaces clustering.py:253-355 and split_large_cluster (:720-775): black rows first, clusters of at
+ * most max_cpc[p] colours one row each in ascending label order, larger clusters split recursively by
+ * KMeans(k, random_state=42, n_init='auto') in the exact arithmetic of oracle/kmeans_restated.py,
+ * leaves in depth-first label order.  leaf[row] = new palette row; n_leaves[p] = new palette size.
+ * rng: the rhccq_kmeans_rng_fill stream on the device.  n_clusters (may be NULL): the counters of
+ * rhccq_palette_dbscan; a negative one is copied to n_leaves[p] and the problem is skipped. */
+int rhccq_palette_split(const uint32_t* pal_keys, const int32_t* pal_off, const int32_t* pal_cnt,
+                        int n_problems, const int32_t* labels, const int32_t* n_clusters,
+                        const int32_t* max_cpc, const double* rng, int rng_len, int32_t* leaf,
+                        int32_t* n_leaves, int max_rows, void* ws, size_t ws_bytes, void* stream);
+
+/* New colour of every leaf = per-channel truncated mean of its members (clustering.py:305,347).
+ * new_keys[pal_off[p] + j], j < n_leaves[p]. */
+int rhccq_palette_finish(const uint32_t* pal_keys, const int32_t* pal_off, const int32_t* pal_cnt,
+                         int n_problems, const int32_t* leaf, const int32_t* n_leaves,
+                         uint32_t* new_keys, int max_rows, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ a3 tail + a5 head: remap and first appearance
+ * indices <- LUT[indices] (clustering.py:373-377) for the pixels of every crop, and per new palette
+ * row the smallest raster position row*W+col at which it appears (0xFFFFFFFF: nowhere) — the order
+ * merge_region_components_simple (encoder/compression/merging.py:52-82) hands out palette slots in.
+ * Entries of crop p: ent_color/ent_fpos[ent_off[p] + j], j < n_leaves[p]. */
+int rhccq_remap_first(const int32_t* seg, int B, int H, int W, const int32_t* crops, int n_crops,
+                      const int32_t* pal_off, const int32_t* leaf, const int32_t* n_leaves,
+                      const uint32_t* new_keys, const int32_t* ent_off, void* index_plane, int idx_bytes,
+                      uint32_t* ent_color, uint32_t* ent_fpos, int max_leaves, void* stream);
+
+/* ------------------------------------------------------------------ a5: merge components of a canvas
+ * merge_region_components_simple (merging.py:8-120) on entries.  Component c owns entries
+ * comp_start[c] .. +comp_cnt[c] (comp_start has n_comps + 1 elements); group g owns components
+ * grp_comp_off[g] .. grp_comp_off[g+1].  Output palette of group g at out_off[g] = comp_start[first
+ * component] + g: black, then the colours in first-appearance order of the reversed paint sequence;
+ * a single non-empty component passes through unchanged (:16-21).  map[entry] = its output row;
+ * out_present[g] = components that took part. */
+int rhccq_merge_level(const uint32_t* color_in, const uint32_t* fpos_in, const int32_t* comp_start,
+                      const int32_t* comp_cnt, const int32_t* grp_comp_off, int n_groups,
+                      uint32_t* color_out, uint32_t* fpos_out, int32_t* out_off, int32_t* out_cnt,
+                      int32_t* out_present, int32_t* map, int max_entries, int max_comps,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* First appearance of clustered rows: fpos_out[off[g] + leaf[off[g]+j]] = min fpos_in[off[g]+j]. */
+int rhccq_first_min(const int32_t* off, const int32_t* cnt, const int32_t* n_leaves, int n_groups,
+                    const int32_t* leaf, const uint32_t* fpos_in, uint32_t* fpos_out, void* stream);
+
+/* Compose segment entry -> final palette row through the three stages
+ * (encoder/compression/test.py:105-142); -1 where the entry does not paint (black, merging.py:76). */
+int rhccq_compose_final(int n_segments, const int32_t* n_leaves1, const int32_t* ent_off0,
+                        const int32_t* seg_region, const int32_t* region_group, const int32_t* group_image,
+                        const int32_t* offA, const int32_t* mapA, const int32_t* offB, const int32_t* mapB,
+                        const int32_t* leaf2, const uint32_t* color2, const int32_t* offC, const int32_t* mapC,
+                        const int32_t* leaf3, const int32_t* presentC, int32_t* ent_final, void* stream);
+
+/* out_plane[pixel] = ent_final[ent_off[p] + index_plane[pixel]] for the pixels of the crops of class
+ * `cls` (crop_class NULL: all crops) whose entry paints.  uint16 output plane [B,H,W]. */
+int rhccq_paint(const int32_t* seg, int B, int H, int W, const int32_t* crops, int n_crops,
+                const int32_t* ent_off, const int32_t* ent_final, const int32_t* crop_class, int cls,
+                const void* index_plane, int idx_bytes, uint16_t* out_plane, void* stream);
+
+/* Operator-level a5 on component dicts that may overlap or leave the canvas (merging.py:52-82).
+ * comps int32 [n,8] = (pixel offset into indices, h, w, row0, col0 relative to the canvas, palette
+ * offset, palette rows, list position).  mode 0: fpos[palette row] = first canvas raster position;
+ * mode 1: prio[pixel] = lowest list position among painting components; mode 2: canvas[pixel] =
+ * map[palette row] for the component that owns the pixel.  Run 0, rhccq_merge_level, 1, 2. */
+int rhccq_comp_pass(const int32_t* comps, int n_comps, const int32_t* indices, int Hc, int Wc, int mode,
+                    const int32_t* map, uint32_t* fpos, int32_t* prio, int32_t* canvas, void* stream);
+
+/* out[i] = sum_{j<i} max(in[j],0), out[n] = total. */
+int rhccq_excl_scan(const int32_t* in, int n, int32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RHCCQ_H */

@@ -1,0 +1,270 @@
+// Per-pixel kernels of the stage-1 driver: one CTA per segment crop.
+//
+//   rhccq_k_unique        sorted unique colours of a segment + index per pixel
+//                         (/root/reference/encoder/compression/clustering.py:4-103,
+//                         with the crop / mask / black-repaint rules of
+//                         encoder/compression/subregions.py:315-421)
+//   rhccq_k_remap_first   indices <- LUT[indices] (clustering.py:373-377) and the
+//                         raster position at which every new colour first
+//                         appears (the order encoder/compression/merging.py:52-82
+//                         assigns palette slots in)
+//   rhccq_k_paint         final index plane through the composed entry table
+//
+// A crop is six int32: image b, row r0, column c0, height h, width w, segment
+// id (0 = every pixel of the rectangle belongs to the crop).  Pixels of the
+// rectangle whose label differs are "outside": black in the reference's crop.
+#include "rhccq_common.cuh"
+#include "rhccq_kernels.h"
+
+#define RHCCQ_PAD_KEY 0xFFFFFFFFu
+
+size_t rhccq_unique_ws_bytes(int max_valid) {
+    size_t np2 = 1;
+    while (np2 < (size_t)(max_valid > 1 ? max_valid : 1)) np2 <<= 1;
+    return rhccq_carve_bytes(np2, 4) * 2;
+}
+
+__device__ __forceinline__ int rhccq_lower_bound_u32(const uint32_t* a, int n, uint32_t key) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <class IdxT>
+__device__ void rhccq_unique_problem(int p, const uint8_t* __restrict__ img, const int32_t* __restrict__ seg,
+                                     int H, int W, const int32_t* __restrict__ crops,
+                                     const int* __restrict__ pal_off, uint32_t* __restrict__ pal_keys,
+                                     int* __restrict__ pal_cnt, IdxT* __restrict__ index_plane, int repaint_black,
+                                     int cap, unsigned char* wsbase) {
+    __shared__ int s_nb, s_valid, s_black;
+    __shared__ unsigned long long s_best;
+    __shared__ uint32_t s_repl;
+    __shared__ int s_scr[RHCCQ_MAX_WARPS + 2];
+    const int32_t* cr = crops + 6 * (size_t)p;
+    const int b = cr[0], r0 = cr[1], c0 = cr[2], h = cr[3], w = cr[4], sid = cr[5];
+    const int npx = h * w;
+    const size_t plane = (size_t)b * H * W;
+    rhccq_carver cv(wsbase);
+    int np2cap = 1;
+    while (np2cap < (cap > 1 ? cap : 1)) np2cap <<= 1;
+    uint32_t* buf = cv.take<uint32_t>(np2cap);
+    int* rank = cv.take<int>(np2cap);
+    if (threadIdx.x == 0) { s_nb = 0; s_valid = 0; s_black = 0; s_best = ~0ull; s_repl = 0u; }
+    __syncthreads();
+    // pass A: collect the non-black colours of the segment
+    RHCCQ_PAR_FOR(q, npx) {
+        const int r = r0 + q / w, c = c0 + q % w;
+        const size_t pos = plane + (size_t)r * W + c;
+        if (seg != nullptr && sid != 0 && seg[pos] != sid) continue;
+        const uint8_t* px = img + 3 * pos;
+        const uint32_t key = rhccq_pack_rgb(px[0], px[1], px[2]);
+        atomicAdd(&s_valid, 1);
+        if (key == 0u) { atomicAdd(&s_black, 1); continue; }
+        const int slot = atomicAdd(&s_nb, 1);
+        if (slot < cap) buf[slot] = key;
+        if (repaint_black) {
+            // "nearest" colour to black = smallest norm, first in raster order (subregions.py:406-416)
+            const unsigned long long cand = ((unsigned long long)rhccq_d2(key, 0u) << 32) | (unsigned)q;
+            atomicMin(&s_best, cand);
+        }
+    }
+    __syncthreads();
+    const int nb = s_nb, nvalid = s_valid, nblack = s_black;
+    if (nb > cap) {                                                // capacity exceeded: report, never truncate
+        if (threadIdx.x == 0) pal_cnt[p] = -1;
+        return;
+    }
+    const bool repaint = repaint_black && nblack > 0 && nb > 0;
+    if (repaint && threadIdx.x == 0) {
+        const int q = (int)(s_best & 0xffffffffu);
+        const uint8_t* px = img + 3 * (plane + (size_t)(r0 + q / w) * W + (c0 + q % w));
+        s_repl = rhccq_pack_rgb(px[0], px[1], px[2]);
+    }
+    const int has_black = (nvalid < npx || (nblack > 0 && !repaint)) ? 1 : 0;
+    const int np2 = rhccq_next_pow2(nb > 1 ? nb : 1);
+    for (int j = nb + (int)threadIdx.x; j < np2; j += (int)blockDim.x) buf[j] = RHCCQ_PAD_KEY;
+    __syncthreads();
+    rhccq_block_bitonic_sort<uint32_t>(buf, np2);
+    RHCCQ_PAR_FOR(j, np2) rank[j] = (j < nb && (j == 0 || buf[j] != buf[j - 1])) ? 1 : 0;
+    __syncthreads();
+    const int n_unique = rhccq_block_excl_scan_array<int>(rank, np2, s_scr);
+    uint32_t* pal = pal_keys + pal_off[p];
+    if (threadIdx.x == 0) {
+        if (has_black) pal[0] = 0u;
+        pal_cnt[p] = ((size_t)(has_black + n_unique) > (size_t)((IdxT)~(IdxT)0) + 1) ? -3 : has_black + n_unique;
+    }
+    RHCCQ_PAR_FOR(j, nb) if (j == 0 || buf[j] != buf[j - 1]) pal[has_black + rank[j]] = buf[j];
+    // pass B: index of every pixel of the segment
+    const uint32_t repl = s_repl;
+    RHCCQ_PAR_FOR(q, npx) {
+        const int r = r0 + q / w, c = c0 + q % w;
+        const size_t pos = plane + (size_t)r * W + c;
+        if (seg != nullptr && sid != 0 && seg[pos] != sid) continue;
+        const uint8_t* px = img + 3 * pos;
+        uint32_t key = rhccq_pack_rgb(px[0], px[1], px[2]);
+        if (key == 0u && repaint) key = repl;
+        int idx = 0;
+        if (key != 0u) idx = has_black + rank[rhccq_lower_bound_u32(buf, nb, key)];
+        index_plane[pos] = (IdxT)idx;
+    }
+}
+
+template <class IdxT>
+__global__ void __launch_bounds__(RHCCQ_PALETTE_THREADS)
+rhccq_k_unique(const uint8_t* __restrict__ img, const int32_t* __restrict__ seg, int H, int W,
+               const int32_t* __restrict__ crops, int n_crops, const int* __restrict__ pal_off,
+               uint32_t* __restrict__ pal_keys, int* __restrict__ pal_cnt, IdxT* __restrict__ index_plane,
+               int repaint_black, int cap, unsigned char* gws, size_t gws_stride) {
+    RHCCQ_DYN_SMEM(dyn);
+    unsigned char* wsbase = gws ? gws + (size_t)blockIdx.x * gws_stride : dyn;
+    for (int p = blockIdx.x; p < n_crops; p += gridDim.x) {
+        rhccq_unique_problem<IdxT>(p, img, seg, H, W, crops, pal_off, pal_keys, pal_cnt, index_plane,
+                                   repaint_black, cap, wsbase);
+        __syncthreads();
+    }
+}
+
+int rhccq_launch_unique(const uint8_t* img, const int32_t* seg, int H, int W, const int32_t* crops, int n_crops,
+                        const int* pal_off, uint32_t* pal_keys, int* pal_cnt, void* index_plane, int idx_bytes,
+                        int repaint_black, int max_valid, rhccq_launch_ws ws, void* stream) {
+    if (n_crops <= 0) return 0;
+    const size_t need = rhccq_unique_ws_bytes(max_valid);
+    size_t smem; unsigned char* gws;
+    if (idx_bytes == 2) {
+        const int grid = rhccq_pick_grid((const void*)rhccq_k_unique<uint16_t>, need, n_crops, ws, &smem, &gws,
+                                         "rhccq_unique_index");
+        if (grid < 0) return -1;
+        RHCCQ_LAUNCH(rhccq_k_unique<uint16_t>, grid, RHCCQ_PALETTE_THREADS, smem, (cudaStream_t)stream,
+                     img, seg, H, W, crops, n_crops, pal_off, pal_keys, pal_cnt, (uint16_t*)index_plane,
+                     repaint_black, max_valid, gws, need);
+    } else if (idx_bytes == 4) {
+        const int grid = rhccq_pick_grid((const void*)rhccq_k_unique<uint32_t>, need, n_crops, ws, &smem, &gws,
+                                         "rhccq_unique_index");
+        if (grid < 0) return -1;
+        RHCCQ_LAUNCH(rhccq_k_unique<uint32_t>, grid, RHCCQ_PALETTE_THREADS, smem, (cudaStream_t)stream,
+                     img, seg, H, W, crops, n_crops, pal_off, pal_keys, pal_cnt, (uint32_t*)index_plane,
+                     repaint_black, max_valid, gws, need);
+    } else {
+        rhccq_set_error("rhccq_unique_index: idx_bytes must be 2 or 4, got %d", idx_bytes);
+        return -1;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- remap + first appearance
+//
+// Entries of crop p live at ent_off[p] .. ent_off[p] + n_leaves[p] of the
+// compact entry table: colour (the clustered palette row) and the smallest
+// raster position r * W + c at which a pixel of the crop carries it
+// (0xFFFFFFFF: no pixel does).
+template <class IdxT>
+__global__ void __launch_bounds__(RHCCQ_PIXEL_THREADS)
+rhccq_k_remap_first(const int32_t* __restrict__ seg, int H, int W, const int32_t* __restrict__ crops, int n_crops,
+                    const int* __restrict__ pal_off, const int* __restrict__ leaf, const int* __restrict__ n_leaves,
+                    const uint32_t* __restrict__ new_keys, const int* __restrict__ ent_off,
+                    IdxT* __restrict__ index_plane, uint32_t* __restrict__ ent_color, uint32_t* __restrict__ ent_fpos,
+                    int smem_rows) {
+    RHCCQ_DYN_SMEM(dyn);
+    uint32_t* s_first = reinterpret_cast<uint32_t*>(dyn);
+    for (int p = blockIdx.x; p < n_crops; p += gridDim.x) {
+        const int32_t* cr = crops + 6 * (size_t)p;
+        const int b = cr[0], r0 = cr[1], c0 = cr[2], h = cr[3], w = cr[4], sid = cr[5];
+        const int npx = h * w;
+        const int m = n_leaves[p];
+        if (m < 0) continue;                                       // an earlier kernel reported an error for p
+        const size_t plane = (size_t)b * H * W;
+        const int* lf = leaf + pal_off[p];
+        uint32_t* first = m <= smem_rows ? s_first : ent_fpos + ent_off[p];
+        RHCCQ_PAR_FOR(v, m) first[v] = 0xFFFFFFFFu;
+        __syncthreads();
+        RHCCQ_PAR_FOR(q, npx) {
+            const int r = r0 + q / w, c = c0 + q % w;
+            const size_t pos = plane + (size_t)r * W + c;
+            if (seg != nullptr && sid != 0 && seg[pos] != sid) continue;
+            const int v = lf[(int)index_plane[pos]] & 0xffff;      // uint16 LUT (clustering.py:373)
+            index_plane[pos] = (IdxT)v;
+            atomicMin(&first[v], (uint32_t)(r * W + c));
+        }
+        __syncthreads();
+        RHCCQ_PAR_FOR(v, m) {
+            if (first == s_first) ent_fpos[ent_off[p] + v] = s_first[v];
+            ent_color[ent_off[p] + v] = new_keys[pal_off[p] + v];
+        }
+        __syncthreads();
+    }
+}
+
+int rhccq_launch_remap_first(const int32_t* seg, int H, int W, const int32_t* crops, int n_crops,
+                             const int* pal_off, const int* leaf, const int* n_leaves, const uint32_t* new_keys,
+                             const int* ent_off, void* index_plane, int idx_bytes, uint32_t* ent_color,
+                             uint32_t* ent_fpos, int max_leaves, void* stream) {
+    if (n_crops <= 0) return 0;
+    int smem_rows = max_leaves;
+    if ((size_t)smem_rows * 4 > 64 * 1024) smem_rows = 16 * 1024;
+    const size_t smem = (size_t)smem_rows * 4;
+    if (idx_bytes == 2) {
+        if (rhccq_smem_optin((const void*)rhccq_k_remap_first<uint16_t>, smem) != 0) return -1;
+        RHCCQ_LAUNCH(rhccq_k_remap_first<uint16_t>, n_crops, RHCCQ_PIXEL_THREADS, smem, (cudaStream_t)stream,
+                     seg, H, W, crops, n_crops, pal_off, leaf, n_leaves, new_keys, ent_off,
+                     (uint16_t*)index_plane, ent_color, ent_fpos, smem_rows);
+    } else if (idx_bytes == 4) {
+        if (rhccq_smem_optin((const void*)rhccq_k_remap_first<uint32_t>, smem) != 0) return -1;
+        RHCCQ_LAUNCH(rhccq_k_remap_first<uint32_t>, n_crops, RHCCQ_PIXEL_THREADS, smem, (cudaStream_t)stream,
+                     seg, H, W, crops, n_crops, pal_off, leaf, n_leaves, new_keys, ent_off,
+                     (uint32_t*)index_plane, ent_color, ent_fpos, smem_rows);
+    } else {
+        rhccq_set_error("rhccq_remap_first: idx_bytes must be 2 or 4, got %d", idx_bytes);
+        return -1;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- paint
+// out[pos] = ent_final[ent_off[p] + index_plane[pos]] for the pixels of crop p
+// whose entry paints (>= 0) and whose crop belongs to class `cls` (crop_class
+// may be null: every crop).  Launch once per class in the reference's paint
+// order (last listed component first) so that the first listed wins overlaps
+// (merging.py:52).
+template <class IdxT>
+__global__ void __launch_bounds__(RHCCQ_PIXEL_THREADS)
+rhccq_k_paint(const int32_t* __restrict__ seg, int H, int W, const int32_t* __restrict__ crops, int n_crops,
+              const int* __restrict__ ent_off, const int* __restrict__ ent_final, const int* __restrict__ crop_class,
+              int cls, const IdxT* __restrict__ index_plane, uint16_t* __restrict__ out_plane) {
+    for (int p = blockIdx.x; p < n_crops; p += gridDim.x) {
+        if (crop_class != nullptr && crop_class[p] != cls) continue;
+        const int32_t* cr = crops + 6 * (size_t)p;
+        const int b = cr[0], r0 = cr[1], c0 = cr[2], h = cr[3], w = cr[4], sid = cr[5];
+        const int npx = h * w;
+        const size_t plane = (size_t)b * H * W;
+        const int* fin = ent_final + ent_off[p];
+        RHCCQ_PAR_FOR(q, npx) {
+            const int r = r0 + q / w, c = c0 + q % w;
+            const size_t pos = plane + (size_t)r * W + c;
+            if (seg != nullptr && sid != 0 && seg[pos] != sid) continue;
+            const int f = fin[(int)index_plane[pos]];
+            if (f >= 0) out_plane[pos] = (uint16_t)f;
+        }
+    }
+}
+
+int rhccq_launch_paint(const int32_t* seg, int H, int W, const int32_t* crops, int n_crops, const int* ent_off,
+                       const int* ent_final, const int* crop_class, int cls, const void* index_plane, int idx_bytes,
+                       uint16_t* out_plane, void* stream) {
+    if (n_crops <= 0) return 0;
+    if (idx_bytes == 2) {
+        RHCCQ_LAUNCH(rhccq_k_paint<uint16_t>, n_crops, RHCCQ_PIXEL_THREADS, 0, (cudaStream_t)stream,
+                     seg, H, W, crops, n_crops, ent_off, ent_final, crop_class, cls,
+                     (const uint16_t*)index_plane, out_plane);
+    } else if (idx_bytes == 4) {
+        RHCCQ_LAUNCH(rhccq_k_paint<uint32_t>, n_crops, RHCCQ_PIXEL_THREADS, 0, (cudaStream_t)stream,
+                     seg, H, W, crops, n_crops, ent_off, ent_final, crop_class, cls,
+                     (const uint32_t*)index_plane, out_plane);
+    } else {
+        rhccq_set_error("rhccq_paint: idx_bytes must be 2 or 4, got %d", idx_bytes);
+        return -1;
+    }
+    return 0;
+}
