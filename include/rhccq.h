@@ -72,8 +72,10 @@ size_t rhccq_merge_level_workspace_bytes(int max_entries, int max_comps);
  * Replaces get_all_unique_colors (encoder/compression/clustering.py:4-103) together with the crop /
  * mask / black-repaint preparation of encoder/compression/subregions.py:315-421.
  *
- * img   uint8 [B,H,W,3]; seg int32 [B,H,W] label map or NULL; crops int32 [n_crops,6] =
- * (image, row0, col0, height, width, segment id; id 0 = whole rectangle).  For crop p the sorted
+ * img   uint8 [B,H,W,3]; seg int32 [K,B,H,W] label maps (one set per class: the ROI and non-ROI
+ * calls have their own, encoder/compression/test.py:105-106) or NULL; crops int32 [n_crops,8] =
+ * (image, row0, col0, height, width, segment id (0 = whole rectangle), class k, unused); the index
+ * plane is [K,B,H,W] like seg.  For crop p the sorted
  * unique colours go to pal_keys[pal_off[p] ..] (capacity height*width), their number to pal_cnt[p],
  * and the palette row of every pixel OF THE SEGMENT to index_plane at the pixel's image position
  * (idx_bytes 2: uint16, 4: uint32; other pixels are left untouched — in the reference's crop they are
@@ -156,9 +158,10 @@ int rhccq_compose_final(int n_segments, const int32_t* n_leaves1, const int32_t*
                         const int32_t* leaf3, const int32_t* presentC, int32_t* ent_final, void* stream);
 
 /* out_plane[pixel] = ent_final[ent_off[p] + index_plane[pixel]] for the pixels of the crops of class
- * `cls` (crop_class NULL: all crops) whose entry paints.  uint16 output plane [B,H,W]. */
+ * `cls` (cls < 0: all crops) whose entry paints.  uint16 output plane [B,H,W].  Call once per class,
+ * last listed class first, so that the first listed one wins overlaps (merging.py:52). */
 int rhccq_paint(const int32_t* seg, int B, int H, int W, const int32_t* crops, int n_crops,
-                const int32_t* ent_off, const int32_t* ent_final, const int32_t* crop_class, int cls,
+                const int32_t* ent_off, const int32_t* ent_final, int cls,
                 const void* index_plane, int idx_bytes, uint16_t* out_plane, void* stream);
 
 /* Operator-level a5 on component dicts that may overlap or leave the canvas (merging.py:52-82).

@@ -45,7 +45,7 @@ SIGNATURES = {
     "rhccq_merge_level": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _Z, _P]),
     "rhccq_first_min": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
     "rhccq_compose_final": (_I, [_I] + [_P] * 17),
-    "rhccq_paint": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P, _I, _P, _P]),
+    "rhccq_paint": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _I, _P, _I, _P, _P]),
     "rhccq_comp_pass": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "rhccq_excl_scan": (_I, [_P, _I, _P, _P]),
 }

@@ -150,7 +150,7 @@ int rhccq_unique_index(const uint8_t* img, const int32_t* seg, int B, int H, int
     RHCCQ_REQUIRE(img && crops && pal_off && pal_keys && pal_cnt && index_plane, "rhccq_unique_index");
     RHCCQ_REQUIRE(B > 0 && H > 0 && W > 0 && n_crops >= 0 && max_valid >= 0, "rhccq_unique_index");
     rhccq_launch_ws lw = {(unsigned char*)ws, ws_bytes};
-    if (rhccq_launch_unique(img, seg, H, W, crops, n_crops, pal_off, pal_keys, pal_cnt, index_plane, idx_bytes,
+    if (rhccq_launch_unique(img, seg, B, H, W, crops, n_crops, pal_off, pal_keys, pal_cnt, index_plane, idx_bytes,
                             repaint_black, max_valid, lw, stream) != 0) return -1;
     return rhccq_after_launch("rhccq_unique_index");
 }
@@ -200,7 +200,7 @@ int rhccq_remap_first(const int32_t* seg, int B, int H, int W, const int32_t* cr
                   "rhccq_remap_first");
     RHCCQ_REQUIRE(B > 0 && H > 0 && W > 0 && n_crops >= 0 && max_leaves >= 1, "rhccq_remap_first");
     RHCCQ_REQUIRE((long long)H * W < 0xFFFFFFFFll, "rhccq_remap_first");
-    if (rhccq_launch_remap_first(seg, H, W, crops, n_crops, pal_off, leaf, n_leaves, new_keys, ent_off, index_plane,
+    if (rhccq_launch_remap_first(seg, B, H, W, crops, n_crops, pal_off, leaf, n_leaves, new_keys, ent_off, index_plane,
                                  idx_bytes, ent_color, ent_fpos, max_leaves, stream) != 0) return -1;
     return rhccq_after_launch("rhccq_remap_first");
 }
@@ -241,11 +241,11 @@ int rhccq_compose_final(int n_segments, const int32_t* n_leaves1, const int32_t*
 }
 
 int rhccq_paint(const int32_t* seg, int B, int H, int W, const int32_t* crops, int n_crops, const int32_t* ent_off,
-                const int32_t* ent_final, const int32_t* crop_class, int cls, const void* index_plane, int idx_bytes,
+                const int32_t* ent_final, int cls, const void* index_plane, int idx_bytes,
                 uint16_t* out_plane, void* stream) {
     RHCCQ_REQUIRE(crops && ent_off && ent_final && index_plane && out_plane, "rhccq_paint");
     RHCCQ_REQUIRE(B > 0 && H > 0 && W > 0 && n_crops >= 0, "rhccq_paint");
-    if (rhccq_launch_paint(seg, H, W, crops, n_crops, ent_off, ent_final, crop_class, cls, index_plane, idx_bytes,
+    if (rhccq_launch_paint(seg, B, H, W, crops, n_crops, ent_off, ent_final, cls, index_plane, idx_bytes,
                            out_plane, stream) != 0) return -1;
     return rhccq_after_launch("rhccq_paint");
 }

@@ -70,15 +70,15 @@ int rhccq_launch_palette_split(const rhccq_palette_batch& B, const int* labels, 
                                rhccq_launch_ws ws, void* stream);
 int rhccq_launch_palette_finish(const rhccq_palette_batch& B, const int* leaf, const int* n_leaves,
                                 uint32_t* new_keys, int max_rows, rhccq_launch_ws ws, void* stream);
-int rhccq_launch_unique(const uint8_t* img, const int32_t* seg, int H, int W, const int32_t* crops, int n_crops,
+int rhccq_launch_unique(const uint8_t* img, const int32_t* seg, int B, int H, int W, const int32_t* crops, int n_crops,
                         const int* pal_off, uint32_t* pal_keys, int* pal_cnt, void* index_plane, int idx_bytes,
                         int repaint_black, int max_valid, rhccq_launch_ws ws, void* stream);
-int rhccq_launch_remap_first(const int32_t* seg, int H, int W, const int32_t* crops, int n_crops,
+int rhccq_launch_remap_first(const int32_t* seg, int B, int H, int W, const int32_t* crops, int n_crops,
                              const int* pal_off, const int* leaf, const int* n_leaves, const uint32_t* new_keys,
                              const int* ent_off, void* index_plane, int idx_bytes, uint32_t* ent_color,
                              uint32_t* ent_fpos, int max_leaves, void* stream);
-int rhccq_launch_paint(const int32_t* seg, int H, int W, const int32_t* crops, int n_crops, const int* ent_off,
-                       const int* ent_final, const int* crop_class, int cls, const void* index_plane, int idx_bytes,
+int rhccq_launch_paint(const int32_t* seg, int B, int H, int W, const int32_t* crops, int n_crops, const int* ent_off,
+                       const int* ent_final, int cls, const void* index_plane, int idx_bytes,
                        uint16_t* out_plane, void* stream);
 int rhccq_launch_merge_level(const rhccq_merge_args& M, int max_entries, int max_comps, rhccq_launch_ws ws,
                              void* stream);

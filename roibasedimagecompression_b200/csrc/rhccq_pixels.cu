@@ -10,9 +10,13 @@
 //                         assigns palette slots in)
 //   rhccq_k_paint         final index plane through the composed entry table
 //
-// A crop is six int32: image b, row r0, column c0, height h, width w, segment
-// id (0 = every pixel of the rectangle belongs to the crop).  Pixels of the
-// rectangle whose label differs are "outside": black in the reference's crop.
+// A crop is eight int32: image b, row r0, column c0, height h, width w, segment
+// id (0 = every pixel of the rectangle belongs to the crop), class k, unused.
+// Pixels of the rectangle whose label differs are "outside": black in the
+// reference's crop.  Label maps and index planes are laid out [K,B,H,W] (one
+// plane set per class: the ROI and non-ROI calls of the stage-1 driver have
+// their own label maps, encoder/compression/test.py:105-106); the image is
+// [B,H,W,3].
 #include "rhccq_common.cuh"
 #include "rhccq_kernels.h"
 
@@ -35,7 +39,7 @@ __device__ __forceinline__ int rhccq_lower_bound_u32(const uint32_t* a, int n, u
 
 template <class IdxT>
 __device__ void rhccq_unique_problem(int p, const uint8_t* __restrict__ img, const int32_t* __restrict__ seg,
-                                     int H, int W, const int32_t* __restrict__ crops,
+                                     int B, int H, int W, const int32_t* __restrict__ crops,
                                      const int* __restrict__ pal_off, uint32_t* __restrict__ pal_keys,
                                      int* __restrict__ pal_cnt, IdxT* __restrict__ index_plane, int repaint_black,
                                      int cap, unsigned char* wsbase) {
@@ -43,10 +47,11 @@ __device__ void rhccq_unique_problem(int p, const uint8_t* __restrict__ img, con
     __shared__ unsigned long long s_best;
     __shared__ uint32_t s_repl;
     __shared__ int s_scr[RHCCQ_MAX_WARPS + 2];
-    const int32_t* cr = crops + 6 * (size_t)p;
+    const int32_t* cr = crops + 8 * (size_t)p;
     const int b = cr[0], r0 = cr[1], c0 = cr[2], h = cr[3], w = cr[4], sid = cr[5];
     const int npx = h * w;
-    const size_t plane = (size_t)b * H * W;
+    const size_t iplane = (size_t)b * H * W;                       // image
+    const size_t plane = ((size_t)cr[6] * B + b) * H * W;          // label map / index plane of the class
     rhccq_carver cv(wsbase);
     int np2cap = 1;
     while (np2cap < (cap > 1 ? cap : 1)) np2cap <<= 1;
@@ -59,7 +64,7 @@ __device__ void rhccq_unique_problem(int p, const uint8_t* __restrict__ img, con
         const int r = r0 + q / w, c = c0 + q % w;
         const size_t pos = plane + (size_t)r * W + c;
         if (seg != nullptr && sid != 0 && seg[pos] != sid) continue;
-        const uint8_t* px = img + 3 * pos;
+        const uint8_t* px = img + 3 * (iplane + (size_t)r * W + c);
         const uint32_t key = rhccq_pack_rgb(px[0], px[1], px[2]);
         atomicAdd(&s_valid, 1);
         if (key == 0u) { atomicAdd(&s_black, 1); continue; }
@@ -80,7 +85,7 @@ __device__ void rhccq_unique_problem(int p, const uint8_t* __restrict__ img, con
     const bool repaint = repaint_black && nblack > 0 && nb > 0;
     if (repaint && threadIdx.x == 0) {
         const int q = (int)(s_best & 0xffffffffu);
-        const uint8_t* px = img + 3 * (plane + (size_t)(r0 + q / w) * W + (c0 + q % w));
+        const uint8_t* px = img + 3 * (iplane + (size_t)(r0 + q / w) * W + (c0 + q % w));
         s_repl = rhccq_pack_rgb(px[0], px[1], px[2]);
     }
     const int has_black = (nvalid < npx || (nblack > 0 && !repaint)) ? 1 : 0;
@@ -103,7 +108,7 @@ __device__ void rhccq_unique_problem(int p, const uint8_t* __restrict__ img, con
         const int r = r0 + q / w, c = c0 + q % w;
         const size_t pos = plane + (size_t)r * W + c;
         if (seg != nullptr && sid != 0 && seg[pos] != sid) continue;
-        const uint8_t* px = img + 3 * pos;
+        const uint8_t* px = img + 3 * (iplane + (size_t)r * W + c);
         uint32_t key = rhccq_pack_rgb(px[0], px[1], px[2]);
         if (key == 0u && repaint) key = repl;
         int idx = 0;
@@ -114,20 +119,20 @@ __device__ void rhccq_unique_problem(int p, const uint8_t* __restrict__ img, con
 
 template <class IdxT>
 __global__ void __launch_bounds__(RHCCQ_PALETTE_THREADS)
-rhccq_k_unique(const uint8_t* __restrict__ img, const int32_t* __restrict__ seg, int H, int W,
+rhccq_k_unique(const uint8_t* __restrict__ img, const int32_t* __restrict__ seg, int B, int H, int W,
                const int32_t* __restrict__ crops, int n_crops, const int* __restrict__ pal_off,
                uint32_t* __restrict__ pal_keys, int* __restrict__ pal_cnt, IdxT* __restrict__ index_plane,
                int repaint_black, int cap, unsigned char* gws, size_t gws_stride) {
     RHCCQ_DYN_SMEM(dyn);
     unsigned char* wsbase = gws ? gws + (size_t)blockIdx.x * gws_stride : dyn;
     for (int p = blockIdx.x; p < n_crops; p += gridDim.x) {
-        rhccq_unique_problem<IdxT>(p, img, seg, H, W, crops, pal_off, pal_keys, pal_cnt, index_plane,
+        rhccq_unique_problem<IdxT>(p, img, seg, B, H, W, crops, pal_off, pal_keys, pal_cnt, index_plane,
                                    repaint_black, cap, wsbase);
         __syncthreads();
     }
 }
 
-int rhccq_launch_unique(const uint8_t* img, const int32_t* seg, int H, int W, const int32_t* crops, int n_crops,
+int rhccq_launch_unique(const uint8_t* img, const int32_t* seg, int B, int H, int W, const int32_t* crops, int n_crops,
                         const int* pal_off, uint32_t* pal_keys, int* pal_cnt, void* index_plane, int idx_bytes,
                         int repaint_black, int max_valid, rhccq_launch_ws ws, void* stream) {
     if (n_crops <= 0) return 0;
@@ -138,14 +143,14 @@ int rhccq_launch_unique(const uint8_t* img, const int32_t* seg, int H, int W, co
                                          "rhccq_unique_index");
         if (grid < 0) return -1;
         RHCCQ_LAUNCH(rhccq_k_unique<uint16_t>, grid, RHCCQ_PALETTE_THREADS, smem, (cudaStream_t)stream,
-                     img, seg, H, W, crops, n_crops, pal_off, pal_keys, pal_cnt, (uint16_t*)index_plane,
+                     img, seg, B, H, W, crops, n_crops, pal_off, pal_keys, pal_cnt, (uint16_t*)index_plane,
                      repaint_black, max_valid, gws, need);
     } else if (idx_bytes == 4) {
         const int grid = rhccq_pick_grid((const void*)rhccq_k_unique<uint32_t>, need, n_crops, ws, &smem, &gws,
                                          "rhccq_unique_index");
         if (grid < 0) return -1;
         RHCCQ_LAUNCH(rhccq_k_unique<uint32_t>, grid, RHCCQ_PALETTE_THREADS, smem, (cudaStream_t)stream,
-                     img, seg, H, W, crops, n_crops, pal_off, pal_keys, pal_cnt, (uint32_t*)index_plane,
+                     img, seg, B, H, W, crops, n_crops, pal_off, pal_keys, pal_cnt, (uint32_t*)index_plane,
                      repaint_black, max_valid, gws, need);
     } else {
         rhccq_set_error("rhccq_unique_index: idx_bytes must be 2 or 4, got %d", idx_bytes);
@@ -162,7 +167,7 @@ int rhccq_launch_unique(const uint8_t* img, const int32_t* seg, int H, int W, co
 // (0xFFFFFFFF: no pixel does).
 template <class IdxT>
 __global__ void __launch_bounds__(RHCCQ_PIXEL_THREADS)
-rhccq_k_remap_first(const int32_t* __restrict__ seg, int H, int W, const int32_t* __restrict__ crops, int n_crops,
+rhccq_k_remap_first(const int32_t* __restrict__ seg, int B, int H, int W, const int32_t* __restrict__ crops, int n_crops,
                     const int* __restrict__ pal_off, const int* __restrict__ leaf, const int* __restrict__ n_leaves,
                     const uint32_t* __restrict__ new_keys, const int* __restrict__ ent_off,
                     IdxT* __restrict__ index_plane, uint32_t* __restrict__ ent_color, uint32_t* __restrict__ ent_fpos,
@@ -170,12 +175,12 @@ rhccq_k_remap_first(const int32_t* __restrict__ seg, int H, int W, const int32_t
     RHCCQ_DYN_SMEM(dyn);
     uint32_t* s_first = reinterpret_cast<uint32_t*>(dyn);
     for (int p = blockIdx.x; p < n_crops; p += gridDim.x) {
-        const int32_t* cr = crops + 6 * (size_t)p;
+        const int32_t* cr = crops + 8 * (size_t)p;
         const int b = cr[0], r0 = cr[1], c0 = cr[2], h = cr[3], w = cr[4], sid = cr[5];
         const int npx = h * w;
         const int m = n_leaves[p];
         if (m < 0) continue;                                       // an earlier kernel reported an error for p
-        const size_t plane = (size_t)b * H * W;
+        const size_t plane = ((size_t)cr[6] * B + b) * H * W;
         const int* lf = leaf + pal_off[p];
         uint32_t* first = m <= smem_rows ? s_first : ent_fpos + ent_off[p];
         RHCCQ_PAR_FOR(v, m) first[v] = 0xFFFFFFFFu;
@@ -197,7 +202,7 @@ rhccq_k_remap_first(const int32_t* __restrict__ seg, int H, int W, const int32_t
     }
 }
 
-int rhccq_launch_remap_first(const int32_t* seg, int H, int W, const int32_t* crops, int n_crops,
+int rhccq_launch_remap_first(const int32_t* seg, int B, int H, int W, const int32_t* crops, int n_crops,
                              const int* pal_off, const int* leaf, const int* n_leaves, const uint32_t* new_keys,
                              const int* ent_off, void* index_plane, int idx_bytes, uint32_t* ent_color,
                              uint32_t* ent_fpos, int max_leaves, void* stream) {
@@ -208,12 +213,12 @@ int rhccq_launch_remap_first(const int32_t* seg, int H, int W, const int32_t* cr
     if (idx_bytes == 2) {
         if (rhccq_smem_optin((const void*)rhccq_k_remap_first<uint16_t>, smem) != 0) return -1;
         RHCCQ_LAUNCH(rhccq_k_remap_first<uint16_t>, n_crops, RHCCQ_PIXEL_THREADS, smem, (cudaStream_t)stream,
-                     seg, H, W, crops, n_crops, pal_off, leaf, n_leaves, new_keys, ent_off,
+                     seg, B, H, W, crops, n_crops, pal_off, leaf, n_leaves, new_keys, ent_off,
                      (uint16_t*)index_plane, ent_color, ent_fpos, smem_rows);
     } else if (idx_bytes == 4) {
         if (rhccq_smem_optin((const void*)rhccq_k_remap_first<uint32_t>, smem) != 0) return -1;
         RHCCQ_LAUNCH(rhccq_k_remap_first<uint32_t>, n_crops, RHCCQ_PIXEL_THREADS, smem, (cudaStream_t)stream,
-                     seg, H, W, crops, n_crops, pal_off, leaf, n_leaves, new_keys, ent_off,
+                     seg, B, H, W, crops, n_crops, pal_off, leaf, n_leaves, new_keys, ent_off,
                      (uint32_t*)index_plane, ent_color, ent_fpos, smem_rows);
     } else {
         rhccq_set_error("rhccq_remap_first: idx_bytes must be 2 or 4, got %d", idx_bytes);
@@ -224,43 +229,44 @@ int rhccq_launch_remap_first(const int32_t* seg, int H, int W, const int32_t* cr
 
 // ---------------------------------------------------------------- paint
 // out[pos] = ent_final[ent_off[p] + index_plane[pos]] for the pixels of crop p
-// whose entry paints (>= 0) and whose crop belongs to class `cls` (crop_class
-// may be null: every crop).  Launch once per class in the reference's paint
+// whose entry paints (>= 0) and whose crop belongs to class `cls` (cls < 0:
+// every crop).  out_plane is [B,H,W].  Launch once per class in the reference's paint
 // order (last listed component first) so that the first listed wins overlaps
 // (merging.py:52).
 template <class IdxT>
 __global__ void __launch_bounds__(RHCCQ_PIXEL_THREADS)
-rhccq_k_paint(const int32_t* __restrict__ seg, int H, int W, const int32_t* __restrict__ crops, int n_crops,
-              const int* __restrict__ ent_off, const int* __restrict__ ent_final, const int* __restrict__ crop_class,
+rhccq_k_paint(const int32_t* __restrict__ seg, int B, int H, int W, const int32_t* __restrict__ crops, int n_crops,
+              const int* __restrict__ ent_off, const int* __restrict__ ent_final,
               int cls, const IdxT* __restrict__ index_plane, uint16_t* __restrict__ out_plane) {
     for (int p = blockIdx.x; p < n_crops; p += gridDim.x) {
-        if (crop_class != nullptr && crop_class[p] != cls) continue;
-        const int32_t* cr = crops + 6 * (size_t)p;
+        const int32_t* cr = crops + 8 * (size_t)p;
+        if (cls >= 0 && cr[6] != cls) continue;
         const int b = cr[0], r0 = cr[1], c0 = cr[2], h = cr[3], w = cr[4], sid = cr[5];
         const int npx = h * w;
-        const size_t plane = (size_t)b * H * W;
+        const size_t oplane = (size_t)b * H * W;
+        const size_t plane = ((size_t)cr[6] * B + b) * H * W;
         const int* fin = ent_final + ent_off[p];
         RHCCQ_PAR_FOR(q, npx) {
             const int r = r0 + q / w, c = c0 + q % w;
             const size_t pos = plane + (size_t)r * W + c;
             if (seg != nullptr && sid != 0 && seg[pos] != sid) continue;
             const int f = fin[(int)index_plane[pos]];
-            if (f >= 0) out_plane[pos] = (uint16_t)f;
+            if (f >= 0) out_plane[oplane + (size_t)r * W + c] = (uint16_t)f;
         }
     }
 }
 
-int rhccq_launch_paint(const int32_t* seg, int H, int W, const int32_t* crops, int n_crops, const int* ent_off,
-                       const int* ent_final, const int* crop_class, int cls, const void* index_plane, int idx_bytes,
+int rhccq_launch_paint(const int32_t* seg, int B, int H, int W, const int32_t* crops, int n_crops, const int* ent_off,
+                       const int* ent_final, int cls, const void* index_plane, int idx_bytes,
                        uint16_t* out_plane, void* stream) {
     if (n_crops <= 0) return 0;
     if (idx_bytes == 2) {
         RHCCQ_LAUNCH(rhccq_k_paint<uint16_t>, n_crops, RHCCQ_PIXEL_THREADS, 0, (cudaStream_t)stream,
-                     seg, H, W, crops, n_crops, ent_off, ent_final, crop_class, cls,
+                     seg, B, H, W, crops, n_crops, ent_off, ent_final, cls,
                      (const uint16_t*)index_plane, out_plane);
     } else if (idx_bytes == 4) {
         RHCCQ_LAUNCH(rhccq_k_paint<uint32_t>, n_crops, RHCCQ_PIXEL_THREADS, 0, (cudaStream_t)stream,
-                     seg, H, W, crops, n_crops, ent_off, ent_final, crop_class, cls,
+                     seg, B, H, W, crops, n_crops, ent_off, ent_final, cls,
                      (const uint32_t*)index_plane, out_plane);
     } else {
         rhccq_set_error("rhccq_paint: idx_bytes must be 2 or 4, got %d", idx_bytes);

@@ -37,13 +37,13 @@ def _as_dev(be: Backend, x, dtype):
 
 
 def unique_index(be: Backend, img, seg, crops, pal_off, pal_capacity: int, *, idx_bytes: int = 2,
-                 repaint_black: bool = False, max_valid: int):
-    """a1 — rhccq_unique_index.  Returns (pal_keys, pal_cnt, index_plane)."""
+                 repaint_black: bool = False, max_valid: int, n_classes: int = 1):
+    """a1 — rhccq_unique_index.  Returns (pal_keys, pal_cnt, index_plane [K,B,H,W])."""
     B, H, W, _ = img.shape
     P = crops.shape[0]
     pal_keys = be.empty((max(pal_capacity, 1),), torch.int32)      # uint32 keys, viewed as int32 storage
     pal_cnt = be.empty((max(P, 1),), I32)
-    plane = be.zeros((B, H, W), torch.int16 if idx_bytes == 2 else torch.int32)
+    plane = be.zeros((n_classes, B, H, W), torch.int16 if idx_bytes == 2 else torch.int32)
     need = be.cdll.rhccq_unique_index_workspace_bytes(max_valid)
     ws, ws_bytes = be.workspace(need, P)
     be.call("rhccq_unique_index", be.ptr(img), be.ptr(seg), B, H, W, be.ptr(crops), P, be.ptr(pal_off),
@@ -133,7 +133,7 @@ def excl_scan(be: Backend, counts):
 def remap_first(be: Backend, seg, plane, crops, pal_off, leaf, n_leaves, new_keys, ent_off, n_entries: int,
                 *, idx_bytes: int, max_leaves: int):
     """LUT remap of the index plane + entry table (colour, first raster position)."""
-    B, H, W = plane.shape
+    _, B, H, W = plane.shape
     P = crops.shape[0]
     ent_color = be.zeros((max(n_entries, 1),), I32)
     ent_fpos = be.empty((max(n_entries, 1),), I32)
@@ -171,6 +171,22 @@ def first_min(be: Backend, off, cnt, n_leaves, leaf, fpos_in):
     be.call("rhccq_first_min", be.ptr(off), be.ptr(cnt), be.ptr(n_leaves), n_groups, be.ptr(leaf),
             be.ptr(fpos_in), be.ptr(fpos_out), be.stream())
     return fpos_out
+
+
+def compose_final(be: Backend, n_segments, n_leaves1, ent_off0, seg_region, region_group, group_image,
+                  A, Bm, leaf2, color2, Cm, leaf3, n_entries: int):
+    ent_final = be.empty((max(n_entries, 1),), I32)
+    be.call("rhccq_compose_final", n_segments, be.ptr(n_leaves1), be.ptr(ent_off0), be.ptr(seg_region),
+            be.ptr(region_group), be.ptr(group_image), be.ptr(A["off"]), be.ptr(A["map"]), be.ptr(Bm["off"]),
+            be.ptr(Bm["map"]), be.ptr(leaf2), be.ptr(color2), be.ptr(Cm["off"]), be.ptr(Cm["map"]), be.ptr(leaf3),
+            be.ptr(Cm["present"]), be.ptr(ent_final), be.stream())
+    return ent_final
+
+
+def paint(be: Backend, seg, crops, ent_off, ent_final, plane, out_plane, *, cls: int, idx_bytes: int):
+    _, B, H, W = plane.shape
+    be.call("rhccq_paint", be.ptr(seg), B, H, W, be.ptr(crops), crops.shape[0], be.ptr(ent_off), be.ptr(ent_final),
+            int(cls), be.ptr(plane), idx_bytes, be.ptr(out_plane), be.stream())
 
 
 def check_counts(name: str, counts) -> None:
