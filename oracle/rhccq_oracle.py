@@ -199,6 +199,29 @@ def dbscan_labels(points: np.ndarray, eps: float, min_samples: int = 1,
                 s = s + t * t
             return s <= r2
 
+    if min_samples <= 1:
+        # every point is core (its neighbourhood holds itself): labels are the connected
+        # components of the eps-graph, numbered by lowest index.  Flood fill from each seed
+        # against the still unlabelled points only.
+        labels = np.full(n, -1, dtype=np.int64)
+        todo = np.arange(n)
+        c = 0
+        while todo.size:
+            seed = todo[0]
+            labels[seed] = c
+            todo = todo[1:]
+            frontier = [seed]
+            while frontier and todo.size:
+                i = frontier.pop()
+                hit = adj_rows(i, i + 1)[0][todo]
+                if hit.any():
+                    got = todo[hit]
+                    labels[got] = c
+                    frontier.extend(got.tolist())
+                    todo = todo[~hit]
+            c += 1
+        return labels
+
     counts = np.zeros(n, dtype=np.int64)
     for lo in range(0, n, step):
         counts[lo:lo + step] = adj_rows(lo, min(n, lo + step)).sum(axis=1)

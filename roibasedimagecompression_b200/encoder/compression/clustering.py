@@ -44,7 +44,7 @@ def get_all_unique_colors(region_image, top_left_coords, *, as_arrays: bool = Fa
     h, w, _ = img.shape
     total = h * w
     d_img = torch.from_numpy(img).to(be.device).reshape(1, h, w, 3)
-    crops = torch.tensor([[0, 0, 0, h, w, 0]], dtype=torch.int32, device=be.device)
+    crops = torch.tensor([[0, 0, 0, h, w, 0, 0, 0]], dtype=torch.int32, device=be.device)
     pal_off = torch.zeros(1, dtype=torch.int32, device=be.device)
     keys, cnt, plane = ops.unique_index(be, d_img, None, crops, pal_off, total, idx_bytes=4, max_valid=total)
     ops.check_counts("get_all_unique_colors", cnt[:1])

@@ -152,11 +152,10 @@ def _dev(be: Backend, a, dtype=torch.int32):
     return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(be.device)
 
 
-def encode_batch(be: Backend, images, labels, table: SegmentTable, *, keep_stages: bool = False) -> EncodeResult:
-    """Three-stage encode of `images` (uint8 [B,H,W,3]) with label maps `labels` (int32 [K,B,H,W]),
-    both already on the backend's device."""
+def stage1(be: Backend, images, labels, table: SegmentTable) -> dict:
+    """Stage 1 for every segment of the batch and the per-region merge
+    (encoder/compression/subregions.py:315-449, :634-683)."""
     B, K, H, W, P, R = table.B, table.K, table.H, table.W, table.P, table.R
-    G = B * K
     if tuple(images.shape) != (B, H, W, 3) or images.dtype != torch.uint8:
         raise ValueError(f"images must be uint8 [{B},{H},{W},3]")
     if tuple(labels.shape) != (K, B, H, W) or labels.dtype != torch.int32:
@@ -164,11 +163,8 @@ def encode_batch(be: Backend, images, labels, table: SegmentTable, *, keep_stage
     if P == 0:
         raise IndexError("no segments: the reference fails here too (regions.py:39 indexes an empty list)")
     q1 = np.asarray(table.qualities, dtype=np.float64)
-    q2 = np.minimum(100.0, 2.0 * q1)                               # test.py:116-120
-    q3 = float(min(100.0, q2.sum()))                               # test.py:139-140
     crops_h = table.crops
     cls_h = crops_h[:, 6]
-    # ---- stage 1: unique colours, clustering, LUT remap
     cap = (crops_h[:, 3].astype(np.int64) * crops_h[:, 4])
     pal_off_h = np.zeros(P + 1, dtype=np.int64)
     np.cumsum(cap, out=pal_off_h[1:])
@@ -180,8 +176,7 @@ def encode_batch(be: Backend, images, labels, table: SegmentTable, *, keep_stage
     pal_keys, pal_cnt, plane = ops.unique_index(be, images, labels, crops, pal_off, int(pal_off_h[-1]),
                                                 idx_bytes=2, repaint_black=True, max_valid=max_valid,
                                                 n_classes=K)
-    max_rows1 = max_valid + 1
-    s1 = ops.cluster_palettes(be, pal_keys, pal_off, pal_cnt, q1[cls_h], max_rows=max_rows1)
+    s1 = ops.cluster_palettes(be, pal_keys, pal_off, pal_cnt, q1[cls_h], max_rows=max_valid + 1)
     nl1_h = s1["n_leaves"][:P].cpu().numpy()                        # the one host synchronisation
     ops.check_counts("stage 1", torch.from_numpy(nl1_h))
     ent_off_h = np.zeros(P + 1, dtype=np.int64)
@@ -191,48 +186,59 @@ def encode_batch(be: Backend, images, labels, table: SegmentTable, *, keep_stage
     ent_color0, ent_fpos0 = ops.remap_first(be, labels, plane, crops, pal_off, s1["leaf"], s1["n_leaves"],
                                             s1["new_keys"], ent_off0, E, idx_bytes=2,
                                             max_leaves=int(nl1_h.max()))
-    # ---- merge level A: segments -> region (subregions.py:639-650)
-    seg_region_h = table.seg_region
-    reg_first = np.searchsorted(seg_region_h, np.arange(R + 1)).astype(np.int32)     # segments of region r
+    # merge level A: segments -> region (subregions.py:639-650)
+    reg_first = np.searchsorted(table.seg_region, np.arange(R + 1)).astype(np.int32)   # segments of region r
     ent_per_region = ent_off_h[reg_first[1:]] - ent_off_h[reg_first[:-1]]
     A = ops.merge_level(be, ent_color0, ent_fpos0, ent_off0, s1["n_leaves"], _dev(be, reg_first), R, E + R + 1,
-                        max_entries=int(ent_per_region.max()), max_comps=int(np.diff(reg_first).max()))
+                        max_entries=int(max(ent_per_region.max(), 1)),
+                        max_comps=int(max(np.diff(reg_first).max(), 1)))
+    return {"pal_keys": pal_keys, "pal_off": pal_off, "pal_cnt": pal_cnt, "plane": plane, "s1": s1, "nl1": nl1_h,
+            "ent_off_h": ent_off_h, "ent_off0": ent_off0, "ent_color0": ent_color0, "ent_fpos0": ent_fpos0,
+            "A": A, "crops": crops, "reg_first": reg_first, "ent_per_region": ent_per_region, "E": E}
+
+
+def encode_batch(be: Backend, images, labels, table: SegmentTable, *, keep_stages: bool = False) -> EncodeResult:
+    """Three-stage encode of `images` (uint8 [B,H,W,3]) with label maps `labels` (int32 [K,B,H,W]),
+    both already on the backend's device."""
+    B, K, H, W, P, R = table.B, table.K, table.H, table.W, table.P, table.R
+    G = B * K
+    st = stage1(be, images, labels, table)
+    q1 = np.asarray(table.qualities, dtype=np.float64)
+    q2 = np.minimum(100.0, 2.0 * q1)                               # test.py:116-120
+    q3 = float(min(100.0, q2.sum()))                               # test.py:139-140
+    A, s1, E, ent_off0, crops, plane = st["A"], st["s1"], st["E"], st["ent_off0"], st["crops"], st["plane"]
+    ent_per_region = st["ent_per_region"]
     # ---- merge level B: regions -> class canvas (regions.py:18-39)
     region_group_h = table.region_group
     grp_first = np.searchsorted(region_group_h, np.arange(G + 1)).astype(np.int32)   # regions of group g
-    capA = ent_per_region + 1
-    capA_cum = np.concatenate([[0], np.cumsum(capA)])
+    capA_cum = np.concatenate([[0], np.cumsum(ent_per_region + 1)])
     ent_per_group = capA_cum[grp_first[1:]] - capA_cum[grp_first[:-1]]
     Bm = ops.merge_level(be, A["color"], A["fpos"], A["off"], A["cnt"], _dev(be, grp_first), G, E + R + G + 1,
                          max_entries=int(max(ent_per_group.max(), 1)),
                          max_comps=int(max(np.diff(grp_first).max(), 1)))
     # ---- stage 2: cluster the class canvases (regions.py:45-68)
-    max_rows2 = int(max(ent_per_group.max(), 1)) + 1
-    q2_g = np.tile(q2, B)
-    s2 = ops.cluster_palettes(be, Bm["color"], Bm["off"][:G], Bm["cnt"], q2_g, max_rows=max_rows2)
+    s2 = ops.cluster_palettes(be, Bm["color"], Bm["off"][:G], Bm["cnt"], np.tile(q2, B),
+                              max_rows=int(max(ent_per_group.max(), 1)) + 1)
     fpos2 = ops.first_min(be, Bm["off"], Bm["cnt"], s2["n_leaves"], s2["leaf"], Bm["fpos"])
     # ---- merge level C: classes -> image (image.py:246-256)
     img_first = (np.arange(B + 1) * K).astype(np.int32)
-    capB = ent_per_group + 1
-    ent_per_image = capB.reshape(B, K).sum(axis=1)
+    ent_per_image = (ent_per_group + 1).reshape(B, K).sum(axis=1)
     Cm = ops.merge_level(be, s2["new_keys"], fpos2, Bm["off"], s2["n_leaves"], _dev(be, img_first), B,
                          E + R + G + B + 1, max_entries=int(ent_per_image.max()), max_comps=K)
     # ---- stage 3 (image.py:261-286)
-    max_rows3 = int(ent_per_image.max()) + 1
-    s3 = ops.cluster_palettes(be, Cm["color"], Cm["off"][:B], Cm["cnt"], [q3] * B, max_rows=max_rows3)
+    s3 = ops.cluster_palettes(be, Cm["color"], Cm["off"][:B], Cm["cnt"], [q3] * B,
+                              max_rows=int(ent_per_image.max()) + 1)
     # ---- compose and paint (last listed class first: merging.py:52)
     group_image_h = (np.arange(G) // K).astype(np.int32)
-    ent_final = ops.compose_final(be, P, s1["n_leaves"], ent_off0, _dev(be, seg_region_h), _dev(be, region_group_h),
-                                  _dev(be, group_image_h), A, Bm, s2["leaf"], s2["new_keys"], Cm, s3["leaf"], E)
+    ent_final = ops.compose_final(be, P, s1["n_leaves"], ent_off0, _dev(be, table.seg_region),
+                                  _dev(be, region_group_h), _dev(be, group_image_h), A, Bm, s2["leaf"],
+                                  s2["new_keys"], Cm, s3["leaf"], E)
     out = be.zeros((B, H, W), torch.int16)
     for k in range(K - 1, -1, -1):
         ops.paint(be, labels, crops, ent_off0, ent_final, plane, out, cls=k, idx_bytes=2)
     res = EncodeResult(indices=out, palette_keys=s3["new_keys"], palette_off=Cm["off"], palette_cnt=s3["n_leaves"])
     if keep_stages:
-        res.stage = {"pal_keys": pal_keys, "pal_off": pal_off, "pal_cnt": pal_cnt, "plane": plane, "s1": s1,
-                     "ent_off0": ent_off0, "ent_color0": ent_color0, "ent_fpos0": ent_fpos0, "A": A, "B": Bm,
-                     "s2": s2, "fpos2": fpos2, "C": Cm, "s3": s3, "ent_final": ent_final, "crops": crops,
-                     "nl1": nl1_h, "ent_off_h": ent_off_h, "reg_first": reg_first, "grp_first": grp_first}
+        res.stage = dict(st, B=Bm, s2=s2, fpos2=fpos2, C=Cm, s3=s3, ent_final=ent_final, grp_first=grp_first)
     return res
 
 
