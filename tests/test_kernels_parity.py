@@ -1,0 +1,276 @@
+"""The kernels (through the C ABI) against the oracle and the reference's golden vectors.
+
+Every test runs twice: on the host-emulation build of the kernel sources (CPU tier) and, marked
+``gpu``, on the nvcc build for sm_100a (the product).  Integer / index work is compared bit for bit.
+K-Means: the kernel must equal oracle/kmeans_restated.py bit for bit; against scikit-learn's own
+assignment (injected through ``leaf_override``) everything downstream is bit-exact as well.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, injected_kmeans, same_component
+from oracle import rhccq_oracle as O
+from roibasedimagecompression_b200 import ops, pipeline
+from roibasedimagecompression_b200.encoder import compression as C
+from roibasedimagecompression_b200.synth import synth, tile_regions
+
+
+# --------------------------------------------------------------------------- a1
+def test_unique_colors_golden(backend):
+    g = golden("unique_colors.npz")
+    for i in range(3):
+        r = C.get_all_unique_colors(g[f"crop{i}"], (7 * i, 3 * i), as_arrays=True)
+        assert np.array_equal(r["palette"], g[f"palette{i}"])
+        assert np.array_equal(r["indices"], g[f"indices{i}"])
+        assert r["actual_colors"] == len(g[f"palette{i}"]) and r["top_left"] == (7 * i, 3 * i)
+
+
+def test_unique_colors_edge_cases(backend):
+    assert C.get_all_unique_colors(None, (0, 0)) is None                       # clustering.py:9-10
+    assert C.get_all_unique_colors(np.zeros((0, 4, 3), np.uint8), (0, 0)) is None
+    one = np.full((1, 1, 3), 7, np.uint8)
+    r = C.get_all_unique_colors(one, (3, 4))
+    assert r["palette"] == [[7, 7, 7]] and r["indices"] == [0]
+    black = np.zeros((5, 6, 3), np.uint8)
+    r = C.get_all_unique_colors(black, (0, 0), as_arrays=True)
+    assert r["palette"].tolist() == [[0, 0, 0]] and not r["indices"].any()
+    rng = np.random.default_rng(3)
+    wide = rng.integers(0, 256, size=(37, 113, 3)).astype(np.uint8)             # every pixel its own colour, ragged size
+    r = C.get_all_unique_colors(wide, (0, 0), as_arrays=True)
+    ref = O.get_all_unique_colors(wide, (0, 0))
+    assert np.array_equal(r["palette"], ref["palette"]) and np.array_equal(r["indices"], ref["indices"])
+
+
+# --------------------------------------------------------------------------- a2
+def test_cluster_params_device_matches_python(backend):
+    be = backend
+    ns = np.array([0, 1, 2, 7, 99, 100, 3164, 9999, 65535, 250000], dtype=np.int32)
+    for q in (1.0, 10.0, 20.0, 33.0, 40.0, 60.0, 99.0, 100.0):
+        dev = ops.cluster_params(be, torch.from_numpy(ns).to(be.device),
+                                 torch.full((len(ns),), q, dtype=torch.float64, device=be.device))
+        want = [O.compute_clustering_params(int(n), q)[2] for n in ns]
+        assert dev.cpu().tolist() == want, q
+
+
+# --------------------------------------------------------------------------- a3'
+def test_palette_dbscan_matches_sklearn_golden(backend):
+    g = golden("dbscan_palette.npz")
+    for ti in range(4):
+        pal = g[f"pal{ti}"]
+        for q in g["qs"]:
+            eps, _, _ = O.compute_clustering_params(len(pal), int(q))
+            lab = C.clustering.dbscan_palette_labels(pal, eps)
+            assert np.array_equal(lab, g[f"lab{ti}_q{q}"]), (ti, int(q))
+
+
+def test_palette_dbscan_ties_and_tiny(backend):
+    # eps^2 integer -> pairs at d2 == eps^2 are float64 ties; q = 75 -> eps 32, q = 50 -> eps 64
+    rng = np.random.default_rng(5)
+    base = rng.integers(1, 200, size=(40, 3))
+    pts = [base]
+    for d in ([32, 0, 0], [0, 32, 0], [0, 0, 32], [64, 0, 0], [0, 64, 0]):
+        pts.append(np.clip(base + d, 1, 255))
+    pal = np.unique(np.concatenate(pts), axis=0).astype(np.uint8)
+    for q in (50, 75, 87.5):
+        eps = 128 - 1.28 * q
+        want = O._dbscan_sklearn(pal, eps, 1) if _have_sklearn() else O.dbscan_labels(pal, eps, 1, colour_scale=True)
+        assert np.array_equal(C.clustering.dbscan_palette_labels(pal, eps), want), q
+    for n in (1, 2, 3):
+        p = np.array([[10, 10, 10], [10, 10, 12], [200, 10, 10]], np.uint8)[:n]
+        assert np.array_equal(C.clustering.dbscan_palette_labels(p, 1.0),
+                              O.dbscan_labels(p, 1.0, 1, colour_scale=True))
+
+
+def _have_sklearn():
+    try:
+        import sklearn  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+# --------------------------------------------------------------------------- a3 / a4
+def _golden_cluster_cases(g):
+    for c in range(int(g["n_cases"])):
+        q = int(g[f"q{c}"])
+        comp = {"palette": g[f"in_palette{c}"], "indices": g[f"in_indices{c}"],
+                "shape": tuple(int(v) for v in g[f"shape{c}"]), "top_left": (0, 0)}
+        eps, _, m = O.compute_clustering_params(len(comp["palette"]), q, "lab")
+        yield c, q, comp, eps, m
+
+
+def test_cluster_palette_equals_restated_oracle(backend):
+    """Kernel K-Means == oracle/kmeans_restated.py bit for bit, so palette and indices are identical."""
+    g = golden("cluster_palette.npz")
+    for c, q, comp, eps, m in _golden_cluster_cases(g):
+        want = O.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m)
+        got = C.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m,
+                                                as_arrays=True)
+        assert np.array_equal(got["palette"], want["palette"]), (c, q)
+        assert np.array_equal(got["indices"], want["indices"]), (c, q)
+        assert got["compressed_colors"] == want["compressed_colors"]
+        assert got["original_unique_colors"] == want["original_unique_colors"]
+
+
+def test_cluster_palette_equals_reference_when_sklearn_assignment_injected(backend):
+    """With scikit-learn's own K-Means labels injected, the result equals the reference's golden output."""
+    g = golden("cluster_palette.npz")
+    km = injected_kmeans(g)
+    for c, q, comp, eps, m in _golden_cluster_cases(g):
+        ref = O.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m,
+                                                kmeans_impl=km)
+        assert np.array_equal(ref["palette"], g[f"out_palette{c}"])
+        # the oracle's LUT (old row -> new row) is the leaf assignment to inject
+        pal_in = comp["palette"]
+        lut = np.zeros(len(pal_in), np.int32)
+        lut[np.asarray(comp["indices"])] = ref["indices"]            # every row is used by some pixel
+        used = np.zeros(len(pal_in), bool)
+        used[np.asarray(comp["indices"])] = True
+        assert used.all()
+        got = C.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m,
+                                                as_arrays=True, leaf_override=lut)
+        assert np.array_equal(got["palette"], g[f"out_palette{c}"]), (c, q)
+        assert np.array_equal(got["indices"], g[f"out_indices{c}"]), (c, q)
+
+
+def test_cluster_palette_degenerate(backend):
+    allblack = {"palette": [[0, 0, 0]], "indices": [0, 0, 0, 0], "shape": (2, 2), "top_left": (0, 0)}
+    assert C.cluster_palette_colors_parallel(20, allblack, eps=102.4, min_samples=1) is allblack   # clustering.py:197-199
+    two = {"palette": [[0, 0, 0], [5, 6, 7]], "indices": [0, 1, 1, 0], "shape": (2, 2), "top_left": (1, 2)}
+    r = C.cluster_palette_colors_parallel(20, two, eps=102.4, min_samples=1, max_colors_per_cluster=1)
+    w = O.cluster_palette_colors_parallel(20, two, eps=102.4, min_samples=1, max_colors_per_cluster=1)
+    assert r["palette"] == w["palette"].tolist() and r["indices"] == w["indices"].tolist()
+    with pytest.raises(NotImplementedError):
+        C.cluster_palette_colors_parallel(20, two, eps=102.4, min_samples=2)
+
+
+# --------------------------------------------------------------------------- a5
+def test_merge_canvas_golden(backend):
+    g = golden("merge_canvas.npz")
+    comps = [{"top_left": tuple(int(v) for v in g[f"top_left{i}"]), "shape": tuple(int(v) for v in g[f"shape{i}"]),
+              "palette": g[f"palette{i}"], "indices": g[f"indices{i}"]} for i in range(int(g["n_comp"]))]
+    r = C.merge_region_components_simple(comps, tuple(int(v) for v in g["bbox"]), as_arrays=True)[0]
+    assert np.array_equal(r["palette"], g["out_palette"])
+    assert np.array_equal(r["indices"], g["out_indices"])
+    assert tuple(r["shape"]) == tuple(g["out_shape"])
+    assert r["actual_colors"] == len(g["out_palette"])
+
+
+def test_merge_degenerate(backend):
+    assert C.merge_region_components_simple([], (0, 0, 4, 4)) == []             # merging.py:13-14
+    one = {"top_left": (0, 0), "shape": (1, 2), "palette": [[1, 2, 3]], "indices": [0, 0]}
+    r = C.merge_region_components_simple([one], (0, 0, 4, 4))                   # :16-21
+    assert r[0]["actual_colors"] == 1 and r[0]["palette"] == one["palette"] and r[0] is not one
+
+
+def test_merge_random_overlaps(backend):
+    rng = np.random.default_rng(21)
+    for trial in range(4):
+        comps = []
+        for _ in range(int(rng.integers(2, 7))):
+            h, w = int(rng.integers(1, 12)), int(rng.integers(1, 12))
+            m = int(rng.integers(1, 6))
+            pal = rng.integers(0, 4, size=(m, 3)).astype(np.uint8) * 60          # few colours -> shared between comps
+            pal = np.unique(pal, axis=0)
+            comps.append({"top_left": (int(rng.integers(-3, 14)), int(rng.integers(-3, 14))), "shape": (h, w),
+                          "palette": pal, "indices": rng.integers(0, len(pal), size=h * w)})
+        want = O.merge_region_components_simple(comps, (0, 0, 16, 16))[0]
+        got = C.merge_region_components_simple(comps, (0, 0, 16, 16), as_arrays=True)[0]
+        assert np.array_equal(got["palette"], want["palette"]), trial
+        assert np.array_equal(got["indices"], want["indices"]), trial
+
+
+# --------------------------------------------------------------------------- a6 / a7: the three stages
+def _encode_device(be, img, roi, non, qualities=(20, 10)):
+    H, W, _ = img.shape
+    tab, lab = pipeline.table_from_regions((H, W), [roi, non], qualities)
+    res = pipeline.encode_batch(be, torch.from_numpy(img[None].copy()).to(be.device),
+                                torch.from_numpy(lab).to(be.device), tab)
+    pipeline.finish_checks(res)
+    return res.palette(0), res.index_image(0).reshape(-1).astype(np.int64)
+
+
+@pytest.mark.parametrize("name", ["pipeline_small.npz", "pipeline_synth.npz"])
+def test_pipeline_equals_oracle(backend, name):
+    g = golden(name)
+    img = g["image"]
+    roi, non = tile_regions(img.shape[0], img.shape[1], int(g["tile"]))
+    want = O.encode_image(img, roi, non)
+    pal, idx = _encode_device(backend, img, roi, non)
+    assert np.array_equal(pal, want["palette"])
+    assert np.array_equal(idx, want["indices"])
+    # against the reference's own output (scikit-learn K-Means): tolerance of SURVEY.md 8 a9
+    rec = pal[idx.reshape(img.shape[:2])]
+    assert abs(O.psnr(rec, img) - float(g["psnr"])) < 0.3
+    assert abs(len(pal) - len(g["palette"])) <= max(2, 0.1 * len(g["palette"]))
+
+
+def test_pipeline_irregular_segments_with_black(backend):
+    """Non-rectangular segments, true-black pixels inside segments (subregions.py:395-421), a region
+    with one segment (:679) and ROI/non-ROI overlap in the 3 px buffer (encoder/ROI/roi.py:685-718)."""
+    H, W = 72, 96
+    img = synth(H, W, 77, sigma=2.0)
+    img[10:14, 20:30] = 0
+    img[50, 60] = 0
+    yy, xx = np.mgrid[0:H, 0:W]
+    roi_mask = ((yy - 36) ** 2 + (xx - 48) ** 2) < 28 ** 2
+    non_mask = ((yy - 36) ** 2 + (xx - 48) ** 2) >= 25 ** 2                   # overlaps the ROI ring
+    seg = (1 + (yy // 24) * 4 + (xx + yy // 3) // 24).astype(np.int32)
+
+    def region(mask):
+        rows = np.flatnonzero(mask.any(axis=1)); cols = np.flatnonzero(mask.any(axis=0))
+        r0, r1, c0, c1 = rows[0], rows[-1] + 1, cols[0], cols[-1] + 1
+        bm = mask[r0:r1, c0:c1]
+        return {"bbox": (int(r0), int(c0), int(r1), int(c1)), "bbox_mask": bm,
+                "segments": np.where(bm, seg[r0:r1, c0:c1], 0).astype(np.int32)}
+    small = np.zeros((H, W), bool)
+    small[2:9, 80:93] = True
+    roi = [region(roi_mask)]
+    single = region(small)
+    single["segments"] = np.where(single["bbox_mask"], 1, 0).astype(np.int32)
+    non = [region(non_mask & ~small), single]
+    want = O.encode_image(img, roi, non)
+    pal, idx = _encode_device(backend, img, roi, non)
+    assert np.array_equal(pal, want["palette"])
+    assert np.array_equal(idx, want["indices"])
+
+
+def test_stage_functions_equal_oracle(backend):
+    """subregion_quantization -> region_quantization -> quantize_image through the reference-named shims."""
+    g = golden("pipeline_small.npz")
+    img = g["image"]
+    H, W, _ = img.shape
+    roi, non = tile_regions(H, W, int(g["tile"]))
+    s1r = C.subregion_quantization(img, roi, 20, "ROI")
+    s1n = C.subregion_quantization(img, non, 10, "nonROI")
+    w1r = O.subregion_quantization(img, roi, 20, "ROI")
+    w1n = O.subregion_quantization(img, non, 10, "nonROI")
+    for got, want in ((s1r, w1r), (s1n, w1n)):
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert len(a) == len(b) and all(same_component(x, y) for x, y in zip(a, b))
+    r2 = C.region_quantization(s1r, H, W, 40)
+    n2 = C.region_quantization(s1n, H, W, 20)
+    assert same_component(r2[0], O.region_quantization(w1r, H, W, 40)[0])
+    assert same_component(n2[0], O.region_quantization(w1n, H, W, 20)[0])
+    fin = C.quantize_image(r2 + n2, H, W, 60)
+    want = O.encode_image(img, roi, non)
+    assert same_component(fin, want)
+    assert isinstance(fin["indices"], list) and isinstance(fin["palette"], list)   # the reference's list contract
+    assert fin["indices_dtype"] == want["indices_dtype"]
+
+
+def test_batch_of_images_equals_per_image(backend):
+    be = backend
+    H, W, tile, B = 64, 96, 32, 3
+    imgs = np.stack([synth(H, W, 1234 + i) for i in range(B)])
+    tab, lab = pipeline.table_from_tiles(B, H, W, tile)
+    labels = np.repeat(lab, B, axis=1)
+    res = pipeline.encode_batch(be, torch.from_numpy(imgs).to(be.device), torch.from_numpy(labels).to(be.device), tab)
+    pipeline.finish_checks(res)
+    roi, non = tile_regions(H, W, tile)
+    for b in range(B):
+        want = O.encode_image(imgs[b], roi, non)
+        assert np.array_equal(res.palette(b), want["palette"]), b
+        assert np.array_equal(res.index_image(b).reshape(-1).astype(np.int64), want["indices"]), b
