@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the RHCCQ encoder hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c1k]
+
+One step = one three-stage encode (stage 1 per segment, stage 2 per class, stage 3 per image:
+/root/reference/encoder/compression/test.py:100-142) of a batch of synthetic images with the synthetic
+tile segmentation of SURVEY.md 8d.  Default workload `c2` is BASELINE.json configs[1]: 64 images of
+1920x1080 per GPU (image-sharded: every rank owns its images, no data-path collective; weak scaling).
+
+JSON keys beyond the base contract:
+  roofline      the dominant kernel of the step, timed with CUDA events on the launching stream inside
+                the timed region; algorithmic bytes = 9 B/pixel x pixels per launch
+  kernels       per entry point: launches per step, ms per step, share of the step
+  cpu_baseline  oracle/ (a numpy port of the reference path) on the host cores, one frame of the batch
+  parity        the GPU result of that frame equals the oracle's bit for bit
+  e2e           the same metric through pipeline.HostEncoder: host buffers in, host buffers out
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_PIXEL = 9          # 3 B RGB + 4 B int32 segment label read, 2 B final index written
+WORKLOADS = {
+    # name: (images per GPU, H, W, tile, description)
+    "c2": (64, 1080, 1920, 64, "64 x 1920x1080 synthetic images per GPU, 64 px checker tiles, qualities 20/10->40/20->60"),
+    "c3": (1, 2160, 3840, 64, "1 x 3840x2160 synthetic image, 64 px checker tiles, qualities 20/10->40/20->60"),
+    "c1k": (8, 1080, 1920, 64, "8 x 1920x1080 synthetic images per GPU (short variant of c2)"),
+}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- inputs
+def make_inputs(B: int, H: int, W: int, tile: int, first_seed: int):
+    from concurrent.futures import ThreadPoolExecutor
+    from roibasedimagecompression_b200.synth import synth
+    from roibasedimagecompression_b200 import pipeline
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        imgs = list(ex.map(lambda i: synth(H, W, first_seed + i), range(B)))
+    table, lab = pipeline.table_from_tiles(B, H, W, tile)
+    return np.stack(imgs), np.ascontiguousarray(np.broadcast_to(lab, (lab.shape[0], B, H, W))), table
+
+
+# --------------------------------------------------------------------------- CPU side (checker / baseline)
+def _seg_job(args):
+    from oracle import rhccq_oracle as O
+    img, region, sid, q = args
+    return O.segment_component(img, region, region["segments"], sid, q)
+
+
+def oracle_encode_frame(img: np.ndarray, tile: int, pool, qualities=(20, 10)):
+    """oracle/rhccq_oracle.encode_image with the independent stage-1 segments spread over `pool`."""
+    from oracle import rhccq_oracle as O
+    from roibasedimagecompression_b200.synth import tile_regions
+    H, W, _ = img.shape
+    roi, non = tile_regions(H, W, tile)
+    stage1 = []
+    for regions, q in ((roi, qualities[0]), (non, qualities[1])):
+        out = []
+        for region in regions:
+            ids = np.unique(region["segments"])
+            jobs = [(img, region, int(s), q) for s in ids[ids != 0]]
+            comps = [c for c in (pool.map(_seg_job, jobs, chunksize=4) if pool else map(_seg_job, jobs)) if c is not None]
+            out.append(O.merge_region_components_simple(comps, tuple(region["bbox"])) if len(comps) > 1 else comps)
+        stage1.append(out)
+    q2 = [min(100, 2 * q) for q in qualities]
+    r = O.region_quantization(stage1[0], H, W, q2[0])
+    n = O.region_quantization(stage1[1], H, W, q2[1])
+    return O.quantize_image(r + n, H, W, min(100, sum(q2)))
+
+
+def cpu_pool():
+    import multiprocessing as mp
+    cores = min(os.cpu_count() or 1, 64)
+    if cores <= 1:
+        return None, 1
+    return mp.get_context("fork").Pool(cores), cores
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the CPU implementation of the same path (the oracle port of the reference's
+    Python modules; the reference itself cannot travel to the GPU box) on all host cores.  One step =
+    one frame of the workload."""
+    if rank != 0:
+        return
+    B, H, W, tile, desc = WORKLOADS[args.workload]
+    from roibasedimagecompression_b200.synth import synth
+    pool, cores = cpu_pool()
+    times = []
+    for s in range(args.warmup + args.steps):
+        img = synth(H, W, 1234 + (s % B))
+        t0 = time.perf_counter()
+        oracle_encode_frame(img, tile, pool)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    if pool:
+        pool.terminate()
+    ms = 1e3 * float(np.mean(times))
+    v = H * W / 1e6 / (ms / 1e3)
+    print(json.dumps({
+        "impl": "reference", "metric": "encode megapixels/sec (DBSCAN+region quantize)", "value": v,
+        "unit": "MPx/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + desc, "step": f"one {W}x{H} frame of the batch per step"},
+        "cpu_baseline": {"value": v, "unit": "MPx/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} frames of {W}x{H} (oracle/rhccq_oracle.py, stage-1 segments over "
+                                   f"{cores} processes)"},
+        "e2e": {"value": v, "unit": "MPx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------- the B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3                                             # timing rule: at least 3 warm-up steps
+
+    import torch
+    import torch.distributed as dist
+    from roibasedimagecompression_b200._lib import lib
+    from roibasedimagecompression_b200 import pipeline
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    be = lib()                                                      # raises without librhccq.so / a B200
+    B, H, W, tile, desc = WORKLOADS[args.workload]
+    imgs_np, labs_np, table = make_inputs(B, H, W, tile, 1234 + rank * B)
+    h_img = torch.from_numpy(imgs_np).pin_memory()
+    h_lab = torch.from_numpy(labs_np).pin_memory()
+    d_img, d_lab = h_img.cuda(non_blocking=True), h_lab.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident steps
+    res = None
+    for _ in range(args.warmup):
+        res = pipeline.encode_batch(be, d_img, d_lab, table)
+    pipeline.finish_checks(res)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier(); torch.cuda.synchronize()
+    be.kernel_timing(True)
+    l0 = be.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = pipeline.encode_batch(be, d_img, d_lab, table)
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    clocks = sampler.stop()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = be.launches - l0
+    ktimes = be.kernel_times_ms()
+    be.kernel_timing(False)
+    pipeline.finish_checks(res)
+    px_rank = B * H * W
+    value = world * px_rank / 1e6 / (ms_step / 1e3)
+
+    kernels = {k: {"launches_per_step": n / args.steps, "ms_per_step": t / args.steps,
+                   "share": (t / args.steps) / ms_step} for k, (n, t) in sorted(ktimes.items(), key=lambda kv: -kv[1][1])}
+    top, (top_n, top_ms) = max(ktimes.items(), key=lambda kv: kv[1][1])
+    peak, peak_src = _peaks()
+    # every launch of the per-segment / per-pixel kernels covers all pixels of the rank's batch
+    achieved = ALGO_BYTES_PER_PIXEL * px_rank / 1e9 / ((top_ms / top_n) / 1e3)
+    roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL * px_rank,
+                "avg_launch_ms": top_ms / top_n, "share_of_step": (top_ms / args.steps) / ms_step,
+                "step_gbs": ALGO_BYTES_PER_PIXEL * px_rank / 1e9 / (ms_step / 1e3)}
+
+    # ---- end to end: host buffers in, host buffers out
+    enc = pipeline.HostEncoder(be, table)
+    for _ in range(2):
+        pals, idx = enc.encode(h_img, h_lab)
+    torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pals, idx = enc.encode(h_img, h_lab)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    barrier()
+    e2e = {"value": world * px_rank / 1e6 / (e2e_ms / 1e3), "unit": "MPx/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": enc.h2d_bytes * world, "d2h_bytes_per_step": (enc.d2h_bytes + sum(p.size for p in pals)) * world,
+           "timing": "host wall clock between device synchronisations, max over ranks"}
+
+    out = {
+        "metric": "encode megapixels/sec (DBSCAN+region quantize)", "value": value, "unit": "MPx/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + desc, "images_per_gpu": B, "global_images": B * world,
+                   "segments_per_gpu": table.P, "sharding": "by image, no data-path collective",
+                   "l2": "inputs larger than L2 (images + label maps per step: %.0f MB)" % (enc.h2d_bytes / 1e6)},
+        "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "kernels": kernels,
+    }
+
+    # ---- CPU baseline + parity of one frame (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        pool, cores = cpu_pool()
+        t0 = time.perf_counter()
+        ref = oracle_encode_frame(imgs_np[0], tile, pool)
+        dt = time.perf_counter() - t0
+        if pool:
+            pool.terminate()
+        same = bool(np.array_equal(pals[0], ref["palette"]) and
+                    np.array_equal(idx[0].reshape(-1).astype(np.int64), ref["indices"]))
+        out["cpu_baseline"] = {"value": H * W / 1e6 / dt, "unit": "MPx/s", "cores": cores, "kind": "port",
+                               "sample": f"frame 0 of the batch ({W}x{H}), oracle/rhccq_oracle.py, stage-1 segments "
+                                         f"over {cores} processes, {dt:.1f} s"}
+        out["parity"] = {"frame0_bit_exact_vs_oracle": same, "palette_colours": int(len(pals[0]))}
+        if not same:
+            raise SystemExit("bench: GPU result of frame 0 differs from the oracle: " + json.dumps(out["parity"]))
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

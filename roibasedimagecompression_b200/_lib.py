@@ -75,6 +75,7 @@ class Backend:
         self._rng = None
         self._rng_lock = threading.Lock()
         self.launches = 0                          # kernels launched through this backend (bench.py reports it)
+        self._events = None                        # [(name, start, end)] while kernel timing is on (bench.py)
 
     # -- plumbing ---------------------------------------------------------
     def stream(self) -> int:
@@ -94,10 +95,30 @@ class Backend:
         return t.data_ptr()
 
     def call(self, name: str, *args, launches: int = 1):
+        ev = None
+        if self._events is not None and self.device.type == "cuda":
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream(self.device))
         rc = getattr(self.cdll, name)(*args)
         if rc != 0:
             raise RhccqError(f"{name}: {self.cdll.rhccq_last_error().decode(errors='replace')}")
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(self.device))
+            self._events.append((name, ev[0], ev[1]))
         self.launches += launches
+
+    def kernel_timing(self, on: bool) -> None:
+        """Bracket every C-ABI launch with CUDA events on the launching stream (bench.py's roofline leg)."""
+        self._events = [] if on else None
+
+    def kernel_times_ms(self) -> dict:
+        """{entry point: (launches, total ms)} of the launches recorded since kernel_timing(True);
+        the caller synchronises first."""
+        out: dict = {}
+        for name, a, b in self._events or []:
+            n, t = out.get(name, (0, 0.0))
+            out[name] = (n + 1, t + a.elapsed_time(b))
+        return out
 
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)

@@ -245,3 +245,41 @@ def encode_batch(be: Backend, images, labels, table: SegmentTable, *, keep_stage
 def finish_checks(res: EncodeResult) -> None:
     """Raise if any stage-2/3 problem was refused (reads the small counters back)."""
     ops.check_counts("final palette", res.palette_cnt)
+
+
+class HostEncoder:
+    """The call a host-side user makes: images and label maps in HOST memory in, final palettes and
+    index planes in HOST memory out (the boundary of encoder/compression/test.py:100-151, where the
+    reference holds numpy arrays and hands `shape` / `palette` / `indices` to the container writer).
+
+    Device and pinned staging buffers are allocated once per table shape; every `encode` call copies
+    the inputs host->device, runs `encode_batch`, and copies the results device->host.
+    """
+
+    def __init__(self, be: Backend, table: SegmentTable):
+        self.be, self.table = be, table
+        B, K, H, W = table.B, table.K, table.H, table.W
+        pin = be.device.type == "cuda"
+        self.d_img = be.empty((B, H, W, 3), torch.uint8)
+        self.d_lab = be.empty((K, B, H, W), torch.int32)
+        self.h_idx = torch.empty((B, H, W), dtype=torch.int16, pin_memory=pin)
+        self.h2d_bytes = self.d_img.numel() + 4 * self.d_lab.numel()
+        self.d2h_bytes = 2 * self.h_idx.numel()
+
+    def encode(self, images_host: torch.Tensor, labels_host: torch.Tensor):
+        """images uint8 [B,H,W,3], labels int32 [K,B,H,W] (pinned host tensors for full copy speed).
+        Returns (palettes: list of uint8 [m,3] arrays, indices: uint16 [B,H,W] array view of pinned memory)."""
+        self.d_img.copy_(images_host, non_blocking=True)
+        self.d_lab.copy_(labels_host, non_blocking=True)
+        res = encode_batch(self.be, self.d_img, self.d_lab, self.table)
+        self.h_idx.copy_(res.indices, non_blocking=True)
+        off = res.palette_off.cpu().numpy()                       # synchronises the stream
+        cnt = res.palette_cnt.cpu().numpy()
+        ops.check_counts("final palette", torch.from_numpy(cnt))
+        n_keys = int(off[len(cnt) - 1] + cnt[-1]) if len(cnt) else 0
+        keys = res.palette_keys[:n_keys].cpu().numpy().astype(np.uint32)
+        pals = []
+        for b in range(len(cnt)):
+            k = keys[off[b]:off[b] + cnt[b]]
+            pals.append(np.stack([(k >> 16) & 255, (k >> 8) & 255, k & 255], axis=-1).astype(np.uint8))
+        return pals, self.h_idx.numpy().view(np.uint16)
