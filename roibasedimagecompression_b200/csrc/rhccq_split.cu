@@ -1,0 +1,837 @@
+// Cluster -> palette-entry assignment: one CTA per palette ("problem").
+//
+//   rhccq_k_palette_split    small clusters -> one entry each, large clusters ->
+//                            recursive K-Means split
+//                            (/root/reference/encoder/compression/clustering.py:253-355, :720-775),
+//                            K-Means in the exact arithmetic of oracle/kmeans_restated.py
+//                            (which cites the scikit-learn lines it restates).
+//
+// Shape of the work.  A stage-1 problem is ~3 000 colours: one top-level
+// K-Means (k = 12..25, ~25 Lloyd iterations) followed by ~10 small K-Means
+// calls (k = 2..4 on 100..400 colours) on the leaves that are still larger than
+// max_colors_per_cluster, recursively.  The recursion of the reference is
+// depth-first, but its RESULT only depends on the tree: a cluster's members sit
+// in one contiguous range of a permutation array, a split partitions the range
+// stably by K-Means label, and the depth-first leaf order is the order of the
+// leaves' ranges.  So the kernel works level by level on a queue of ranges:
+// ranges that are large (or need many centres) are split by the whole CTA one
+// after another, the many small ones by one warp each, concurrently; leaves are
+// flagged at their first position and numbered by one scan at the end.
+//
+// The working set (20 bytes per colour) lives in shared memory when it fits
+// (two CTAs per SM for palettes of up to ~4 000 colours), otherwise in the
+// caller's global workspace.  Nothing here touches HBM beyond reading the
+// palette and writing one int per row: the kernel is bound by FP64 issue
+// (distances are evaluated in IEEE double without contraction, like the oracle)
+// and by barrier latency, not by memory bandwidth.
+#include "rhccq_common.cuh"
+#include "rhccq_kernels.h"
+
+#define RHCCQ_SPLIT_THREADS 256
+#define RHCCQ_KM_MAXT 12               // 2 + int(log(k)) for k < 22027
+#define RHCCQ_KC 128                   // centres of a CTA-level K-Means kept in shared memory
+#define RHCCQ_KW 8                     // centres of a warp-level K-Means
+#define RHCCQ_WARP_RANGE 1024          // largest range a single warp splits
+#define RHCCQ_KPRIV 32                 // k up to which the CTA-level M step uses per-warp histograms
+#define RHCCQ_SPLIT_MAX_WARPS (RHCCQ_SPLIT_THREADS / 32)
+
+// ---------------------------------------------------------------- index types
+// Small: palettes of up to 32 767 rows (every palette the DBSCAN branch can see:
+// the reference switches to MiniBatchKMeans at 10 000 colours).  Bit 15 of a
+// permutation entry flags a leaf start; bit 15 of a label marks a point taken
+// by the empty-cluster relocation.  Cumulative sums of squared distances fit in
+// 32 bits up to 11 008 points (195 075 per point).
+struct rhccq_cfg_small {
+    typedef uint16_t idx_t;
+    typedef uint32_t cum_t;
+    typedef uint32_t q_t;
+    typedef uint32_t key_t;
+    static const uint32_t FLAG = 0x8000u;
+    static const int MAX_ROWS = 11008;
+    __device__ static __forceinline__ q_t q_pack(int lo, int hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
+    __device__ static __forceinline__ int q_lo(q_t v) { return (int)(v & 0xffffu); }
+    __device__ static __forceinline__ int q_hi(q_t v) { return (int)(v >> 16); }
+    __device__ static __forceinline__ key_t key(int label, int j) { return ((uint32_t)label << 16) | (uint32_t)j; }
+    __device__ static __forceinline__ int key_j(key_t v) { return (int)(v & 0xffffu); }
+};
+struct rhccq_cfg_large {
+    typedef uint32_t idx_t;
+    typedef unsigned long long cum_t;
+    typedef unsigned long long q_t;
+    typedef unsigned long long key_t;
+    static const uint32_t FLAG = 0x80000000u;
+    static const int MAX_ROWS = 0x7fffffff;
+    __device__ static __forceinline__ q_t q_pack(int lo, int hi) { return (unsigned long long)(uint32_t)lo | ((unsigned long long)(uint32_t)hi << 32); }
+    __device__ static __forceinline__ int q_lo(q_t v) { return (int)(v & 0xffffffffull); }
+    __device__ static __forceinline__ int q_hi(q_t v) { return (int)(v >> 32); }
+    __device__ static __forceinline__ key_t key(int label, int j) { return ((unsigned long long)(uint32_t)label << 32) | (uint32_t)j; }
+    __device__ static __forceinline__ int key_j(key_t v) { return (int)(v & 0xffffffffull); }
+};
+
+// ---------------------------------------------------------------- thread groups
+// The K-Means below is written once against a "group": the whole CTA or one
+// warp.  Every member of the group must call the collective functions.
+struct rhccq_grp_cta {
+    long long* sll;                    // RHCCQ_MAX_WARPS * RHCCQ_KM_MAXT + 2 elements of shared scratch
+    __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
+    __device__ __forceinline__ int size() const { return (int)blockDim.x; }
+    __device__ __forceinline__ int sub() const { return RHCCQ_WARP; }          // warp of the caller inside the group
+    __device__ __forceinline__ int nsub() const { return RHCCQ_NWARPS; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ int any(int v) const { return rhccq_block_or(v, (int*)sll); }
+    template <class T> __device__ __forceinline__ T excl_scan(T v, T* total) const {
+        return rhccq_block_excl_scan<T>(v, total, reinterpret_cast<T*>(sll));
+    }
+    __device__ __forceinline__ double max_d(double v) const { return rhccq_block_max<double>(v, reinterpret_cast<double*>(sll)); }
+    __device__ __forceinline__ int min_i(int v) const { return rhccq_block_min<int>(v, reinterpret_cast<int*>(sll)); }
+    __device__ __forceinline__ int sum_i(int v) const { return rhccq_block_sum<int>(v, reinterpret_cast<int*>(sll)); }
+    // v[0..cnt) <- sums over the group (integers: the order of additions is immaterial)
+    __device__ __forceinline__ void sum_vec(long long* v, int cnt) const {
+#ifndef RHCCQ_HOST_EMU
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+        __syncthreads();                                          // scratch may still be read by a previous call
+#pragma unroll
+        for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {                   // unrolled: v stays in registers
+            if (t < cnt) {
+                long long x = v[t];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+                if (lane == 0) sll[warp * RHCCQ_KM_MAXT + t] = x;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {
+            if (t < cnt) {
+                long long x = 0;
+                for (int w = 0; w < nwarp; ++w) x += sll[w * RHCCQ_KM_MAXT + t];
+                v[t] = x;
+            }
+        }
+#endif
+    }
+    __device__ __forceinline__ double bcast_d(double v) const {   // value of thread 0
+#ifndef RHCCQ_HOST_EMU
+        double* sd = reinterpret_cast<double*>(sll);
+        __syncthreads();
+        if (threadIdx.x == 0) sd[0] = v;
+        __syncthreads();
+        v = sd[0];
+#endif
+        return v;
+    }
+};
+
+struct rhccq_grp_warp {
+    __device__ __forceinline__ int tid() const { return RHCCQ_LANE; }
+    __device__ __forceinline__ int size() const { return RHCCQ_WARP_SIZE; }
+    __device__ __forceinline__ int sub() const { return 0; }
+    __device__ __forceinline__ int nsub() const { return 1; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+#ifdef RHCCQ_HOST_EMU
+    __device__ __forceinline__ int any(int v) const { return v; }
+    template <class T> __device__ __forceinline__ T excl_scan(T v, T* total) const { *total = v; return (T)0; }
+    __device__ __forceinline__ double max_d(double v) const { return v; }
+    __device__ __forceinline__ int min_i(int v) const { return v; }
+    __device__ __forceinline__ int sum_i(int v) const { return v; }
+    __device__ __forceinline__ void sum_vec(long long*, int) const {}
+    __device__ __forceinline__ double bcast_d(double v) const { return v; }
+#else
+    // every collective doubles as a memory barrier among the lanes (like its CTA counterpart)
+    __device__ __forceinline__ int any(int v) const { __syncwarp(); return __any_sync(0xffffffffu, v); }
+    template <class T> __device__ __forceinline__ T excl_scan(T v, T* total) const {
+        const int lane = threadIdx.x & 31;
+        __syncwarp();
+        T incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            T o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        *total = __shfl_sync(0xffffffffu, incl, 31);
+        return incl - v;
+    }
+    __device__ __forceinline__ double max_d(double v) const {
+        __syncwarp();
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, v, d); v = o > v ? o : v; }
+        return v;
+    }
+    __device__ __forceinline__ int min_i(int v) const {
+        __syncwarp();
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, v, d); v = o < v ? o : v; }
+        return v;
+    }
+    __device__ __forceinline__ int sum_i(int v) const {
+        __syncwarp();
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        return v;
+    }
+    __device__ __forceinline__ void sum_vec(long long* v, int cnt) const {
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {
+            if (t < cnt) {
+                long long x = v[t];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+                v[t] = x;
+            }
+        }
+    }
+    __device__ __forceinline__ double bcast_d(double v) const { __syncwarp(); return __shfl_sync(0xffffffffu, v, 0); }
+#endif
+};
+
+// ---------------------------------------------------------------- K-Means (exact arithmetic)
+__device__ __forceinline__ int rhccq_kmeans_local_trials(int k) {   // 2 + int(log(k)), sklearn/_kmeans.py:226
+    const int e[] = {3, 8, 21, 55, 149, 404, 1097, 2981, 8104, 22027, 59875, 162755, 442414, 1202605};
+    int t = 2;
+    for (int i = 0; i < 14; ++i) if (k >= e[i]) ++t;
+    return t;
+}
+
+// Per-position arrays of a problem (a K-Means call on the range [lo, lo + n) only touches
+// positions of its range, so concurrent calls on disjoint ranges do not interfere) ...
+template <class Cfg> struct rhccq_km_arrays {
+    uint32_t* x;                        // colour at every position
+    uint32_t* closest;                  // seeding: squared distance to the nearest chosen centre
+    typename Cfg::cum_t* cum;           // seeding: inclusive cumulative sum of closest over the range
+    typename Cfg::idx_t* label;         // Lloyd: cluster of every position
+};
+// ... and the per-call centre tables (k entries, private to the calling group).
+struct rhccq_km_centers {
+    double* center;                     // [3k]
+    double* center_new;                 // [3k]
+    double* term;                       // [k]
+    int* sums;                          // [3k]
+    int* cnt;                           // [k]
+    int* hist;                          // [nsub * 4k] per-warp (r, g, b, count) accumulators, or nullptr
+    int* cand;                          // [RHCCQ_KM_MAXT]
+};
+
+__device__ __forceinline__ double rhccq_dist3(double x0, double x1, double x2, const double* c) {
+    const double d0 = __dsub_rn(x0, c[0]), d1 = __dsub_rn(x1, c[1]), d2 = __dsub_rn(x2, c[2]);
+    return __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+}
+
+__device__ __forceinline__ int rhccq_nearest_center(uint32_t c, const double* center, int k) {
+    // first minimum over centres of ((d0^2 + d1^2) + d2^2) in IEEE double
+    const double x0 = (double)rhccq_key_r(c), x1 = (double)rhccq_key_g(c), x2 = (double)rhccq_key_b(c);
+    double best = rhccq_dist3(x0, x1, x2, center);
+    int bi = 0;
+    for (int q = 1; q < k; ++q) {
+        const double d = rhccq_dist3(x0, x1, x2, center + 3 * q);
+        if (d < best) { best = d; bi = q; }
+    }
+    return bi;
+}
+
+// Labels of KMeans(k, random_state=42, n_init='auto').fit_predict on the n colours at positions
+// [lo, lo + n), as restated in oracle/kmeans_restated.py.  On return A.label holds the labels and
+// C.cnt the cluster sizes.  Group-uniform control flow; every thread of the group must call.
+template <class G, class Cfg>
+__device__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<Cfg>& A, const rhccq_km_centers& C, int lo, int n, int k,
+                             const double* __restrict__ rng) {
+    typedef typename Cfg::cum_t cum_t;
+    typedef typename Cfg::idx_t idx_t;
+    const int tid = g.tid(), gsz = g.size();
+    const uint32_t* x = A.x + lo;
+    uint32_t* closest = A.closest + lo;
+    cum_t* cum = A.cum + lo;
+    idx_t* label = A.label + lo;
+    // contiguous chunk of the caller (scans need a fixed element order)
+    const int per = (n + gsz - 1) / gsz;
+    const int c_lo = tid * per < n ? tid * per : n;
+    const int c_hi = c_lo + per < n ? c_lo + per : n;
+
+    // ---- k-means++ seeding (kmeans_restated.kmeans_pp_seeds)
+    const int T = rhccq_kmeans_local_trials(k);
+    int first = (int)__dmul_rn(rng[0], (double)n);
+    if (first > n - 1) first = n - 1;
+    long long acc[RHCCQ_KM_MAXT];
+    cum_t chunk_sum = 0;
+    {
+        const uint32_t cf = x[first];
+        long long p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
+        for (int j = c_lo; j < c_hi; ++j) {
+            const uint32_t c = x[j];
+            const uint32_t d = (uint32_t)rhccq_d2(c, cf);
+            closest[j] = d;
+            chunk_sum += d;
+            const long long r = rhccq_key_r(c), gg = rhccq_key_g(c), b = rhccq_key_b(c);
+            p1[0] += r; p1[1] += gg; p1[2] += b;
+            p2[0] += r * r; p2[1] += gg * gg; p2[2] += b * b;
+        }
+        acc[0] = (long long)chunk_sum;
+        for (int d = 0; d < 3; ++d) { acc[1 + d] = p1[d]; acc[4 + d] = p2[d]; }
+        g.sum_vec(acc, 7);
+        for (int q = tid; q < 3; q += gsz) C.center[q] = (double)((cf >> (16 - 8 * q)) & 255u);
+    }
+    long long pot = acc[0];
+    const long long S1[3] = {acc[1], acc[2], acc[3]}, S2[3] = {acc[4], acc[5], acc[6]};
+    int ri = 1;
+    for (int c = 1; c < k; ++c) {
+        // inclusive cumulative sum of closest (exact integers)
+        cum_t total;
+        cum_t run = g.template excl_scan<cum_t>(chunk_sum, &total);
+        for (int j = c_lo; j < c_hi; ++j) { run += closest[j]; cum[j] = run; }
+        g.sync();
+        // candidates: searchsorted(cum, r * pot, side='left'), clipped
+        for (int t = tid; t < T; t += gsz) {
+            const double rv = __dmul_rn(rng[ri + t], (double)pot);
+            int l = 0, h = n;                                       // first j with cum[j] >= rv
+            while (l < h) {
+                const int mid = (l + h) >> 1;
+                if ((double)cum[mid] < rv) l = mid + 1; else h = mid;
+            }
+            C.cand[t] = l < n - 1 ? l : n - 1;
+        }
+        g.sync();
+        ri += T;
+        uint32_t xc[RHCCQ_KM_MAXT];
+#pragma unroll
+        for (int t = 0; t < RHCCQ_KM_MAXT; ++t) { acc[t] = 0; xc[t] = t < T ? x[C.cand[t]] : 0u; }
+        for (int j = c_lo; j < c_hi; ++j) {
+            const uint32_t cj = x[j], o = closest[j];
+#pragma unroll
+            for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {
+                if (t < T) {
+                    const uint32_t d = (uint32_t)rhccq_d2(cj, xc[t]);
+                    acc[t] += d < o ? d : o;
+                }
+            }
+        }
+        g.sum_vec(acc, T);
+        int best = 0;
+        long long best_pot = acc[0];
+#pragma unroll
+        for (int t = 1; t < RHCCQ_KM_MAXT; ++t) if (t < T && acc[t] < best_pot) { best_pot = acc[t]; best = t; }
+        uint32_t cs = xc[0];
+#pragma unroll
+        for (int t = 1; t < RHCCQ_KM_MAXT; ++t) if (t == best) cs = xc[t];
+        chunk_sum = 0;
+        for (int j = c_lo; j < c_hi; ++j) {
+            const uint32_t d = (uint32_t)rhccq_d2(x[j], cs);
+            const uint32_t o = closest[j];
+            const uint32_t m = d < o ? d : o;
+            closest[j] = m;
+            chunk_sum += m;
+        }
+        for (int q = tid; q < 3; q += gsz) C.center[3 * c + q] = (double)((cs >> (16 - 8 * q)) & 255u);
+        pot = best_pot;
+        // the next pass writes cum / cand only after a collective, which orders it after the reads above
+    }
+
+    // ---- tolerance (kmeans_restated.tolerance)
+    double tol;
+    {
+        const double nn = __dmul_rn((double)n, (double)n);
+        double v[3];
+        for (int d = 0; d < 3; ++d) v[d] = __ddiv_rn((double)((long long)n * S2[d] - S1[d] * S1[d]), nn);
+        tol = __dmul_rn(__ddiv_rn(__dadd_rn(__dadd_rn(v[0], v[1]), v[2]), 3.0), 1e-4);
+    }
+
+    // ---- Lloyd (kmeans_restated.kmeans_labels)
+    const idx_t NOLABEL = (idx_t)(Cfg::FLAG - 1u);                  // never a real label (k < FLAG - 1)
+    for (int j = tid; j < n; j += gsz) label[j] = NOLABEL;
+    int* acc_base = C.hist ? C.hist + (size_t)g.sub() * 4 * k : nullptr;
+    if (C.hist) { for (int q = tid; q < g.nsub() * 4 * k; q += gsz) C.hist[q] = 0; }
+    else { for (int q = tid; q < k; q += gsz) { C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0; } }
+    g.sync();
+    bool strict = false;
+    for (int it = 0; it < 300; ++it) {
+        // E step fused with the accumulation of the M step
+        int changed = 0;
+        for (int j = tid; j < n; j += gsz) {
+            const uint32_t c = x[j];
+            const int bi = rhccq_nearest_center(c, C.center, k);
+            if ((int)label[j] != bi) changed = 1;
+            label[j] = (idx_t)bi;
+            if (acc_base) {
+                int* h = acc_base + 4 * bi;
+                atomicAdd(h, rhccq_key_r(c)); atomicAdd(h + 1, rhccq_key_g(c)); atomicAdd(h + 2, rhccq_key_b(c));
+                atomicAdd(h + 3, 1);
+            } else {
+                atomicAdd(&C.sums[3 * bi], rhccq_key_r(c)); atomicAdd(&C.sums[3 * bi + 1], rhccq_key_g(c));
+                atomicAdd(&C.sums[3 * bi + 2], rhccq_key_b(c)); atomicAdd(&C.cnt[bi], 1);
+            }
+        }
+        changed = g.any(changed);
+        int empty = 0;
+        for (int q = tid; q < k; q += gsz) {
+            if (C.hist) {
+                int s0 = 0, s1 = 0, s2 = 0, cn = 0;
+                for (int w = 0; w < g.nsub(); ++w) {
+                    int* h = C.hist + ((size_t)w * k + q) * 4;
+                    s0 += h[0]; s1 += h[1]; s2 += h[2]; cn += h[3];
+                    h[0] = 0; h[1] = 0; h[2] = 0; h[3] = 0;
+                }
+                C.sums[3 * q] = s0; C.sums[3 * q + 1] = s1; C.sums[3 * q + 2] = s2; C.cnt[q] = cn;
+            }
+            if (C.cnt[q] == 0) ++empty;
+        }
+        const int n_empty = g.sum_i(empty);
+        if (n_empty > 0) {
+            // relocate empty clusters to the points farthest from their centre
+            // (_k_means_common.pyx:177-211): farthest first, ties to the lower index.
+            double mx = 0.0;
+            for (int j = tid; j < n; j += gsz) {
+                const uint32_t c = x[j];
+                const double d = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c), (double)rhccq_key_b(c),
+                                             C.center + 3 * (int)label[j]);
+                if (d > mx) mx = d;
+            }
+            mx = g.max_d(mx);
+            if (mx != 0.0) {
+                // the empty set is fixed before any relocation (a donor cluster may drop to zero later)
+                for (int q = tid; q < k; q += gsz) C.term[q] = C.cnt[q] == 0 ? 1.0 : 0.0;
+                g.sync();
+                int e = 0;
+                for (int done = 0; done < n_empty; ++done) {
+                    while (C.term[e] == 0.0) ++e;                   // next empty cluster, ascending (group-uniform)
+                    double bm = -1.0;
+                    int bj = 0x7fffffff;
+                    for (int j = tid; j < n; j += gsz) {
+                        const uint32_t lj = label[j];
+                        if (lj & Cfg::FLAG) continue;               // already taken
+                        const uint32_t c = x[j];
+                        const double d = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c),
+                                                     (double)rhccq_key_b(c), C.center + 3 * (int)lj);
+                        if (d > bm) { bm = d; bj = j; }             // ascending j: the first maximum stays
+                    }
+                    const double gm = g.max_d(bm);
+                    bj = g.min_i(bm == gm ? bj : 0x7fffffff);
+                    if (tid == 0) {
+                        const int old = (int)label[bj];
+                        const uint32_t c = x[bj];
+                        C.sums[3 * old] -= rhccq_key_r(c); C.sums[3 * old + 1] -= rhccq_key_g(c); C.sums[3 * old + 2] -= rhccq_key_b(c);
+                        C.sums[3 * e] = rhccq_key_r(c); C.sums[3 * e + 1] = rhccq_key_g(c); C.sums[3 * e + 2] = rhccq_key_b(c);
+                        C.cnt[e] = 1;
+                        C.cnt[old] -= 1;
+                        label[bj] = (idx_t)(old | Cfg::FLAG);
+                    }
+                    g.sync();
+                    ++e;
+                }
+                for (int j = tid; j < n; j += gsz) label[j] = (idx_t)(label[j] & ~Cfg::FLAG);
+                g.sync();
+            }
+        }
+        for (int q = tid; q < k; q += gsz) {
+            double c0, c1, c2;
+            if (C.cnt[q] > 0) {
+                const double cn = (double)C.cnt[q];
+                c0 = __ddiv_rn((double)C.sums[3 * q], cn);
+                c1 = __ddiv_rn((double)C.sums[3 * q + 1], cn);
+                c2 = __ddiv_rn((double)C.sums[3 * q + 2], cn);
+            } else {
+                c0 = __ddiv_rn((double)S1[0], (double)n);
+                c1 = __ddiv_rn((double)S1[1], (double)n);
+                c2 = __ddiv_rn((double)S1[2], (double)n);
+            }
+            C.center_new[3 * q] = c0; C.center_new[3 * q + 1] = c1; C.center_new[3 * q + 2] = c2;
+            const double a0 = __dsub_rn(c0, C.center[3 * q]), a1 = __dsub_rn(c1, C.center[3 * q + 1]),
+                         a2 = __dsub_rn(c2, C.center[3 * q + 2]);
+            C.term[q] = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+            if (!C.hist) { C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0; }
+        }
+        g.sync();
+        double shift = 0.0;
+        if (tid == 0) for (int q = 0; q < k; ++q) shift = __dadd_rn(shift, C.term[q]);     // fixed order
+        shift = g.bcast_d(shift);
+        for (int q = tid; q < 3 * k; q += gsz) C.center[q] = C.center_new[q];
+        g.sync();
+        if (!changed) { strict = true; break; }
+        if (shift <= tol) break;
+    }
+    if (!strict) {
+        for (int j = tid; j < n; j += gsz) label[j] = (idx_t)rhccq_nearest_center(x[j], C.center, k);
+    }
+    for (int q = tid; q < k; q += gsz) C.cnt[q] = 0;
+    g.sync();
+    for (int j = tid; j < n; j += gsz) atomicAdd(&C.cnt[(int)label[j]], 1);
+    g.sync();
+}
+
+// Ascending sort of a[0..n) for any n: the bitonic network in its "flip" form, in which every
+// compare-exchange orders (lower index, higher index) ascending; padding the array to a power of two
+// with +infinity would leave the padding in place, so pairs that reach beyond n are skipped.
+template <class G, class T>
+__device__ __forceinline__ void rhccq_group_sort(const G& g, T* a, int n) {
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int t = g.tid(); t < (np2 >> 1); t += g.size()) {      // flip step: i ^ (k - 1)
+            const int blk = t / (k >> 1), off = t % (k >> 1);
+            const int i = blk * k + off, l = blk * k + (k - 1 - off);
+            if (l < n) { const T xa = a[i], xb = a[l]; if (xb < xa) { a[i] = xb; a[l] = xa; } }
+        }
+        g.sync();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int t = g.tid(); t < (np2 >> 1); t += g.size()) {
+                const int i = 2 * t - (t & (j - 1)), l = i + j;
+                if (l < n) { const T xa = a[i], xb = a[l]; if (xb < xa) { a[i] = xb; a[l] = xa; } }
+            }
+            g.sync();
+        }
+    }
+}
+
+// ---------------------------------------------------------------- split driver
+template <class Cfg> struct rhccq_split_ws {
+    rhccq_km_arrays<Cfg> A;
+    typename Cfg::idx_t* perm;          // row of every position; Cfg::FLAG marks the first position of a leaf
+    typename Cfg::q_t* queue;           // ranges still to split, level by level
+};
+
+__device__ __forceinline__ void rhccq_carve_centers(rhccq_km_centers& C, unsigned char* base, size_t kc) {
+    rhccq_carver cv(base);
+    C.center = cv.take<double>(3 * kc);
+    C.center_new = cv.take<double>(3 * kc);
+    C.term = cv.take<double>(kc);
+    C.sums = cv.take<int>(3 * kc);
+    C.cnt = cv.take<int>(kc);
+}
+
+template <class Cfg>
+__host__ __device__ static inline size_t rhccq_split_row_bytes(size_t rows) {
+    typedef typename Cfg::idx_t idx_t;
+    return rhccq_carve_bytes(rows, 4) * 2 + rhccq_carve_bytes(rows, sizeof(typename Cfg::cum_t))
+           + rhccq_carve_bytes(rows, sizeof(idx_t)) * 2 + rhccq_carve_bytes(rows, sizeof(typename Cfg::q_t));
+}
+__host__ __device__ static inline size_t rhccq_split_center_bytes(size_t kc) {
+    return rhccq_carve_bytes(3 * kc, 8) * 2 + rhccq_carve_bytes(kc, 8) + rhccq_carve_bytes(3 * kc, 4)
+           + rhccq_carve_bytes(kc, 4);
+}
+
+size_t rhccq_palette_split_ws_bytes(int max_rows) {
+    // one slice of the global workspace: the per-row arrays and centre tables for k up to max_rows
+    const size_t r = (size_t)(max_rows > 1 ? max_rows : 1);
+    const size_t rows = max_rows <= rhccq_cfg_small::MAX_ROWS ? rhccq_split_row_bytes<rhccq_cfg_small>(r)
+                                                              : rhccq_split_row_bytes<rhccq_cfg_large>(r);
+    // never 0 and never within the shared-memory budget: the caller must always pass a workspace (the
+    // centre tables of a K-Means with more than RHCCQ_KC centres live there)
+    const size_t need = rows + rhccq_split_center_bytes(r);
+    return need > RHCCQ_SMEM_BUDGET ? need : (size_t)RHCCQ_SMEM_BUDGET + 16;
+}
+
+// Split the range [lo, hi) by K-Means and partition it stably by label; children that are still too
+// large are queued, the others are flagged as leaves.  Every thread of the group must call.
+template <class G, class Cfg>
+__device__ void rhccq_split_range(const G& g, const rhccq_split_ws<Cfg>& W, const rhccq_km_centers& C, int lo, int hi,
+                                  int k, int mcpc, const double* __restrict__ rng, int* q_tail, int q_cap, int* err) {
+    typedef typename Cfg::idx_t idx_t;
+    typedef typename Cfg::key_t key_t;
+    const int cnt = hi - lo;
+    rhccq_kmeans<G, Cfg>(g, W.A, C, lo, cnt, k, rng);
+    // stable partition by label: sort (label, position) keys, then move colours and rows
+    key_t* keys = reinterpret_cast<key_t*>(W.A.cum + lo);            // cum is dead after the seeding
+    for (int j = g.tid(); j < cnt; j += g.size()) keys[j] = Cfg::key((int)W.A.label[lo + j], j);
+    g.sync();
+    rhccq_group_sort<G, key_t>(g, keys, cnt);
+    uint32_t* tx = W.A.closest + lo;                                 // dead as well
+    idx_t* tp = W.A.label + lo;                                      // labels are in the keys now
+    for (int j = g.tid(); j < cnt; j += g.size()) {
+        const int src = lo + Cfg::key_j(keys[j]);
+        tx[j] = W.A.x[src];
+        tp[j] = W.perm[src];
+    }
+    g.sync();
+    for (int j = g.tid(); j < cnt; j += g.size()) { W.A.x[lo + j] = tx[j]; W.perm[lo + j] = tp[j]; }
+    // children in label order (clustering.py:755-767): start offsets, then one decision per child
+    for (int q = g.tid(); q < k; q += g.size()) C.sums[q] = C.cnt[q];
+    g.sync();
+    if (g.tid() == 0) {                                              // k is small next to the K-Means above
+        int run = 0;
+        for (int q = 0; q < k; ++q) { const int c = C.sums[q]; C.sums[q] = run; run += c; }
+    }
+    g.sync();
+    for (int q = g.tid(); q < k; q += g.size()) {
+        const int c = C.cnt[q];
+        if (c == 0) continue;                                        // clustering.py:757
+        const int s = lo + C.sums[q];
+        if (c > mcpc && c < cnt && c > 2) {                          // :763-767, :745
+            const int slot = atomicAdd(q_tail, 1);
+            if (slot < q_cap) W.queue[slot] = Cfg::q_pack(s, s + c); else *err = 1;
+        } else {
+            W.perm[s] = (idx_t)(W.perm[s] | Cfg::FLAG);
+        }
+    }
+    g.sync();
+}
+
+template <class Cfg>
+__device__ void rhccq_palette_split_problem(const rhccq_palette_batch& B, int p, const int* __restrict__ labels,
+                                            const int* __restrict__ status_in, const int* __restrict__ max_cpc,
+                                            const double* __restrict__ rng, int rng_len, int* __restrict__ leaf,
+                                            int* __restrict__ n_leaves, int max_rows, unsigned char* row_base,
+                                            unsigned char* small_base, unsigned char* cent_s, int kc_s,
+                                            unsigned char* cent_g, int kc_g) {
+    typedef typename Cfg::idx_t idx_t;
+    typedef typename Cfg::q_t q_t;
+    __shared__ long long s_ll[RHCCQ_MAX_WARPS * RHCCQ_KM_MAXT + 2];
+    __shared__ int s_scan[RHCCQ_MAX_WARPS + 2];
+    __shared__ int s_tail, s_err, s_base;
+    const int n = B.pal_cnt[p];
+    const uint32_t* keys = B.pal_keys + B.pal_off[p];
+    const int* lab = labels + B.pal_off[p];
+    int* lf = leaf + B.pal_off[p];
+    const int mcpc = max_cpc[p];
+    if (n < 0 || (status_in != nullptr && status_in[p] < 0)) {     // upstream error: pass it on
+        if (threadIdx.x == 0) n_leaves[p] = n < 0 ? -2 : status_in[p];
+        return;
+    }
+    if (n > max_rows || n > Cfg::MAX_ROWS) {
+        if (threadIdx.x == 0) n_leaves[p] = -1;
+        return;
+    }
+    rhccq_split_ws<Cfg> W;
+    {
+        rhccq_carver cv(row_base);
+        W.A.x = cv.take<uint32_t>(max_rows);
+        W.A.closest = cv.take<uint32_t>(max_rows);
+        W.A.cum = cv.take<typename Cfg::cum_t>(max_rows);
+        W.A.label = cv.take<idx_t>(max_rows);
+        W.perm = cv.take<idx_t>(max_rows);
+        W.queue = cv.take<q_t>(max_rows);
+    }
+    // CTA-level centre tables: in shared memory for k <= kc_s, else in the global workspace (k <= kc_g)
+    rhccq_km_centers CS, CG;
+    rhccq_carve_centers(CS, cent_s, (size_t)kc_s);
+    rhccq_carve_centers(CG, cent_g, (size_t)kc_g);
+    // small shared tables: per-warp centre sets, per-warp M-step histograms, candidate slots
+    rhccq_carver sv(small_base);
+    int* hist = sv.take<int>((size_t)RHCCQ_SPLIT_MAX_WARPS * 4 * RHCCQ_KPRIV);
+    int* cand = sv.take<int>((size_t)(RHCCQ_SPLIT_MAX_WARPS + 1) * RHCCQ_KM_MAXT);
+    double* wcent = sv.take<double>((size_t)RHCCQ_SPLIT_MAX_WARPS * 7 * RHCCQ_KW);
+    int* wint = sv.take<int>((size_t)RHCCQ_SPLIT_MAX_WARPS * 4 * RHCCQ_KW);
+    CS.cand = CG.cand = cand + RHCCQ_SPLIT_MAX_WARPS * RHCCQ_KM_MAXT;
+
+    // ---- entries that need no K-Means.  csize / crank live in the (still unused) seeding arrays.
+    int* csize = reinterpret_cast<int*>(W.A.x);
+    int* crank = reinterpret_cast<int*>(W.A.closest);
+    // black rows first, one entry each, in row order (clustering.py:253-255)
+    RHCCQ_PAR_FOR(i, n) { crank[i] = (keys[i] == 0u) ? 1 : 0; csize[i] = 0; }
+    __syncthreads();
+    const int n_black = rhccq_block_excl_scan_array<int>(crank, n, s_scan);
+    RHCCQ_PAR_FOR(i, n) if (keys[i] == 0u) lf[i] = crank[i];
+    // cluster sizes; labels are dense non-negative (a noise row would carry -1: one entry each, :258-264)
+    RHCCQ_PAR_FOR(i, n) if (lab[i] >= 0) atomicAdd(&csize[lab[i]], 1);
+    __syncthreads();
+    RHCCQ_PAR_FOR(i, n) crank[i] = (keys[i] != 0u && lab[i] == -1) ? 1 : 0;
+    __syncthreads();
+    const int n_noise = rhccq_block_excl_scan_array<int>(crank, n, s_scan);
+    RHCCQ_PAR_FOR(i, n) if (keys[i] != 0u && lab[i] == -1) lf[i] = n_black + crank[i];
+    __syncthreads();
+    // small clusters in ascending label order (:273-310)
+    RHCCQ_PAR_FOR(l, n) crank[l] = (csize[l] > 0 && csize[l] <= mcpc) ? 1 : 0;
+    __syncthreads();
+    const int n_small = rhccq_block_excl_scan_array<int>(crank, n, s_scan);
+    RHCCQ_PAR_FOR(i, n) {
+        const int l = lab[i];
+        if (l >= 0 && csize[l] <= mcpc) lf[i] = n_black + n_noise + crank[l];
+    }
+    __syncthreads();
+    // large clusters in ascending label order (:315-355): their members, in ascending row order, fill
+    // consecutive ranges of the permutation; crank[l] <- first position of cluster l
+    RHCCQ_PAR_FOR(l, n) crank[l] = csize[l] > mcpc ? csize[l] : 0;
+    __syncthreads();
+    const int n_members = rhccq_block_excl_scan_array<int>(crank, n, s_scan);
+    if (threadIdx.x == 0) { s_tail = 0; s_err = 0; s_base = n_black + n_noise + n_small; }
+    __syncthreads();
+    // roots: a cluster of more than two colours is split (:745), a larger-than-allowed pair stays one entry
+    RHCCQ_PAR_FOR(l, n) {
+        const int c = csize[l];
+        if (c > mcpc) {
+            const int slot = atomicAdd(&s_tail, 1);
+            W.queue[slot] = Cfg::q_pack(crank[l], crank[l] + c);     // at most n / 2 roots: fits
+        }
+    }
+    __syncthreads();
+    const int n_roots = s_tail;
+    if (n_roots > 0) {
+        // rows of the large clusters in (cluster, row) order: rank of a row inside its cluster by a scan per
+        // root (there is rarely more than one root: the eps radii of the reference chain whole palettes)
+        for (int ri = 0; ri < n_roots; ++ri) {
+            const int r_lo = Cfg::q_lo(W.queue[ri]);
+            int L = -1;
+            // the cluster whose range starts at r_lo
+            __shared__ int s_L;
+            RHCCQ_PAR_FOR(l, n) if (csize[l] > mcpc && crank[l] == r_lo) s_L = l;
+            __syncthreads();
+            L = s_L;
+            int* flag = reinterpret_cast<int*>(W.A.cum);             // n ints fit: cum_t is at least 4 bytes
+            RHCCQ_PAR_FOR(i, n) flag[i] = (lab[i] == L) ? 1 : 0;
+            __syncthreads();
+            rhccq_block_excl_scan_array<int>(flag, n, s_scan);
+            RHCCQ_PAR_FOR(i, n) if (lab[i] == L) W.perm[r_lo + flag[i]] = (idx_t)i;
+            __syncthreads();
+        }
+    }
+    // csize / crank are dead from here on: x takes the colours of the permuted rows
+    __syncthreads();
+    {
+        // a root of one or two colours cannot be split (:745): it is a leaf; mark and drop it from the queue
+        __shared__ int s_keep;
+        if (threadIdx.x == 0) {
+            int keep = 0;
+            for (int ri = 0; ri < n_roots; ++ri) {
+                const q_t e = W.queue[ri];
+                if (Cfg::q_hi(e) - Cfg::q_lo(e) <= 2) W.perm[Cfg::q_lo(e)] = (idx_t)(W.perm[Cfg::q_lo(e)] | Cfg::FLAG);
+                else W.queue[keep++] = e;
+            }
+            s_keep = keep;
+            s_tail = keep;
+        }
+        __syncthreads();
+        (void)s_keep;
+    }
+    RHCCQ_PAR_FOR(j, n_members) W.A.x[j] = keys[(int)(W.perm[j] & (idx_t)~Cfg::FLAG)];
+    __syncthreads();
+
+    // ---- level-synchronous splitting
+    rhccq_grp_cta gc; gc.sll = s_ll;
+    rhccq_grp_warp gw;
+    int head = 0;
+    while (true) {
+        __syncthreads();
+        const int tail = s_tail;
+        if (head >= tail || s_err) break;
+        // ranges for the whole CTA
+        for (int e = head; e < tail; ++e) {
+            const q_t qe = W.queue[e];
+            const int lo = Cfg::q_lo(qe), hi = Cfg::q_hi(qe), cnt = hi - lo;
+            int k = (cnt + mcpc - 1) / mcpc;                        // clustering.py:739-742
+            if (k < 2) k = 2;
+            if (k > cnt) k = cnt;
+            if (cnt <= RHCCQ_WARP_RANGE && k <= RHCCQ_KW) continue;  // a warp's job
+            const bool in_smem = k <= kc_s;
+            if (1 + (k - 1) * rhccq_kmeans_local_trials(k) > rng_len || (!in_smem && (cent_g == nullptr || k > kc_g))) {
+                // random table too short, or more centres than the caller's workspace holds: report, do not guess
+                if (threadIdx.x == 0) s_err = (1 + (k - 1) * rhccq_kmeans_local_trials(k) > rng_len) ? 2 : 3;
+                break;
+            }
+            rhccq_km_centers C = in_smem ? CS : CG;
+            C.hist = k <= RHCCQ_KPRIV ? hist : nullptr;
+            rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
+        }
+        __syncthreads();
+        if (s_err) break;
+        // ranges for single warps, concurrently
+        for (int e = head + RHCCQ_WARP; e < tail; e += RHCCQ_NWARPS) {
+            const q_t qe = W.queue[e];
+            const int lo = Cfg::q_lo(qe), hi = Cfg::q_hi(qe), cnt = hi - lo;
+            int k = (cnt + mcpc - 1) / mcpc;
+            if (k < 2) k = 2;
+            if (k > cnt) k = cnt;
+            if (!(cnt <= RHCCQ_WARP_RANGE && k <= RHCCQ_KW)) continue;
+            if (1 + (k - 1) * rhccq_kmeans_local_trials(k) > rng_len) { s_err = 2; continue; }
+            rhccq_km_centers C;
+            double* wc = wcent + (size_t)RHCCQ_WARP * 7 * RHCCQ_KW;
+            int* wi = wint + (size_t)RHCCQ_WARP * 4 * RHCCQ_KW;
+            C.center = wc; C.center_new = wc + 3 * RHCCQ_KW; C.term = wc + 6 * RHCCQ_KW;
+            C.sums = wi; C.cnt = wi + 3 * RHCCQ_KW;
+            C.hist = nullptr;
+            C.cand = cand + RHCCQ_WARP * RHCCQ_KM_MAXT;
+            rhccq_split_range<rhccq_grp_warp, Cfg>(gw, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
+        }
+        head = tail;
+    }
+    __syncthreads();
+    if (s_err) {
+        if (threadIdx.x == 0) n_leaves[p] = s_err == 2 ? -2 : -1;
+        return;
+    }
+    // ---- leaves in range order == depth-first K-Means label order
+    int* lrank = reinterpret_cast<int*>(W.A.closest);
+    RHCCQ_PAR_FOR(j, n_members) lrank[j] = (W.perm[j] & Cfg::FLAG) ? 1 : 0;
+    __syncthreads();
+    const int n_split_leaves = rhccq_block_excl_scan_array<int>(lrank, n_members, s_scan);
+    {
+        // inclusive rank - 1 == leaf number of the position; every thread walks a contiguous chunk
+        const int nt = (int)blockDim.x, t = (int)threadIdx.x;
+        const int per = (n_members + nt - 1) / nt;
+        const int lo = t * per < n_members ? t * per : n_members;
+        const int hi = lo + per < n_members ? lo + per : n_members;
+        const int base = s_base;
+        for (int j = lo; j < hi; ++j) {
+            const uint32_t pe = W.perm[j];
+            const int is_start = (pe & Cfg::FLAG) ? 1 : 0;
+            lf[(int)(pe & ~Cfg::FLAG)] = base + lrank[j] + is_start - 1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) n_leaves[p] = s_base + n_split_leaves;
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(RHCCQ_SPLIT_THREADS, 2)
+rhccq_k_palette_split(rhccq_palette_batch B, const int* __restrict__ labels, const int* __restrict__ status_in,
+                      const int* __restrict__ max_cpc, const double* __restrict__ rng, int rng_len,
+                      int* __restrict__ leaf, int* __restrict__ n_leaves, int max_rows, int rows_in_smem, int kc_s,
+                      unsigned char* gws, size_t gws_stride, size_t small_bytes, size_t row_bytes) {
+    RHCCQ_DYN_SMEM(dyn);
+    // shared memory: [small tables][per-row arrays, if they fit][centre tables for kc_s centres]
+    // global slice:  [per-row arrays][centre tables for max_rows centres]
+    unsigned char* slice = gws ? gws + (size_t)blockIdx.x * gws_stride : nullptr;
+    unsigned char* row_base = rows_in_smem ? dyn + small_bytes : slice;
+    unsigned char* cent_s = dyn + small_bytes + (rows_in_smem ? row_bytes : 0);
+    unsigned char* cent_g = slice ? slice + row_bytes : nullptr;
+    for (int p = blockIdx.x; p < B.n_problems; p += gridDim.x) {
+        rhccq_palette_split_problem<Cfg>(B, p, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves, max_rows,
+                                         row_base, dyn, cent_s, kc_s, cent_g, max_rows);
+        __syncthreads();
+    }
+}
+
+static size_t rhccq_split_small_bytes() {
+    return rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * 4 * RHCCQ_KPRIV, 4)
+           + rhccq_carve_bytes((size_t)(RHCCQ_SPLIT_MAX_WARPS + 1) * RHCCQ_KM_MAXT, 4)
+           + rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * 7 * RHCCQ_KW, 8)
+           + rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * 4 * RHCCQ_KW, 4);
+}
+
+template <class Cfg>
+static int rhccq_launch_split_cfg(const rhccq_palette_batch& B, const int* labels, const int* status_in,
+                                  const int* max_cpc, const double* rng, int rng_len, int* leaf, int* n_leaves,
+                                  int max_rows, rhccq_launch_ws ws, void* stream) {
+    const size_t rows = (size_t)(max_rows > 1 ? max_rows : 1);
+    const size_t small = rhccq_split_small_bytes();
+    const size_t row_bytes = rhccq_split_row_bytes<Cfg>(rows);
+    const size_t kc_s = rows < RHCCQ_KC ? rows : RHCCQ_KC;
+    const size_t cent_s = rhccq_split_center_bytes(kc_s);
+    const size_t slice = rhccq_palette_split_ws_bytes(max_rows);
+    const size_t slices = ws.ws ? ws.ws_bytes / slice : 0;
+    const int rows_in_smem = small + row_bytes + cent_s <= RHCCQ_SMEM_BUDGET;
+    if (!rows_in_smem && slices == 0) {
+        rhccq_set_error("rhccq_palette_split: the per-row working set (%zu bytes) exceeds shared memory and the "
+                        "workspace (%zu bytes) holds no slice of %zu bytes", row_bytes, ws.ws_bytes, slice);
+        return -1;
+    }
+    // one CTA per problem, at most one per workspace slice (a CTA without a slice could not run a K-Means
+    // with more than RHCCQ_KC centres); CTAs walk the problems with a grid stride
+    int grid = B.n_problems;
+    if (slices > 0 && (size_t)grid > slices) grid = (int)slices;
+    if (!rows_in_smem) { const int cap = rhccq_sm_count() * 2; if (grid > cap) grid = cap; }
+    const size_t smem = small + (rows_in_smem ? row_bytes : 0) + cent_s;
+    const void* kern = (const void*)rhccq_k_palette_split<Cfg>;
+    if (rhccq_smem_optin(kern, smem) != 0) return -1;
+    RHCCQ_LAUNCH(rhccq_k_palette_split<Cfg>, grid, RHCCQ_SPLIT_THREADS, smem, (cudaStream_t)stream,
+                 B, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves, max_rows, rows_in_smem, (int)kc_s,
+                 slices > 0 ? ws.ws : nullptr, slice, small, row_bytes);
+    return 0;
+}
+
+int rhccq_launch_palette_split(const rhccq_palette_batch& B, const int* labels, const int* status_in, const int* max_cpc,
+                               const double* rng, int rng_len, int* leaf, int* n_leaves, int max_rows,
+                               rhccq_launch_ws ws, void* stream) {
+    if (B.n_problems <= 0) return 0;
+    if (max_rows <= rhccq_cfg_small::MAX_ROWS)
+        return rhccq_launch_split_cfg<rhccq_cfg_small>(B, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves,
+                                                       max_rows, ws, stream);
+    return rhccq_launch_split_cfg<rhccq_cfg_large>(B, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves,
+                                                   max_rows, ws, stream);
+}

@@ -274,3 +274,38 @@ def test_batch_of_images_equals_per_image(backend):
         want = O.encode_image(imgs[b], roi, non)
         assert np.array_equal(res.palette(b), want["palette"]), b
         assert np.array_equal(res.index_image(b).reshape(-1).astype(np.int64), want["indices"]), b
+
+
+# --------------------------------------------------------------------------- split kernel stress
+def _split_case(rng, kind):
+    if kind == "clumps":            # several well separated clumps: several large clusters at high quality
+        centres = rng.integers(20, 236, size=(int(rng.integers(2, 7)), 3))
+        pts = np.concatenate([c + rng.integers(-9, 10, size=(int(rng.integers(5, 400)), 3)) for c in centres])
+    elif kind == "dups":            # few distinct values per channel: many exact distance ties, empty clusters
+        pts = rng.integers(0, 6, size=(int(rng.integers(30, 600)), 3)) * int(rng.integers(1, 40)) + 1
+    elif kind == "line":
+        t = rng.integers(1, 256, size=int(rng.integers(3, 1500)))
+        pts = np.stack([t, t, np.clip(t + rng.integers(-1, 2, size=t.size), 1, 255)], axis=1)
+    else:
+        pts = rng.integers(1, 256, size=(int(rng.integers(1, 2500)), 3))
+    return np.unique(np.clip(pts, 1, 255).astype(np.uint8), axis=0)
+
+
+@pytest.mark.parametrize("kind", ["clumps", "dups", "line", "uniform"])
+def test_split_kernel_stress_equals_oracle(backend, kind):
+    """Many shapes of palettes through DBSCAN + recursive K-Means split: warp-level and CTA-level splits,
+    several roots, ties, empty-cluster relocation, k from 2 to n."""
+    rng = np.random.default_rng({"clumps": 1, "dups": 2, "line": 3, "uniform": 4}[kind])
+    for trial in range(10):
+        pal = _split_case(rng, kind)
+        n = len(pal)
+        q = float(rng.choice([1, 5, 10, 20, 40, 60, 80, 90, 95, 99, 100]))
+        comp = {"palette": pal, "indices": np.arange(n), "shape": (1, n), "top_left": (0, 0)}
+        eps, _, m = O.compute_clustering_params(n, q)
+        if trial % 3 == 2:
+            m = int(rng.integers(1, max(2, n // 2)))
+        want = O.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m)
+        got = C.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m,
+                                                as_arrays=True)
+        assert np.array_equal(got["palette"], want["palette"]), (kind, trial, n, q, m)
+        assert np.array_equal(got["indices"], want["indices"]), (kind, trial, n, q, m)
