@@ -238,6 +238,9 @@ def main():
     ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     launches = be.launches - l0
     ktimes = be.kernel_times_ms()
+    trace = be.kernel_trace_ms()
+    per_step = len(trace) // args.steps
+    last_step = [(n, round(t, 4)) for n, t in trace[-per_step:]] if per_step else []
     be.kernel_timing(False)
     pipeline.finish_checks(res)
     px_rank = B * H * W
@@ -278,6 +281,7 @@ def main():
                    "segments_per_gpu": table.P, "sharding": "by image, no data-path collective",
                    "l2": "inputs larger than L2 (images + label maps per step: %.0f MB)" % (enc.h2d_bytes / 1e6)},
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "kernels": kernels,
+        "last_step_launches_ms": last_step,
     }
 
     # ---- CPU baseline + parity of one frame (rank 0, N = 1 only)

@@ -120,6 +120,10 @@ class Backend:
             out[name] = (n + 1, t + a.elapsed_time(b))
         return out
 
+    def kernel_trace_ms(self) -> list:
+        """[(entry point, ms)] in launch order."""
+        return [(name, a.elapsed_time(b)) for name, a, b in self._events or []]
+
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 

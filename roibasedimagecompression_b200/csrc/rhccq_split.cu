@@ -210,6 +210,7 @@ struct rhccq_km_centers {
     int* cnt;                           // [k]
     int* hist;                          // [nsub * 4k] per-warp (r, g, b, count) accumulators, or nullptr
     int* cand;                          // [RHCCQ_KM_MAXT]
+    int* poff;                          // [k * nsub] offsets of the counting partition, or nullptr (sort instead)
 };
 
 __device__ __forceinline__ double rhccq_dist3(double x0, double x1, double x2, const double* c) {
@@ -217,23 +218,35 @@ __device__ __forceinline__ double rhccq_dist3(double x0, double x1, double x2, c
     return __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
 }
 
-__device__ __forceinline__ int rhccq_nearest_center(uint32_t c, const double* center, int k) {
-    // first minimum over centres of ((d0^2 + d1^2) + d2^2) in IEEE double
-    const double x0 = (double)rhccq_key_r(c), x1 = (double)rhccq_key_g(c), x2 = (double)rhccq_key_b(c);
-    double best = rhccq_dist3(x0, x1, x2, center);
-    int bi = 0;
-    for (int q = 1; q < k; ++q) {
-        const double d = rhccq_dist3(x0, x1, x2, center + 3 * q);
-        if (d < best) { best = d; bi = q; }
+// First minimum over centres of ((d0^2 + d1^2) + d2^2) in IEEE double, for NB points at once: every
+// centre is loaded once per NB points, and the NB distance chains are independent (the FP64 pipe is
+// the bound of this kernel).
+#define RHCCQ_EB 4
+__device__ __forceinline__ void rhccq_nearest_centers(const uint32_t (&c)[RHCCQ_EB], const double* center, int k,
+                                                      int (&bi)[RHCCQ_EB]) {
+    double x0[RHCCQ_EB], x1[RHCCQ_EB], x2[RHCCQ_EB], best[RHCCQ_EB];
+#pragma unroll
+    for (int u = 0; u < RHCCQ_EB; ++u) {
+        x0[u] = (double)rhccq_key_r(c[u]); x1[u] = (double)rhccq_key_g(c[u]); x2[u] = (double)rhccq_key_b(c[u]);
+        best[u] = rhccq_dist3(x0[u], x1[u], x2[u], center);
+        bi[u] = 0;
     }
-    return bi;
+    for (int q = 1; q < k; ++q) {
+        const double c0 = center[3 * q], c1 = center[3 * q + 1], c2 = center[3 * q + 2];
+#pragma unroll
+        for (int u = 0; u < RHCCQ_EB; ++u) {
+            const double d0 = __dsub_rn(x0[u], c0), d1 = __dsub_rn(x1[u], c1), d2 = __dsub_rn(x2[u], c2);
+            const double d = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+            if (d < best[u]) { best[u] = d; bi[u] = q; }
+        }
+    }
 }
 
 // Labels of KMeans(k, random_state=42, n_init='auto').fit_predict on the n colours at positions
 // [lo, lo + n), as restated in oracle/kmeans_restated.py.  On return A.label holds the labels and
 // C.cnt the cluster sizes.  Group-uniform control flow; every thread of the group must call.
 template <class G, class Cfg>
-__device__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<Cfg>& A, const rhccq_km_centers& C, int lo, int n, int k,
+__device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<Cfg>& A, const rhccq_km_centers& C, int lo, int n, int k,
                              const double* __restrict__ rng) {
     typedef typename Cfg::cum_t cum_t;
     typedef typename Cfg::idx_t idx_t;
@@ -345,18 +358,28 @@ __device__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<Cfg>& A, const rh
     for (int it = 0; it < 300; ++it) {
         // E step fused with the accumulation of the M step
         int changed = 0;
-        for (int j = tid; j < n; j += gsz) {
-            const uint32_t c = x[j];
-            const int bi = rhccq_nearest_center(c, C.center, k);
-            if ((int)label[j] != bi) changed = 1;
-            label[j] = (idx_t)bi;
-            if (acc_base) {
-                int* h = acc_base + 4 * bi;
-                atomicAdd(h, rhccq_key_r(c)); atomicAdd(h + 1, rhccq_key_g(c)); atomicAdd(h + 2, rhccq_key_b(c));
-                atomicAdd(h + 3, 1);
-            } else {
-                atomicAdd(&C.sums[3 * bi], rhccq_key_r(c)); atomicAdd(&C.sums[3 * bi + 1], rhccq_key_g(c));
-                atomicAdd(&C.sums[3 * bi + 2], rhccq_key_b(c)); atomicAdd(&C.cnt[bi], 1);
+        for (int j0 = tid; j0 < n; j0 += RHCCQ_EB * gsz) {
+            uint32_t cb[RHCCQ_EB];
+            int bb[RHCCQ_EB];
+#pragma unroll
+            for (int u = 0; u < RHCCQ_EB; ++u) { const int j = j0 + u * gsz; cb[u] = x[j < n ? j : j0]; }
+            rhccq_nearest_centers(cb, C.center, k, bb);
+#pragma unroll
+            for (int u = 0; u < RHCCQ_EB; ++u) {
+                const int j = j0 + u * gsz;
+                if (j >= n) continue;
+                const uint32_t c = cb[u];
+                const int bi = bb[u];
+                if ((int)label[j] != bi) changed = 1;
+                label[j] = (idx_t)bi;
+                if (acc_base) {
+                    int* h = acc_base + 4 * bi;
+                    atomicAdd(h, rhccq_key_r(c)); atomicAdd(h + 1, rhccq_key_g(c)); atomicAdd(h + 2, rhccq_key_b(c));
+                    atomicAdd(h + 3, 1);
+                } else {
+                    atomicAdd(&C.sums[3 * bi], rhccq_key_r(c)); atomicAdd(&C.sums[3 * bi + 1], rhccq_key_g(c));
+                    atomicAdd(&C.sums[3 * bi + 2], rhccq_key_b(c)); atomicAdd(&C.cnt[bi], 1);
+                }
             }
         }
         changed = g.any(changed);
@@ -448,7 +471,15 @@ __device__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<Cfg>& A, const rh
         if (shift <= tol) break;
     }
     if (!strict) {
-        for (int j = tid; j < n; j += gsz) label[j] = (idx_t)rhccq_nearest_center(x[j], C.center, k);
+        for (int j0 = tid; j0 < n; j0 += RHCCQ_EB * gsz) {
+            uint32_t cb[RHCCQ_EB];
+            int bb[RHCCQ_EB];
+#pragma unroll
+            for (int u = 0; u < RHCCQ_EB; ++u) { const int j = j0 + u * gsz; cb[u] = x[j < n ? j : j0]; }
+            rhccq_nearest_centers(cb, C.center, k, bb);
+#pragma unroll
+            for (int u = 0; u < RHCCQ_EB; ++u) { const int j = j0 + u * gsz; if (j < n) label[j] = (idx_t)bb[u]; }
+        }
     }
     for (int q = tid; q < k; q += gsz) C.cnt[q] = 0;
     g.sync();
@@ -521,34 +552,88 @@ size_t rhccq_palette_split_ws_bytes(int max_rows) {
 // Split the range [lo, hi) by K-Means and partition it stably by label; children that are still too
 // large are queued, the others are flagged as leaves.  Every thread of the group must call.
 template <class G, class Cfg>
-__device__ void rhccq_split_range(const G& g, const rhccq_split_ws<Cfg>& W, const rhccq_km_centers& C, int lo, int hi,
+__device__ __forceinline__ void rhccq_split_range(const G& g, const rhccq_split_ws<Cfg>& W, const rhccq_km_centers& C, int lo, int hi,
                                   int k, int mcpc, const double* __restrict__ rng, int* q_tail, int q_cap, int* err) {
     typedef typename Cfg::idx_t idx_t;
     typedef typename Cfg::key_t key_t;
     const int cnt = hi - lo;
     rhccq_kmeans<G, Cfg>(g, W.A, C, lo, cnt, k, rng);
-    // stable partition by label: sort (label, position) keys, then move colours and rows
-    key_t* keys = reinterpret_cast<key_t*>(W.A.cum + lo);            // cum is dead after the seeding
-    for (int j = g.tid(); j < cnt; j += g.size()) keys[j] = Cfg::key((int)W.A.label[lo + j], j);
-    g.sync();
-    rhccq_group_sort<G, key_t>(g, keys, cnt);
-    uint32_t* tx = W.A.closest + lo;                                 // dead as well
-    idx_t* tp = W.A.label + lo;                                      // labels are in the keys now
-    for (int j = g.tid(); j < cnt; j += g.size()) {
-        const int src = lo + Cfg::key_j(keys[j]);
-        tx[j] = W.A.x[src];
-        tp[j] = W.perm[src];
+    uint32_t* tx = W.A.closest + lo;                                 // dead after the seeding
+    if (C.poff != nullptr) {
+        // stable partition by label, counting form: every warp of the group owns a contiguous segment of the
+        // range; offsets per (label, warp) in label-major order; inside a warp the elements of a tile of 32
+        // consecutive positions are ranked among equal labels with a match, tiles in order
+        const int nsub = g.nsub(), sub = g.sub();
+        const int seg = (cnt + nsub - 1) / nsub;
+        const int s_lo = sub * seg < cnt ? sub * seg : cnt;
+        const int s_hi = s_lo + seg < cnt ? s_lo + seg : cnt;
+        idx_t* tp = reinterpret_cast<idx_t*>(W.A.cum + lo);          // dead as well; labels stay readable
+        for (int q = g.tid(); q < k * nsub; q += g.size()) C.poff[q] = 0;
+        g.sync();
+        for (int j = s_lo + RHCCQ_LANE; j < s_hi; j += RHCCQ_WARP_SIZE)
+            atomicAdd(&C.poff[(int)W.A.label[lo + j] * nsub + sub], 1);
+        g.sync();
+        {   // exclusive scan of poff[0 .. k * nsub)
+            const int N = k * nsub, gsz = g.size(), tid = g.tid();
+            const int per = (N + gsz - 1) / gsz;
+            const int a = tid * per < N ? tid * per : N, b = a + per < N ? a + per : N;
+            int sum = 0;
+            for (int i = a; i < b; ++i) sum += C.poff[i];
+            int total;
+            int base = g.template excl_scan<int>(sum, &total);
+            for (int i = a; i < b; ++i) { const int v = C.poff[i]; C.poff[i] = base; base += v; }
+        }
+        g.sync();
+        for (int q = g.tid(); q < k; q += g.size()) C.sums[q] = C.poff[q * nsub];      // first position of child q
+        g.sync();
+        for (int t0 = s_lo; t0 < s_hi; t0 += RHCCQ_WARP_SIZE) {
+            const int j = t0 + RHCCQ_LANE;
+            const bool valid = j < s_hi;
+            const int L = valid ? (int)W.A.label[lo + j] : -1;
+#ifdef RHCCQ_HOST_EMU
+            const int rank = 0, same = 1;
+            const bool leader = true;
+#else
+            const unsigned m = __match_any_sync(0xffffffffu, L);
+            const int rank = __popc(m & ((1u << (threadIdx.x & 31)) - 1u)), same = __popc(m);
+            const bool leader = rank == same - 1;
+#endif
+            int base = 0;
+            if (valid) base = C.poff[L * nsub + sub];
+            __syncwarp();
+            if (valid) {
+                tx[base + rank] = W.A.x[lo + j];
+                tp[base + rank] = W.perm[lo + j];
+                if (leader) C.poff[L * nsub + sub] = base + same;
+            }
+            __syncwarp();
+        }
+        g.sync();
+        for (int j = g.tid(); j < cnt; j += g.size()) { W.A.x[lo + j] = tx[j]; W.perm[lo + j] = tp[j]; }
+    } else {
+        // many centres: sort (label, position) keys, then move colours and rows
+        key_t* keys = reinterpret_cast<key_t*>(W.A.cum + lo);
+        for (int j = g.tid(); j < cnt; j += g.size()) keys[j] = Cfg::key((int)W.A.label[lo + j], j);
+        g.sync();
+        rhccq_group_sort<G, key_t>(g, keys, cnt);
+        idx_t* tp = W.A.label + lo;                                  // labels are in the keys now
+        for (int j = g.tid(); j < cnt; j += g.size()) {
+            const int src = lo + Cfg::key_j(keys[j]);
+            tx[j] = W.A.x[src];
+            tp[j] = W.perm[src];
+        }
+        g.sync();
+        for (int j = g.tid(); j < cnt; j += g.size()) { W.A.x[lo + j] = tx[j]; W.perm[lo + j] = tp[j]; }
+        // first position of every child
+        for (int q = g.tid(); q < k; q += g.size()) C.sums[q] = C.cnt[q];
+        g.sync();
+        if (g.tid() == 0) {
+            int run = 0;
+            for (int q = 0; q < k; ++q) { const int c = C.sums[q]; C.sums[q] = run; run += c; }
+        }
     }
     g.sync();
-    for (int j = g.tid(); j < cnt; j += g.size()) { W.A.x[lo + j] = tx[j]; W.perm[lo + j] = tp[j]; }
-    // children in label order (clustering.py:755-767): start offsets, then one decision per child
-    for (int q = g.tid(); q < k; q += g.size()) C.sums[q] = C.cnt[q];
-    g.sync();
-    if (g.tid() == 0) {                                              // k is small next to the K-Means above
-        int run = 0;
-        for (int q = 0; q < k; ++q) { const int c = C.sums[q]; C.sums[q] = run; run += c; }
-    }
-    g.sync();
+    // children in label order (clustering.py:755-767): one decision per child
     for (int q = g.tid(); q < k; q += g.size()) {
         const int c = C.cnt[q];
         if (c == 0) continue;                                        // clustering.py:757
@@ -564,7 +649,7 @@ __device__ void rhccq_split_range(const G& g, const rhccq_split_ws<Cfg>& W, cons
 }
 
 template <class Cfg>
-__device__ void rhccq_palette_split_problem(const rhccq_palette_batch& B, int p, const int* __restrict__ labels,
+__device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_batch& B, int p, const int* __restrict__ labels,
                                             const int* __restrict__ status_in, const int* __restrict__ max_cpc,
                                             const double* __restrict__ rng, int rng_len, int* __restrict__ leaf,
                                             int* __restrict__ n_leaves, int max_rows, unsigned char* row_base,
@@ -607,7 +692,8 @@ __device__ void rhccq_palette_split_problem(const rhccq_palette_batch& B, int p,
     int* hist = sv.take<int>((size_t)RHCCQ_SPLIT_MAX_WARPS * 4 * RHCCQ_KPRIV);
     int* cand = sv.take<int>((size_t)(RHCCQ_SPLIT_MAX_WARPS + 1) * RHCCQ_KM_MAXT);
     double* wcent = sv.take<double>((size_t)RHCCQ_SPLIT_MAX_WARPS * 7 * RHCCQ_KW);
-    int* wint = sv.take<int>((size_t)RHCCQ_SPLIT_MAX_WARPS * 4 * RHCCQ_KW);
+    int* wint = sv.take<int>((size_t)RHCCQ_SPLIT_MAX_WARPS * 5 * RHCCQ_KW);
+    int* poff = sv.take<int>((size_t)RHCCQ_SPLIT_MAX_WARPS * RHCCQ_KC);
     CS.cand = CG.cand = cand + RHCCQ_SPLIT_MAX_WARPS * RHCCQ_KM_MAXT;
 
     // ---- entries that need no K-Means.  csize / crank live in the (still unused) seeding arrays.
@@ -714,9 +800,17 @@ __device__ void rhccq_palette_split_problem(const rhccq_palette_batch& B, int p,
                 if (threadIdx.x == 0) s_err = (1 + (k - 1) * rhccq_kmeans_local_trials(k) > rng_len) ? 2 : 3;
                 break;
             }
-            rhccq_km_centers C = in_smem ? CS : CG;
-            C.hist = k <= RHCCQ_KPRIV ? hist : nullptr;
-            rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
+            if (in_smem) {
+                rhccq_km_centers C = CS;
+                C.hist = k <= RHCCQ_KPRIV ? hist : nullptr;
+                C.poff = poff;
+                rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
+            } else {
+                rhccq_km_centers C = CG;
+                C.hist = nullptr;
+                C.poff = nullptr;
+                rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
+            }
         }
         __syncthreads();
         if (s_err) break;
@@ -731,9 +825,9 @@ __device__ void rhccq_palette_split_problem(const rhccq_palette_batch& B, int p,
             if (1 + (k - 1) * rhccq_kmeans_local_trials(k) > rng_len) { s_err = 2; continue; }
             rhccq_km_centers C;
             double* wc = wcent + (size_t)RHCCQ_WARP * 7 * RHCCQ_KW;
-            int* wi = wint + (size_t)RHCCQ_WARP * 4 * RHCCQ_KW;
+            int* wi = wint + (size_t)RHCCQ_WARP * 5 * RHCCQ_KW;
             C.center = wc; C.center_new = wc + 3 * RHCCQ_KW; C.term = wc + 6 * RHCCQ_KW;
-            C.sums = wi; C.cnt = wi + 3 * RHCCQ_KW;
+            C.sums = wi; C.cnt = wi + 3 * RHCCQ_KW; C.poff = wi + 4 * RHCCQ_KW;
             C.hist = nullptr;
             C.cand = cand + RHCCQ_WARP * RHCCQ_KM_MAXT;
             rhccq_split_range<rhccq_grp_warp, Cfg>(gw, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
@@ -767,18 +861,18 @@ __device__ void rhccq_palette_split_problem(const rhccq_palette_batch& B, int p,
     if (threadIdx.x == 0) n_leaves[p] = s_base + n_split_leaves;
 }
 
-template <class Cfg>
+template <class Cfg, bool ROWS_SMEM>
 __global__ void __launch_bounds__(RHCCQ_SPLIT_THREADS, 2)
 rhccq_k_palette_split(rhccq_palette_batch B, const int* __restrict__ labels, const int* __restrict__ status_in,
                       const int* __restrict__ max_cpc, const double* __restrict__ rng, int rng_len,
-                      int* __restrict__ leaf, int* __restrict__ n_leaves, int max_rows, int rows_in_smem, int kc_s,
+                      int* __restrict__ leaf, int* __restrict__ n_leaves, int max_rows, int kc_s,
                       unsigned char* gws, size_t gws_stride, size_t small_bytes, size_t row_bytes) {
     RHCCQ_DYN_SMEM(dyn);
     // shared memory: [small tables][per-row arrays, if they fit][centre tables for kc_s centres]
     // global slice:  [per-row arrays][centre tables for max_rows centres]
     unsigned char* slice = gws ? gws + (size_t)blockIdx.x * gws_stride : nullptr;
-    unsigned char* row_base = rows_in_smem ? dyn + small_bytes : slice;
-    unsigned char* cent_s = dyn + small_bytes + (rows_in_smem ? row_bytes : 0);
+    unsigned char* row_base = ROWS_SMEM ? dyn + small_bytes : slice;    // compile-time: keeps the address space known
+    unsigned char* cent_s = dyn + small_bytes + (ROWS_SMEM ? row_bytes : 0);
     unsigned char* cent_g = slice ? slice + row_bytes : nullptr;
     for (int p = blockIdx.x; p < B.n_problems; p += gridDim.x) {
         rhccq_palette_split_problem<Cfg>(B, p, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves, max_rows,
@@ -791,7 +885,8 @@ static size_t rhccq_split_small_bytes() {
     return rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * 4 * RHCCQ_KPRIV, 4)
            + rhccq_carve_bytes((size_t)(RHCCQ_SPLIT_MAX_WARPS + 1) * RHCCQ_KM_MAXT, 4)
            + rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * 7 * RHCCQ_KW, 8)
-           + rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * 4 * RHCCQ_KW, 4);
+           + rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * 5 * RHCCQ_KW, 4)
+           + rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * RHCCQ_KC, 4);
 }
 
 template <class Cfg>
@@ -817,11 +912,18 @@ static int rhccq_launch_split_cfg(const rhccq_palette_batch& B, const int* label
     if (slices > 0 && (size_t)grid > slices) grid = (int)slices;
     if (!rows_in_smem) { const int cap = rhccq_sm_count() * 2; if (grid > cap) grid = cap; }
     const size_t smem = small + (rows_in_smem ? row_bytes : 0) + cent_s;
-    const void* kern = (const void*)rhccq_k_palette_split<Cfg>;
-    if (rhccq_smem_optin(kern, smem) != 0) return -1;
-    RHCCQ_LAUNCH(rhccq_k_palette_split<Cfg>, grid, RHCCQ_SPLIT_THREADS, smem, (cudaStream_t)stream,
-                 B, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves, max_rows, rows_in_smem, (int)kc_s,
-                 slices > 0 ? ws.ws : nullptr, slice, small, row_bytes);
+    unsigned char* gws = slices > 0 ? ws.ws : nullptr;
+    if (rows_in_smem) {
+        if (rhccq_smem_optin((const void*)rhccq_k_palette_split<Cfg, true>, smem) != 0) return -1;
+        RHCCQ_LAUNCH((rhccq_k_palette_split<Cfg, true>), grid, RHCCQ_SPLIT_THREADS, smem, (cudaStream_t)stream,
+                     B, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves, max_rows, (int)kc_s,
+                     gws, slice, small, row_bytes);
+    } else {
+        if (rhccq_smem_optin((const void*)rhccq_k_palette_split<Cfg, false>, smem) != 0) return -1;
+        RHCCQ_LAUNCH((rhccq_k_palette_split<Cfg, false>), grid, RHCCQ_SPLIT_THREADS, smem, (cudaStream_t)stream,
+                     B, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves, max_rows, (int)kc_s,
+                     gws, slice, small, row_bytes);
+    }
     return 0;
 }
 
