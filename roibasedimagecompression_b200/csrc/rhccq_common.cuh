@@ -63,6 +63,19 @@ static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
     for (int s = 0; s < 32; s += 8) c += ((a >> s) & 255) * ((b >> s) & 255);
     return c;
 }
+#define RHCCQ_EMU_BYTEWISE(name, expr)                                        \
+    static inline unsigned name(unsigned a, unsigned b) {                     \
+        unsigned r = 0;                                                       \
+        for (int s = 0; s < 32; s += 8) {                                     \
+            int x = (a >> s) & 255, y = (b >> s) & 255;                       \
+            r |= ((unsigned)(expr) & 255u) << s;                              \
+        }                                                                     \
+        return r;                                                             \
+    }
+RHCCQ_EMU_BYTEWISE(__vsubus4, x > y ? x - y : 0)
+RHCCQ_EMU_BYTEWISE(__vminu4, x < y ? x : y)
+RHCCQ_EMU_BYTEWISE(__vmaxu4, x > y ? x : y)
+RHCCQ_EMU_BYTEWISE(__vadd4, x + y)
 #define RHCCQ_LAUNCH(kern, grid, block, smem, stream, ...)                          \
     do {                                                                            \
         gridDim.x = (unsigned)(grid); blockDim.x = 1; threadIdx.x = 0;              \
@@ -85,11 +98,20 @@ static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
 #define RHCCQ_WARP 0
 #define RHCCQ_NWARPS 1
 #define RHCCQ_WARP_SIZE 1
+// warp votes / shuffles of a one-lane warp
+static inline unsigned rhccq_ballot(int pred) { return pred ? 1u : 0u; }
+static inline int rhccq_any(int pred) { return pred; }
+template <class T> static inline T rhccq_shfl(T v, int) { return v; }
+template <class T> static inline T rhccq_shfl_xor(T v, int) { return v; }
 #else
 #define RHCCQ_LANE ((int)(threadIdx.x & 31))
 #define RHCCQ_WARP ((int)(threadIdx.x >> 5))
 #define RHCCQ_NWARPS ((int)(blockDim.x >> 5))
 #define RHCCQ_WARP_SIZE 32
+__device__ __forceinline__ unsigned rhccq_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
+__device__ __forceinline__ int rhccq_any(int pred) { return __any_sync(0xffffffffu, pred); }
+template <class T> __device__ __forceinline__ T rhccq_shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <class T> __device__ __forceinline__ T rhccq_shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 #endif
 
 #define RHCCQ_PAR_FOR(i, n) for (int i = (int)threadIdx.x; i < (int)(n); i += (int)blockDim.x)

@@ -54,7 +54,9 @@ __host__ __device__ static inline void rhccq_cellgrid_init(rhccq_cellgrid& g, in
 }
 
 size_t rhccq_palette_dbscan_ws_bytes(int max_rows, int max_slots) {
-    return rhccq_carve_bytes(max_rows, 4) * 3 + rhccq_carve_bytes(max_slots, 4) * 4;
+    // col, slot_of, order per row; hkey, cstart, cend, parent, minidx, box_lo, box_hi per slot; offset table
+    return rhccq_carve_bytes(max_rows, 4) * 3 + rhccq_carve_bytes((size_t)max_slots + 1, 4) * 7
+           + rhccq_carve_bytes(128, 4);
 }
 
 extern "C" int rhccq_palette_dbscan_slots(int thr, int n_rows) {
@@ -100,9 +102,9 @@ __device__ __forceinline__ bool rhccq_tie_accept(uint32_t a, uint32_t b, double 
     return s <= r2;
 }
 
-__device__ __forceinline__ int rhccq_slot_lookup(const rhccq_cellgrid& g, const uint32_t* hkey,
-                                                 const int* head, uint32_t cell) {
-    if (g.direct) return head[cell] >= 0 ? (int)cell : -1;
+__device__ __forceinline__ int rhccq_slot_lookup(const rhccq_cellgrid& g, const uint32_t* hkey, uint32_t cell) {
+    // cell = packed (r, g, b) cell coordinates; returns its slot or -1
+    if (g.direct) return (int)((((cell >> 16) & 255u) * g.G + ((cell >> 8) & 255u)) * g.G + (cell & 255u));
     uint32_t h = (cell * 2654435761u) >> g.hshift;
     while (true) {
         uint32_t k = hkey[h];
@@ -112,6 +114,25 @@ __device__ __forceinline__ int rhccq_slot_lookup(const rhccq_cellgrid& g, const 
     }
 }
 
+// squared distance between a colour and a box / between two boxes (packed bytes, exact)
+__device__ __forceinline__ int rhccq_d2_point_box(uint32_t c, uint32_t lo, uint32_t hi) {
+    const unsigned gap = __vadd4(__vsubus4(lo, c), __vsubus4(c, hi));   // one of the two terms is 0 per channel
+    return (int)__dp4a(gap, gap, 0u);
+}
+__device__ __forceinline__ int rhccq_d2_box_box_min(uint32_t loa, uint32_t hia, uint32_t lob, uint32_t hib) {
+    const unsigned gap = __vadd4(__vsubus4(loa, hib), __vsubus4(lob, hia));
+    return (int)__dp4a(gap, gap, 0u);
+}
+__device__ __forceinline__ int rhccq_d2_box_box_max(uint32_t loa, uint32_t hia, uint32_t lob, uint32_t hib) {
+    const unsigned far = __vmaxu4(__vabsdiffu4(hia, lob), __vabsdiffu4(hib, loa));
+    return (int)__dp4a(far, far, 0u);
+}
+
+// The join phase is organised by cells, one warp per occupied cell: its lanes look up the forward
+// neighbour cells (offsets decoded from a small table, not by division), and every occupied neighbour
+// that is not yet in the same set is tested by the whole warp: bounding boxes first (certainly apart /
+// certainly all within eps), then lanes over the points of one cell against the points of the other,
+// leaving at the first pair within eps.
 __device__ void rhccq_palette_dbscan_problem(const rhccq_palette_batch& B, int p, int* __restrict__ labels,
                                              int* __restrict__ n_clusters, int max_rows, int max_slots,
                                              unsigned char* wsbase) {
@@ -147,26 +168,38 @@ __device__ void rhccq_palette_dbscan_problem(const rhccq_palette_batch& B, int p
     }
     rhccq_carver cv(wsbase);
     uint32_t* col = cv.take<uint32_t>(max_rows);
-    int* next = cv.take<int>(max_rows);                            // cell lists; reused as the label scan
     int* slot_of = cv.take<int>(max_rows);
-    uint32_t* hkey = cv.take<uint32_t>(max_slots);
-    int* head = cv.take<int>(max_slots);
-    int* parent = cv.take<int>(max_slots);
-    int* minidx = cv.take<int>(max_slots);
+    int* order = cv.take<int>(max_rows);                           // rows grouped by cell; later the label scan
+    uint32_t* hkey = cv.take<uint32_t>((size_t)max_slots + 1);
+    int* cstart = cv.take<int>((size_t)max_slots + 1);
+    int* cend = cv.take<int>((size_t)max_slots + 1);
+    int* parent = cv.take<int>((size_t)max_slots + 1);
+    int* minidx = cv.take<int>((size_t)max_slots + 1);
+    uint32_t* box_lo = cv.take<uint32_t>((size_t)max_slots + 1);
+    uint32_t* box_hi = cv.take<uint32_t>((size_t)max_slots + 1);
+    int* offtab = cv.take<int>(128);                               // forward neighbour offsets, 3 signed bytes each
 
-    RHCCQ_PAR_FOR(s, g.hcap) { hkey[s] = RHCCQ_EMPTY_KEY; head[s] = -1; parent[s] = s; minidx[s] = 0x7fffffff; }
+    const int side = 2 * g.reach + 1;                              // reach <= 2: at most 5^3 cells around a cell
+    const int half = (side * side * side - 1) / 2;                 // offsets after the centre in raster order
+    RHCCQ_PAR_FOR(s, g.hcap) { hkey[s] = RHCCQ_EMPTY_KEY; cstart[s] = 0; parent[s] = s; minidx[s] = 0x7fffffff; }
+    RHCCQ_PAR_FOR(o, half) {
+        const int L = half + 1 + o;
+        const int dr = L / (side * side) - g.reach, dg = (L / side) % side - g.reach, db = L % side - g.reach;
+        offtab[o] = ((dr & 255) << 16) | ((dg & 255) << 8) | (db & 255);
+    }
     RHCCQ_PAR_FOR(i, n) col[i] = keys[i];
     __syncthreads();
 
-    // cell lists
+    // cell of every row; black rows take no part (clustering.py:185-192)
     RHCCQ_PAR_FOR(i, n) {
         const uint32_t c = col[i];
-        if (c == 0u) { slot_of[i] = -1; next[i] = -1; continue; }  // black rows take no part (clustering.py:185-192)
-        const uint32_t cell = ((uint32_t)(rhccq_key_r(c) / g.s) * g.G + (uint32_t)(rhccq_key_g(c) / g.s)) * g.G
-                              + (uint32_t)(rhccq_key_b(c) / g.s);
+        if (c == 0u) { slot_of[i] = -1; continue; }
+        const uint32_t cell = ((uint32_t)(rhccq_key_r(c) / g.s) << 16) | ((uint32_t)(rhccq_key_g(c) / g.s) << 8)
+                              | (uint32_t)(rhccq_key_b(c) / g.s);
         int slot;
         if (g.direct) {
-            slot = (int)cell;
+            slot = rhccq_slot_lookup(g, hkey, cell);
+            hkey[slot] = cell;                                     // every writer stores the same value
         } else {
             uint32_t h = (cell * 2654435761u) >> g.hshift;
             while (true) {
@@ -177,50 +210,108 @@ __device__ void rhccq_palette_dbscan_problem(const rhccq_palette_batch& B, int p
             slot = (int)h;
         }
         slot_of[i] = slot;
-        next[i] = atomicExch(&head[slot], i);
+        atomicAdd(&cstart[slot], 1);
+        atomicMin(&minidx[slot], i);
+    }
+    __syncthreads();
+    rhccq_block_excl_scan_array<int>(cstart, g.hcap, s_scratch);
+    RHCCQ_PAR_FOR(s, g.hcap) cend[s] = cstart[s];
+    __syncthreads();
+    RHCCQ_PAR_FOR(i, n) if (slot_of[i] >= 0) order[atomicAdd(&cend[slot_of[i]], 1)] = i;
+    __syncthreads();
+    // bounding box of every occupied cell
+    for (int s = RHCCQ_WARP; s < g.hcap; s += RHCCQ_NWARPS) {
+        const int a0 = cstart[s], a1 = cend[s];
+        if (a1 <= a0) continue;
+        uint32_t lo = 0xffffffffu, hi = 0u;
+        for (int j = a0 + RHCCQ_LANE; j < a1; j += RHCCQ_WARP_SIZE) {
+            const uint32_t c = col[order[j]];
+            lo = __vminu4(lo, c); hi = __vmaxu4(hi, c);
+        }
+        for (int d = RHCCQ_WARP_SIZE >> 1; d > 0; d >>= 1) {
+            lo = __vminu4(lo, rhccq_shfl_xor(lo, d)); hi = __vmaxu4(hi, rhccq_shfl_xor(hi, d));
+        }
+        if (RHCCQ_LANE == 0) { box_lo[s] = lo & 0x00ffffffu; box_hi[s] = hi; }
     }
     __syncthreads();
 
     // join cells
-    const int side = 2 * g.reach + 1;
-    const int half = (side * side * side - 1) / 2;                 // offsets after the centre in raster order
-    const long long work = (long long)n * half;
-    for (long long w = threadIdx.x; w < work; w += blockDim.x) {
-        const int i = (int)(w / half);
-        const int a = slot_of[i];
-        if (a < 0) continue;
-        const int L = half + 1 + (int)(w % half);
-        const int dr = L / (side * side) - g.reach;
-        const int dg = (L / side) % side - g.reach;
-        const int db = L % side - g.reach;
-        const uint32_t c = col[i];
-        const int cr = rhccq_key_r(c) / g.s + dr, cg = rhccq_key_g(c) / g.s + dg, cb = rhccq_key_b(c) / g.s + db;
-        if (cr < 0 || cg < 0 || cb < 0 || cr >= g.G || cg >= g.G || cb >= g.G) continue;
-        const int b = rhccq_slot_lookup(g, hkey, head, ((uint32_t)cr * g.G + (uint32_t)cg) * g.G + (uint32_t)cb);
-        if (b < 0) continue;
-        if (rhccq_uf_find(parent, a) == rhccq_uf_find(parent, b)) continue;
-        for (int j = ((volatile int*)head)[b]; j >= 0; j = next[j]) {
-            const int d2 = rhccq_d2(c, col[j]);
-            bool hit = tie ? (d2 < thr) : (d2 <= thr);
-            if (!hit && tie && d2 == thr) hit = rhccq_tie_accept(c, col[j], eps);
-            if (hit) { rhccq_uf_union(parent, a, b); break; }
+    for (int s = RHCCQ_WARP; s < g.hcap; s += RHCCQ_NWARPS) {
+        const int a0 = cstart[s], a1 = cend[s];
+        if (a1 <= a0) continue;
+        const uint32_t cell = hkey[s];
+        const int cr = (int)((cell >> 16) & 255u), cg = (int)((cell >> 8) & 255u), cb = (int)(cell & 255u);
+        const uint32_t alo = box_lo[s], ahi = box_hi[s];
+        for (int o0 = 0; o0 < half; o0 += RHCCQ_WARP_SIZE) {
+            const int o = o0 + RHCCQ_LANE;
+            int b = -1;
+            if (o < half) {
+                const int e = offtab[o];
+                const int nr = cr + (int)(signed char)(e >> 16), ng = cg + (int)(signed char)(e >> 8),
+                          nb = cb + (int)(signed char)e;
+                if (nr >= 0 && ng >= 0 && nb >= 0 && nr < g.G && ng < g.G && nb < g.G) {
+                    b = rhccq_slot_lookup(g, hkey, ((uint32_t)nr << 16) | ((uint32_t)ng << 8) | (uint32_t)nb);
+                    if (b >= 0 && cend[b] <= cstart[b]) b = -1;
+                }
+            }
+            unsigned found = rhccq_ballot(b >= 0);
+            while (found) {
+                const int src = __ffs((int)found) - 1;
+                found &= found - 1;
+                const int bb = rhccq_shfl(b, src);
+                // other warps move parents concurrently: one lane decides, so that the warp stays converged
+                int same = 0;
+                if (RHCCQ_LANE == 0) same = rhccq_uf_find(parent, s) == rhccq_uf_find(parent, bb);
+                if (rhccq_shfl(same, 0)) continue;
+                const uint32_t blo = box_lo[bb], bhi = box_hi[bb];
+                if (rhccq_d2_box_box_min(alo, ahi, blo, bhi) > thr) continue;        // certainly apart
+                const int far = rhccq_d2_box_box_max(alo, ahi, blo, bhi);
+                bool joined = tie ? far < thr : far <= thr;                           // certainly all within eps
+                if (!joined) {
+                    const int b0 = cstart[bb], b1 = cend[bb];
+                    for (int ja = a0; ja < a1 && !joined; ja += RHCCQ_WARP_SIZE) {
+                        const int j = ja + RHCCQ_LANE;
+                        const uint32_t c = j < a1 ? col[order[j]] : 0u;
+                        const bool live = j < a1 && rhccq_d2_point_box(c, blo, bhi) <= thr;
+                        if (!rhccq_any(live)) continue;
+                        for (int jb = b0; jb < b1; ++jb) {
+                            const uint32_t cj = col[order[jb]];
+                            bool hit = false;
+                            if (live) {
+                                const int d2 = rhccq_d2(c, cj);
+                                hit = tie ? (d2 < thr) : (d2 <= thr);
+                                if (!hit && tie && d2 == thr) hit = rhccq_tie_accept(c, cj, eps);
+                            }
+                            if (rhccq_any(hit)) { joined = true; break; }
+                        }
+                    }
+                }
+                if (joined && RHCCQ_LANE == 0) rhccq_uf_union(parent, s, bb);
+                __syncwarp();
+            }
         }
     }
     __syncthreads();
 
     // canonical numbering: clusters in order of their lowest row (sklearn's DFS seeds ascend)
-    RHCCQ_PAR_FOR(i, n) if (slot_of[i] >= 0) atomicMin(&minidx[rhccq_uf_find(parent, slot_of[i])], i);
+    RHCCQ_PAR_FOR(s, g.hcap) {
+        if (cend[s] > cstart[s]) {
+            const int r = rhccq_uf_find(parent, s);
+            if (r != s) atomicMin(&minidx[r], minidx[s]);          // a concurrently lowered value is a member too
+        }
+    }
+    RHCCQ_PAR_FOR(i, n) order[i] = 0;
     __syncthreads();
-    RHCCQ_PAR_FOR(i, n) next[i] = 0;
+    RHCCQ_PAR_FOR(s, g.hcap) if (cend[s] > cstart[s] && parent[s] == s) order[minidx[s]] = 1;
     __syncthreads();
-    RHCCQ_PAR_FOR(s, g.hcap) if (head[s] >= 0 && parent[s] == s) next[minidx[s]] = 1;
-    __syncthreads();
-    const int total = rhccq_block_excl_scan_array<int>(next, n, s_scratch);
-    RHCCQ_PAR_FOR(i, n) lab[i] = slot_of[i] >= 0 ? next[minidx[rhccq_uf_find(parent, slot_of[i])]] : -2;
+    const int total = rhccq_block_excl_scan_array<int>(order, n, s_scratch);
+    RHCCQ_PAR_FOR(i, n) lab[i] = slot_of[i] >= 0 ? order[minidx[rhccq_uf_find(parent, slot_of[i])]] : -2;
     if (threadIdx.x == 0) n_clusters[p] = total;
 }
 
-__global__ void __launch_bounds__(RHCCQ_PALETTE_THREADS)
+#define RHCCQ_DBSCAN_THREADS 256
+
+__global__ void __launch_bounds__(RHCCQ_DBSCAN_THREADS)
 rhccq_k_palette_dbscan(rhccq_palette_batch B, int* __restrict__ labels, int* __restrict__ n_clusters,
                        int max_rows, int max_slots, unsigned char* gws, size_t gws_stride) {
     RHCCQ_DYN_SMEM(dyn);
@@ -264,7 +355,7 @@ int rhccq_launch_palette_dbscan(const rhccq_palette_batch& B, int* labels, int* 
     const int grid = rhccq_pick_grid((const void*)rhccq_k_palette_dbscan, need, B.n_problems, ws, &smem, &gws,
                                      "rhccq_palette_dbscan");
     if (grid < 0) return -1;
-    RHCCQ_LAUNCH(rhccq_k_palette_dbscan, grid, RHCCQ_PALETTE_THREADS, smem, (cudaStream_t)stream,
+    RHCCQ_LAUNCH(rhccq_k_palette_dbscan, grid, RHCCQ_DBSCAN_THREADS, smem, (cudaStream_t)stream,
                  B, labels, n_clusters, max_rows, max_slots, gws, need);
     return 0;
 }
