@@ -38,7 +38,12 @@ WORKLOADS = {
     "c2": (64, 1080, 1920, 64, "64 x 1920x1080 synthetic images per GPU, 64 px checker tiles, qualities 20/10->40/20->60"),
     "c3": (1, 2160, 3840, 64, "1 x 3840x2160 synthetic image, 64 px checker tiles, qualities 20/10->40/20->60"),
     "c1k": (8, 1080, 1920, 64, "8 x 1920x1080 synthetic images per GPU (short variant of c2)"),
+    # DBSCAN-only (BASELINE.json configs[4]): images per GPU, H, W, unused, description
+    "c5": (1, 4096, 4096, 0, "DBSCAN of 16.8 M 5-D points (x, y, R, G, B) of a 4096x4096 synthetic image"),
+    "c5s": (1, 1024, 1024, 0, "DBSCAN of 1.05 M 5-D points (x, y, R, G, B) of a 1024x1024 synthetic image"),
+    "c5u": (1, 2048, 2048, 0, "DBSCAN of 4.2 M uniform points in [0,256)^5 (3-D cell grid)"),
 }
+DBSCAN_BYTES_PER_POINT = 24       # 20 B read + 4 B written, both for the count kernel and the whole
 
 
 def _peaks():
@@ -170,6 +175,91 @@ def run_reference(args, rank: int):
     }))
 
 
+# --------------------------------------------------------------------------- DBSCAN-only workload (C5)
+def run_dbscan(args, be, rank, world, local, H, W, desc):
+    import torch
+    import torch.distributed as dist
+    from roibasedimagecompression_b200 import dbscan as D
+    from roibasedimagecompression_b200.synth import synth, pixel_features
+    eps, min_pts = args.eps, args.min_pts
+    n = H * W
+    if args.workload == "c5u":
+        pts_np = np.random.default_rng(rank).uniform(0, 256, size=(n, 5)).astype(np.float32)
+        gd = 3
+    else:
+        th, tw = min(H, 2048), min(W, 2048)                         # synth tiles of at most 2048^2 (host memory)
+        img = np.concatenate([np.concatenate([synth(th, tw, 1234 + rank * 64 + (r * 8 + c)) for c in range(W // tw)], axis=1)
+                              for r in range(H // th)], axis=0)
+        pts_np = pixel_features(img)
+        gd = 2
+    h_pts = torch.from_numpy(pts_np).pin_memory()
+    d_pts = h_pts.cuda()
+    lo, hi = D.point_bounds(be, d_pts, gd)
+    plan = D.PointDbscan(be, n, 5, eps, min_pts, lo, hi, gd)
+    for _ in range(args.warmup):
+        labels, core = plan.run(d_pts)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local); sampler.start()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    be.kernel_timing(True); l0 = be.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        labels, core = plan.run(d_pts)
+    e1.record(); torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    kt = be.kernel_times_ms(); launches = be.launches - l0; be.kernel_timing(False)
+    peak, peak_src = _peaks()
+    cnt_n, cnt_ms = kt["rhccq_dbscan_count"]
+    ach = DBSCAN_BYTES_PER_POINT * n / 1e9 / ((cnt_ms / cnt_n) / 1e3)
+    # end to end: host points in, host labels out
+    h_lab = torch.empty(n, dtype=torch.int32).pin_memory()
+    for _ in range(2):
+        d_pts.copy_(h_pts, non_blocking=True); labels, core = plan.run(d_pts); h_lab.copy_(labels, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d_pts.copy_(h_pts, non_blocking=True); labels, core = plan.run(d_pts); h_lab.copy_(labels, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    out = {"metric": "DBSCAN points/sec (bin + count + union-find + border + relabel)", "value": world * n / (ms / 1e3),
+           "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": args.workload + ": " + desc, "eps": eps, "min_pts": min_pts, "grid_dims": gd,
+                      "clusters": int(labels.max().item()) + 1, "core_fraction": float(core.float().mean().item()),
+                      "noise_fraction": float((labels < 0).float().mean().item()),
+                      "l2": "points (%.0f MB) + sorted records larger than L2" % (n * 20 / 1e6)},
+           "clocks": clocks, "gpu_launches": launches,
+           "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": "points/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": n * 20 * world, "d2h_bytes_per_step": n * 4 * world},
+           "roofline": {"kernel": "rhccq_dbscan_count (rhccq_k_pt_sweep<0>)", "bound": "hbm", "achieved": ach, "peak": peak,
+                        "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": DBSCAN_BYTES_PER_POINT * n, "avg_launch_ms": cnt_ms / cnt_n,
+                        "share_of_step": (cnt_ms / args.steps) / ms},
+           "kernels": {k: {"ms_per_step": t / args.steps, "share": (t / args.steps) / ms} for k, (c, t) in kt.items()}}
+    if rank == 0 and world == 1 and not args.no_cpu and n <= 1100000:
+        # CPU baseline: scikit-learn's own DBSCAN (the third-party operator the reference calls), single thread
+        try:
+            from sklearn.cluster import DBSCAN
+            t0 = time.perf_counter(); ref = DBSCAN(eps=eps, min_samples=min_pts).fit(pts_np); dt = time.perf_counter() - t0
+            same = bool(np.array_equal(ref.labels_, h_lab.numpy()))
+            out["cpu_baseline"] = {"value": n / dt, "unit": "points/s", "cores": 1, "kind": "reference",
+                                   "sample": f"sklearn.cluster.DBSCAN on the same {n} points, {dt:.1f} s"}
+            out["parity"] = {"labels_identical_to_sklearn": same}
+            if not same:
+                raise SystemExit("bench: labels differ from scikit-learn: " + json.dumps(out["parity"]))
+        except ImportError:
+            out["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------- the B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -179,6 +269,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--eps", type=float, default=3.0, help="c5 workloads: DBSCAN radius")
+    ap.add_argument("--min-pts", type=int, default=8, help="c5 workloads: DBSCAN min_samples")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,6 +292,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     be = lib()                                                      # raises without librhccq.so / a B200
     B, H, W, tile, desc = WORKLOADS[args.workload]
+    if args.workload.startswith("c5"):
+        return run_dbscan(args, be, rank, world, local, H, W, desc)
     imgs_np, labs_np, table = make_inputs(B, H, W, tile, 1234 + rank * B)
     h_img = torch.from_numpy(imgs_np).pin_memory()
     h_lab = torch.from_numpy(labs_np).pin_memory()

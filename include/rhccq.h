@@ -172,6 +172,42 @@ int rhccq_paint(const int32_t* seg, int B, int H, int W, const int32_t* crops, i
 int rhccq_comp_pass(const int32_t* comps, int n_comps, const int32_t* indices, int Hc, int Wc, int mode,
                     const int32_t* map, uint32_t* fpos, int32_t* prio, int32_t* canvas, void* stream);
 
+/* ------------------------------------------------------------------ a3' at scale: DBSCAN of a point cloud
+ * Replaces sklearn.cluster.DBSCAN(eps, min_samples).fit_predict(X) — the third-party operator the
+ * reference calls at encoder/compression/clustering.py:233-235 (semantics: sklearn/cluster/_dbscan.py:
+ * 397-470, _dbscan_inner.pyx) — for float32 X [n, dims] with dims <= 6, e.g. (x, y, R, G, B) pixel
+ * features, n up to 2^31 / 32.  Labels follow scikit-learn: clusters numbered by their lowest core index,
+ * a non-core point within eps of core points takes the lowest-numbered of their clusters, the rest is -1.
+ * The phases are separate calls (each is one or a few kernels) so that they can be timed one by one:
+ *   plan_make (host) -> [bounds] -> bin -> count -> union -> border -> relabel. */
+typedef struct rhccq_dbscan_plan {
+    int n, dims, grid_dims, min_pts;
+    double eps, side;                 /* cell side: eps * (1 + 2^-20) */
+    double origin[3];
+    int ncell[3];
+    long long n_cells;
+    int cells_per_tile;
+    long long n_tiles;
+} rhccq_dbscan_plan;
+
+/* Host only.  lo / hi: bounds of the first grid_dims coordinates (rhccq_dbscan_bounds computes them). */
+int rhccq_dbscan_plan_make(int n, int dims, int grid_dims, double eps, int min_pts, const double* host_lo,
+                           const double* host_hi, rhccq_dbscan_plan* host_plan);
+size_t rhccq_dbscan_workspace_bytes(const rhccq_dbscan_plan* host_plan);
+/* out6 (device doubles): min of coordinates 0..2, max of coordinates 0..2; ws >= 24 KiB. */
+int rhccq_dbscan_bounds(const float* pts, int n, int dims, int grid_dims, double* out6, void* ws, size_t ws_bytes,
+                        void* stream);
+/* cell of every point, cell histogram, exclusive scan, counting sort into 32-byte records */
+int rhccq_dbscan_bin(const rhccq_dbscan_plan* host_plan, const float* pts, void* ws, size_t ws_bytes, void* stream);
+/* neighbours within eps (self included); core[i] = count >= min_pts (uint8 [n], original order) */
+int rhccq_dbscan_count(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, uint8_t* core, void* stream);
+/* union-find over core pairs within eps; a set's root is its lowest original index */
+int rhccq_dbscan_union(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, uint8_t* core, void* stream);
+/* flatten + border attachment */
+int rhccq_dbscan_border(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, uint8_t* core, void* stream);
+/* labels int32 [n], original order */
+int rhccq_dbscan_relabel(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, int32_t* labels, void* stream);
+
 /* out[i] = sum_{j<i} max(in[j],0), out[n] = total. */
 int rhccq_excl_scan(const int32_t* in, int n, int32_t* out, void* stream);
 

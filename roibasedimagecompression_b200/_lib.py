@@ -48,7 +48,22 @@ SIGNATURES = {
     "rhccq_paint": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _I, _P, _I, _P, _P]),
     "rhccq_comp_pass": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "rhccq_excl_scan": (_I, [_P, _I, _P, _P]),
+    "rhccq_dbscan_plan_make": (_I, [_I, _I, _I, _D, _I, _P, _P, _P]),
+    "rhccq_dbscan_workspace_bytes": (_Z, [_P]),
+    "rhccq_dbscan_bounds": (_I, [_P, _I, _I, _I, _P, _P, _Z, _P]),
+    "rhccq_dbscan_bin": (_I, [_P, _P, _P, _Z, _P]),
+    "rhccq_dbscan_count": (_I, [_P, _P, _Z, _P, _P]),
+    "rhccq_dbscan_union": (_I, [_P, _P, _Z, _P, _P]),
+    "rhccq_dbscan_border": (_I, [_P, _P, _Z, _P, _P]),
+    "rhccq_dbscan_relabel": (_I, [_P, _P, _Z, _P, _P]),
 }
+
+
+class DbscanPlan(ctypes.Structure):
+    """rhccq_dbscan_plan (include/rhccq.h)."""
+    _fields_ = [("n", _I), ("dims", _I), ("grid_dims", _I), ("min_pts", _I), ("eps", _D), ("side", _D),
+                ("origin", _D * 3), ("ncell", _I * 3), ("n_cells", ctypes.c_longlong), ("cells_per_tile", _I),
+                ("n_tiles", ctypes.c_longlong)]
 
 
 class RhccqError(RuntimeError):

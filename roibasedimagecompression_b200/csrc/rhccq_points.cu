@@ -1,0 +1,563 @@
+// DBSCAN of large point clouds (x, y, colour ...) — the operator the reference calls as
+// sklearn.cluster.DBSCAN(eps, min_samples).fit_predict(X)
+// (/root/reference/encoder/compression/clustering.py:233-235; semantics:
+// sklearn/cluster/_dbscan.py:397-470, _dbscan_inner.pyx), for N up to tens of millions of points.
+//
+//   bin      points -> cells of side eps over the first 2 or 3 coordinates; counting sort into 32-byte
+//            records (coordinates, neighbour count, original index), cells in raster order
+//   count    number of points within eps of every point (itself included); core <=> count >= min_samples
+//   union    lock-free union-find over core points that are within eps of each other; a set's root is its
+//            lowest original index, which is also the order sklearn numbers clusters in
+//   border   pointer-jumping flatten; a non-core point takes the lowest-rooted cluster among the core
+//            points within eps (the cluster sklearn's depth-first labelling reaches it from first)
+//   relabel  cluster number = rank of the root among roots
+//
+// count / union / border share one traversal.  A CTA owns a run of consecutive cells of one cell row;
+// the points of those cells and of the neighbouring cells (3^(grid dims) cells around each) are
+// contiguous spans of the sorted record array, one span per neighbouring row, so they are staged into
+// shared memory with TMA bulk copies (cp.async.bulk + mbarrier, double buffered) and every thread
+// walks only the records of the 3 cells around its own point in each row.
+//
+// Distances: scikit-learn's KD-tree evaluates sum_d (x_d - y_d)^2 <= eps^2 in float64 on the float32
+// inputs.  The kernel evaluates the sum in float32 and, when it lands within a relative 2^-18 of eps^2
+// (well above the float32 evaluation error of (dims + 3) * 2^-24), decides in float64 without contraction.
+#include "rhccq_common.cuh"
+#include "rhccq_kernels.h"
+#include "../../include/rhccq.h"
+
+#define RHCCQ_PT_THREADS 256
+#define RHCCQ_PT_CAP 1024                 // records per staging buffer (32 KiB)
+#define RHCCQ_REC_FLOATS 8
+#define RHCCQ_REC_COUNT 6                 // slot of the neighbour count (int bits)
+#define RHCCQ_REC_ID 7                    // slot of the original index (int bits)
+
+struct rhccq_pt_grid {
+    int n, dims, gd, min_pts;
+    int nc0, nc1, nc2;                    // cells per grid dimension (nc2 = 1 for a 2-D grid)
+    int cw;                               // cells per tile along dimension 0
+    int tiles_per_row, rows;
+    double o0, o1, o2, inv_side;
+    float r2f, r2lo, r2hi;
+    double r2;
+};
+
+__host__ __device__ static inline int rhccq_pt_cell(double x, double o, double inv, int nc) {
+    int c = (int)floor((x - o) * inv);
+    return c < 0 ? 0 : (c >= nc ? nc - 1 : c);
+}
+
+// ---------------------------------------------------------------- bounds of the grid coordinates
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_pt_bounds(const float* __restrict__ pts, int n, int dims, int gd, float* __restrict__ partial) {
+    __shared__ float s_f[RHCCQ_MAX_WARPS + 2];
+    float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        for (int d = 0; d < gd; ++d) {
+            const float v = pts[i * dims + d];
+            lo[d] = v < lo[d] ? v : lo[d];
+            hi[d] = v > hi[d] ? v : hi[d];
+        }
+    for (int d = 0; d < 3; ++d) {
+        const float a = rhccq_block_min<float>(lo[d], s_f);
+        const float b = rhccq_block_max<float>(hi[d], s_f);
+        if (threadIdx.x == 0) { partial[blockIdx.x * 6 + d] = a; partial[blockIdx.x * 6 + 3 + d] = b; }
+    }
+}
+__global__ void rhccq_k_pt_bounds_final(const float* __restrict__ partial, int nblocks, double* __restrict__ out) {
+    // one small block: out[0..3) = min, out[3..6) = max
+    RHCCQ_PAR_FOR(d, 6) {
+        float v = partial[d];
+        for (int b = 1; b < nblocks; ++b) {
+            const float w = partial[b * 6 + d];
+            v = d < 3 ? (w < v ? w : v) : (w > v ? w : v);
+        }
+        out[d] = (double)v;
+    }
+}
+
+// ---------------------------------------------------------------- multi-block exclusive scan (int32)
+#define RHCCQ_SCAN_ITEMS 8
+#define RHCCQ_SCAN_TILE (RHCCQ_PT_THREADS * RHCCQ_SCAN_ITEMS)
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_scan_partial(const int* __restrict__ in, long long n, int* __restrict__ block_sums) {
+    __shared__ int s_i[RHCCQ_MAX_WARPS + 2];
+    const long long base = (long long)blockIdx.x * RHCCQ_SCAN_TILE;
+    int s = 0;
+    for (int k = (int)threadIdx.x; k < RHCCQ_SCAN_TILE; k += (int)blockDim.x)
+        if (base + k < n) s += in[base + k];
+    s = rhccq_block_sum<int>(s, s_i);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_scan_apply(const int* __restrict__ in, long long n, const int* __restrict__ block_offsets, int* __restrict__ out) {
+    __shared__ int s_i[RHCCQ_MAX_WARPS + 2];
+    // every thread owns a contiguous chunk of the tile: sum it, scan the sums, then write (reading each
+    // input again just before its slot is written, so out may alias in)
+    const int per = RHCCQ_SCAN_TILE / (int)blockDim.x;
+    const long long base = (long long)blockIdx.x * RHCCQ_SCAN_TILE + (long long)threadIdx.x * per;
+    int s = 0;
+    for (int k = 0; k < per; ++k) if (base + k < n) s += in[base + k];
+    int total;
+    int run = rhccq_block_excl_scan<int>(s, &total, s_i) + block_offsets[blockIdx.x];
+    for (int k = 0; k < per; ++k) if (base + k < n) { const int v = in[base + k]; out[base + k] = run; run += v; }
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_scan_small(int* __restrict__ a, int n, int* __restrict__ total_out) {     // one block, in place
+    __shared__ int s_i[RHCCQ_MAX_WARPS + 2];
+    const int t = rhccq_block_excl_scan_array<int>(a, n, s_i);
+    if (threadIdx.x == 0 && total_out) *total_out = t;
+}
+
+// out[i] = sum_{j<i} in[i] for i < n (out may alias in); scratch: ints for the block sums of every level
+static size_t rhccq_scan_scratch_ints(long long n) {
+    size_t tot = 0;
+    while (n > RHCCQ_SCAN_TILE) { n = (n + RHCCQ_SCAN_TILE - 1) / RHCCQ_SCAN_TILE; tot += (size_t)n + 1; }
+    return tot + 1;
+}
+static int rhccq_scan_i32(const int* in, long long n, int* out, int* scratch, void* stream) {
+    if (n <= 0) return 0;
+    if (n <= RHCCQ_SCAN_TILE) {
+        if (in != out) { rhccq_set_error("rhccq_scan_i32: small scans run in place"); return -1; }
+        RHCCQ_LAUNCH(rhccq_k_scan_small, 1, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, out, (int)n, (int*)nullptr);
+        return 0;
+    }
+    const long long nb = (n + RHCCQ_SCAN_TILE - 1) / RHCCQ_SCAN_TILE;
+    RHCCQ_LAUNCH(rhccq_k_scan_partial, (unsigned)nb, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, in, n, scratch);
+    if (rhccq_scan_i32(scratch, nb, scratch, scratch + nb + 1, stream) != 0) return -1;
+    RHCCQ_LAUNCH(rhccq_k_scan_apply, (unsigned)nb, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, in, n, scratch, out);
+    return 0;
+}
+
+// ---------------------------------------------------------------- bin
+// a record is 32 bytes, 32-byte aligned: two 16-byte accesses
+__device__ __forceinline__ void rhccq_load_rec(const float* r, float* v) {
+#ifdef RHCCQ_HOST_EMU
+    for (int d = 0; d < RHCCQ_REC_FLOATS; ++d) v[d] = r[d];
+#else
+    const float4 u = reinterpret_cast<const float4*>(r)[0], w = reinterpret_cast<const float4*>(r)[1];
+    v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; v[4] = w.x; v[5] = w.y; v[6] = w.z; v[7] = w.w;
+#endif
+}
+__device__ __forceinline__ void rhccq_store_rec(float* r, const float* v) {
+#ifdef RHCCQ_HOST_EMU
+    for (int d = 0; d < RHCCQ_REC_FLOATS; ++d) r[d] = v[d];
+#else
+    reinterpret_cast<float4*>(r)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(r)[1] = make_float4(v[4], v[5], v[6], v[7]);
+#endif
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_pt_cellid(const float* __restrict__ pts, rhccq_pt_grid G, int* __restrict__ cell_id, int* __restrict__ cell_cnt) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < G.n; i += (long long)gridDim.x * blockDim.x) {
+        const float* p = pts + i * G.dims;
+        const int c0 = rhccq_pt_cell((double)p[0], G.o0, G.inv_side, G.nc0);
+        const int c1 = rhccq_pt_cell((double)p[1], G.o1, G.inv_side, G.nc1);
+        const int c2 = G.gd > 2 ? rhccq_pt_cell((double)p[2], G.o2, G.inv_side, G.nc2) : 0;
+        const int key = (c2 * G.nc1 + c1) * G.nc0 + c0;
+        cell_id[i] = key;
+        atomicAdd(&cell_cnt[key], 1);
+    }
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_pt_scatter(const float* __restrict__ pts, rhccq_pt_grid G, const int* __restrict__ cell_id,
+                   const int* __restrict__ cell_start, int* __restrict__ cell_fill, float* __restrict__ rec) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < G.n; i += (long long)gridDim.x * blockDim.x) {
+        const int key = cell_id[i];
+        const int pos = cell_start[key] + atomicAdd(&cell_fill[key], 1);
+        const float* p = pts + i * G.dims;
+        float v[RHCCQ_REC_FLOATS];
+        for (int d = 0; d < RHCCQ_REC_FLOATS; ++d) v[d] = d < G.dims ? p[d] : 0.0f;
+        int id = (int)i;
+        memcpy(&v[RHCCQ_REC_ID], &id, 4);
+        rhccq_store_rec(rec + (size_t)pos * RHCCQ_REC_FLOATS, v);
+    }
+}
+
+// ---------------------------------------------------------------- staging: TMA bulk copy + mbarrier
+#ifndef RHCCQ_HOST_EMU
+__device__ __forceinline__ uint32_t rhccq_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rhccq_mbar_init(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rhccq_smem_addr(bar)));
+}
+__device__ __forceinline__ void rhccq_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rhccq_smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(rhccq_smem_addr(dst)), "l"(src), "r"(bytes), "r"(rhccq_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void rhccq_mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+        ::"r"(rhccq_smem_addr(bar)), "r"(phase) : "memory");
+}
+#endif
+
+// float32 evaluation with a float64 decision near the radius (see the header)
+__device__ __forceinline__ bool rhccq_pt_within(const float* a, const float* b, const rhccq_pt_grid& G) {
+    float s = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) { const float t = a[d] - b[d]; s = fmaf(t, t, s); }     // slots past dims hold 0 in both
+    if (s <= G.r2lo) return true;
+    if (s > G.r2hi) return false;
+    double sd = 0.0;
+    for (int d = 0; d < 6; ++d) {
+        const double t = __dsub_rn((double)a[d], (double)b[d]);
+        sd = __dadd_rn(sd, __dmul_rn(t, t));
+    }
+    return sd <= G.r2;
+}
+
+__device__ __forceinline__ int rhccq_pt_find(int* parent, int x) {
+    while (true) {
+        const int p = ((volatile int*)parent)[x];
+        if (p == x) return x;
+        const int gp = ((volatile int*)parent)[p];
+        if (gp != p) parent[x] = gp;                               // path halving; racing writers only shorten paths
+        x = p;
+    }
+}
+__device__ __forceinline__ int rhccq_pt_find_ro(const int* parent, int x) {     // no path compression: no writes
+    while (true) {
+        const int p = parent[x];
+        if (p == x) return x;
+        x = p;
+    }
+}
+__device__ __forceinline__ void rhccq_pt_union(int* parent, int a, int b) {
+    while (true) {
+        a = rhccq_pt_find(parent, a);
+        b = rhccq_pt_find(parent, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }              // the larger root goes under the smaller
+        if (atomicCAS(&parent[a], a, b) == a) return;
+    }
+}
+
+// MODE 0: count + core flag, 1: union of core pairs, 2: labels of roots (border attachment)
+template <int MODE>
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_pt_sweep(rhccq_pt_grid G, float* __restrict__ rec, const int* __restrict__ cell_start,
+                 uint8_t* __restrict__ core, int* __restrict__ parent, int* __restrict__ rootlab) {
+    RHCCQ_DYN_SMEM(dyn);
+    float* buf0 = reinterpret_cast<float*>(dyn);
+    float* buf1 = buf0 + (size_t)RHCCQ_PT_CAP * RHCCQ_REC_FLOATS;
+#ifndef RHCCQ_HOST_EMU
+    __shared__ __align__(8) uint64_t s_bar[2];
+    if (threadIdx.x == 0) {
+        rhccq_mbar_init(&s_bar[0]); rhccq_mbar_init(&s_bar[1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase[2] = {0u, 0u};
+#endif
+    const int nrows_nb = G.gd > 2 ? 9 : 3;
+    for (int tile = blockIdx.x; tile < G.rows * G.tiles_per_row; tile += gridDim.x) {
+        const int row = tile / G.tiles_per_row, bx = tile % G.tiles_per_row;
+        const int cy = row % G.nc1, cz = row / G.nc1;
+        const int cx0 = bx * G.cw, cx1 = (cx0 + G.cw < G.nc0 ? cx0 + G.cw : G.nc0) - 1;
+        const int rowkey = row * G.nc0;
+        const int t0 = cell_start[rowkey + cx0], t1 = cell_start[rowkey + cx1 + 1];
+        if (t1 <= t0) continue;                                    // no point in the tile (block-uniform)
+        const int sx0 = cx0 > 0 ? cx0 - 1 : 0, sx1 = cx1 + 1 < G.nc0 ? cx1 + 1 : G.nc0 - 1;
+        for (int c0 = t0; c0 < t1; c0 += (int)blockDim.x) {        // centre points, one per thread
+            const int me = c0 + (int)threadIdx.x;
+            const bool have = me < t1;
+            float a[RHCCQ_REC_FLOATS];
+            int my_id = -1, my_cnt = 0, mycx = cx0;
+            bool active = false;
+            if (have) {
+                rhccq_load_rec(rec + (size_t)me * RHCCQ_REC_FLOATS, a);
+                memcpy(&my_id, &a[RHCCQ_REC_ID], 4);
+                memcpy(&my_cnt, &a[RHCCQ_REC_COUNT], 4);
+                mycx = rhccq_pt_cell((double)a[0], G.o0, G.inv_side, G.nc0);
+                active = MODE == 0 ? true : (MODE == 1 ? my_cnt >= G.min_pts : my_cnt < G.min_pts);
+            }
+            int acc = MODE == 2 ? 0x7fffffff : 0;
+            int my_root = my_id;                                   // MODE 1: last known root of my set
+            const int mx0 = mycx > 0 ? mycx - 1 : 0, mx1 = mycx + 1 < G.nc0 ? mycx + 1 : G.nc0 - 1;
+            // stages: (neighbour row, chunk of its span); the next stage is in flight while this one is read
+            int ri = 0, off = 0;                                   // current stage
+            int s_lo = 0, s_hi = 0, s_key = 0;
+            auto row_span = [&](int r, int& lo, int& hi, int& key) -> bool {
+                const int dy = r % 3 - 1, dz = r / 3 - (G.gd > 2 ? 1 : 0);
+                const int ny = cy + dy, nz = cz + dz;
+                if (ny < 0 || ny >= G.nc1 || nz < 0 || nz >= G.nc2) { lo = hi = 0; key = 0; return false; }
+                key = (nz * G.nc1 + ny) * G.nc0;
+                lo = cell_start[key + sx0]; hi = cell_start[key + sx1 + 1];
+                return hi > lo;
+            };
+            auto next_stage = [&](int& r, int& o, int& lo, int& hi, int& key) -> bool {
+                // advance (r, o) to the next non-empty chunk; r == nrows_nb means done
+                while (r < nrows_nb) {
+                    if (o == 0) { if (!row_span(r, lo, hi, key)) { ++r; continue; } }
+                    if (lo + o < hi) return true;
+                    ++r; o = 0;
+                }
+                return false;
+            };
+            int stage = 0;
+            bool more = next_stage(ri, off, s_lo, s_hi, s_key);
+#ifndef RHCCQ_HOST_EMU
+            if (more && threadIdx.x == 0) {
+                const int cnt = s_hi - (s_lo + off) < RHCCQ_PT_CAP ? s_hi - (s_lo + off) : RHCCQ_PT_CAP;
+                rhccq_bulk_load(buf0, rec + (size_t)(s_lo + off) * RHCCQ_REC_FLOATS, (uint32_t)cnt * 32u, &s_bar[0]);
+            }
+#endif
+            while (more) {
+                const int cur_lo = s_lo + off;
+                const int cur_n = s_hi - cur_lo < RHCCQ_PT_CAP ? s_hi - cur_lo : RHCCQ_PT_CAP;
+                const int cur_key = s_key;
+                float* cur = (stage & 1) ? buf1 : buf0;
+                // look ahead
+                int nri = ri, noff = off + cur_n, nlo = s_lo, nhi = s_hi, nkey = s_key;
+                const bool nmore = next_stage(nri, noff, nlo, nhi, nkey);
+#ifdef RHCCQ_HOST_EMU
+                memcpy(cur, rec + (size_t)cur_lo * RHCCQ_REC_FLOATS, (size_t)cur_n * 32);
+#else
+                if (nmore && threadIdx.x == 0) {
+                    const int cnt = nhi - (nlo + noff) < RHCCQ_PT_CAP ? nhi - (nlo + noff) : RHCCQ_PT_CAP;
+                    rhccq_bulk_load((stage & 1) ? buf0 : buf1, rec + (size_t)(nlo + noff) * RHCCQ_REC_FLOATS,
+                                    (uint32_t)cnt * 32u, &s_bar[(stage + 1) & 1]);
+                }
+                rhccq_mbar_wait(&s_bar[stage & 1], phase[stage & 1]);
+                phase[stage & 1] ^= 1u;
+#endif
+                if (active) {
+                    // records of the 3 cells around my cell in this row, clipped to the staged chunk
+                    int lo = cell_start[cur_key + mx0], hi = cell_start[cur_key + mx1 + 1];
+                    lo = lo > cur_lo ? lo : cur_lo;
+                    hi = hi < cur_lo + cur_n ? hi : cur_lo + cur_n;
+                    for (int j = lo; j < hi; ++j) {
+                        float b[RHCCQ_REC_FLOATS];
+                        rhccq_load_rec(cur + (size_t)(j - cur_lo) * RHCCQ_REC_FLOATS, b);
+                        if (MODE != 0) {
+                            int bc; memcpy(&bc, &b[RHCCQ_REC_COUNT], 4);
+                            if (bc < G.min_pts) continue;          // only core candidates matter
+                        }
+                        if (!rhccq_pt_within(a, b, G)) continue;
+                        if (MODE == 0) ++acc;
+                        else {
+                            int bid; memcpy(&bid, &b[RHCCQ_REC_ID], 4);
+                            if (MODE == 1) {
+                                // one hop is enough to see that a neighbour already hangs under my root (the
+                                // common case once a dense region is linked); only otherwise walk and link
+                                if (bid < my_id && ((volatile int*)parent)[bid] != my_root) {
+                                    rhccq_pt_union(parent, my_id, bid);
+                                    my_root = rhccq_pt_find(parent, my_id);
+                                }
+                            } else { const int r = rootlab[bid]; acc = r < acc ? r : acc; }
+                        }
+                    }
+                }
+                __syncthreads();                                   // everyone is done with `cur` before it is refilled
+                ri = nri; off = noff; s_lo = nlo; s_hi = nhi; s_key = nkey; more = nmore;
+                ++stage;
+            }
+            if (have) {
+                if (MODE == 0) {
+                    memcpy(&rec[(size_t)me * RHCCQ_REC_FLOATS + RHCCQ_REC_COUNT], &acc, 4);
+                    core[my_id] = acc >= G.min_pts ? 1 : 0;
+                } else if (MODE == 2) {
+                    // core points keep the root the flatten pass stored; others take the lowest adjacent root
+                    if (my_cnt < G.min_pts) rootlab[my_id] = acc == 0x7fffffff ? -1 : acc;
+                }
+            }
+            __syncthreads();                                       // (barrier parities are tracked per buffer)
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_pt_init_parent(int n, int* __restrict__ parent) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        parent[i] = (int)i;
+}
+// Root of every core point into rootlab (read-only walk: a compressing walk could overwrite a finished
+// entry with a stale ancestor), -1 for the others; is_root marks the roots.
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_pt_flatten(int n, const int* __restrict__ parent, const uint8_t* __restrict__ core, int* __restrict__ rootlab,
+                   int* __restrict__ is_root) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = core[i] ? rhccq_pt_find_ro(parent, (int)i) : -1;
+        rootlab[i] = r;
+        is_root[i] = r == (int)i ? 1 : 0;
+    }
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_pt_labels(int n, const int* __restrict__ rootlab, const int* __restrict__ root_rank, int* __restrict__ labels) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = rootlab[i];
+        labels[i] = r < 0 ? -1 : root_rank[r];
+    }
+}
+
+// ---------------------------------------------------------------- host side
+struct rhccq_pt_ws {
+    float* rec; int* cell_id; int* cell_start; int* cell_fill; int* parent; int* rootlab; int* is_root; int* scan;
+    float* partial;
+};
+static size_t rhccq_al(size_t b) { return (b + 255) & ~(size_t)255; }
+static size_t rhccq_pt_carve(const rhccq_dbscan_plan* P, unsigned char* base, rhccq_pt_ws* W) {
+    size_t o = 0;
+    const size_t n = (size_t)P->n, m = (size_t)P->n_cells + 2;
+    auto take = [&](size_t bytes) { unsigned char* p = base ? base + o : nullptr; o += rhccq_al(bytes); return p; };
+    float* rec = (float*)take(n * 32);
+    int* cell_id = (int*)take(n * 4);
+    int* cell_start = (int*)take(m * 4);
+    int* cell_fill = (int*)take(m * 4);
+    int* parent = (int*)take(n * 4);
+    int* rootlab = (int*)take(n * 4);
+    int* is_root = (int*)take(n * 4);
+    const size_t big = m > n ? m : n;
+    int* scan = (int*)take(rhccq_scan_scratch_ints((long long)big) * 4 + 64);
+    float* partial = (float*)take(1024 * 6 * 4);
+    if (W) { W->rec = rec; W->cell_id = cell_id; W->cell_start = cell_start; W->cell_fill = cell_fill; W->parent = parent;
+             W->rootlab = rootlab; W->is_root = is_root; W->scan = scan; W->partial = partial; }
+    return o;
+}
+
+static rhccq_pt_grid rhccq_pt_make_grid(const rhccq_dbscan_plan* P) {
+    rhccq_pt_grid G;
+    G.n = P->n; G.dims = P->dims; G.gd = P->grid_dims; G.min_pts = P->min_pts;
+    G.nc0 = P->ncell[0]; G.nc1 = P->ncell[1]; G.nc2 = P->grid_dims > 2 ? P->ncell[2] : 1;
+    G.cw = P->cells_per_tile; G.tiles_per_row = (G.nc0 + G.cw - 1) / G.cw; G.rows = G.nc1 * G.nc2;
+    G.o0 = P->origin[0]; G.o1 = P->origin[1]; G.o2 = P->origin[2]; G.inv_side = 1.0 / P->side;
+    G.r2 = P->eps * P->eps;
+    G.r2f = (float)G.r2;
+    G.r2lo = (float)(G.r2 * (1.0 - 1.0 / 262144.0));
+    G.r2hi = (float)(G.r2 * (1.0 + 1.0 / 262144.0));
+    return G;
+}
+
+static int rhccq_pt_blocks(long long n) {
+    long long b = (n + RHCCQ_PT_THREADS - 1) / RHCCQ_PT_THREADS;
+    const long long cap = (long long)rhccq_sm_count() * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" {
+
+int rhccq_dbscan_plan_make(int n, int dims, int grid_dims, double eps, int min_pts, const double* lo,
+                           const double* hi, rhccq_dbscan_plan* P) {
+    if (!P || !lo || !hi || n < 0 || dims < 2 || dims > 6 || grid_dims < 2 || grid_dims > 3 || grid_dims > dims ||
+        !(eps > 0.0) || min_pts < 1) {
+        rhccq_set_error("rhccq_dbscan_plan_make: need n >= 0, 2 <= dims <= 6, grid_dims 2 or 3 (<= dims), eps > 0, "
+                        "min_pts >= 1");
+        return -1;
+    }
+    memset(P, 0, sizeof *P);
+    P->n = n; P->dims = dims; P->grid_dims = grid_dims; P->min_pts = min_pts; P->eps = eps;
+    // cells a hair wider than eps: two points within eps are then at most one cell apart even after the
+    // rounding of the cell computation (done in float64)
+    P->side = eps * (1.0 + 1.0 / 1048576.0);
+    long long cells = 1;
+    for (int d = 0; d < 3; ++d) {
+        P->origin[d] = d < grid_dims ? lo[d] : 0.0;
+        long long nc = 1;
+        if (d < grid_dims) {
+            const double span = hi[d] - lo[d];
+            if (!(span >= 0.0)) { rhccq_set_error("rhccq_dbscan_plan_make: empty or NaN bounds in dimension %d", d); return -1; }
+            nc = (long long)floor(span / P->side) + 1;
+        }
+        if (nc > 2000000000LL) { rhccq_set_error("rhccq_dbscan_plan_make: too many cells in dimension %d", d); return -1; }
+        P->ncell[d] = (int)nc;
+        cells *= nc;
+        if (cells > 1500000000LL) {
+            rhccq_set_error("rhccq_dbscan_plan_make: %lld cells exceed the int32 cell index; use a larger eps or fewer grid dims", cells);
+            return -1;
+        }
+    }
+    P->n_cells = cells;
+    const double ppc = cells > 0 ? (double)n / (double)cells : 1.0;
+    long long cw = (long long)(RHCCQ_PT_THREADS / (ppc > 0.0625 ? ppc : 0.0625));
+    if (cw < 1) cw = 1;
+    if (cw > P->ncell[0]) cw = P->ncell[0];
+    P->cells_per_tile = (int)cw;
+    P->n_tiles = (long long)((P->ncell[0] + cw - 1) / cw) * P->ncell[1] * (grid_dims > 2 ? P->ncell[2] : 1);
+    return 0;
+}
+
+size_t rhccq_dbscan_workspace_bytes(const rhccq_dbscan_plan* P) {
+    return P ? rhccq_pt_carve(P, nullptr, nullptr) : 0;
+}
+
+int rhccq_dbscan_bounds(const float* pts, int n, int dims, int grid_dims, double* out6, void* ws, size_t ws_bytes,
+                        void* stream) {
+    if (n <= 0 || !pts || !out6 || !ws || ws_bytes < 1024 * 6 * 4) { rhccq_set_error("rhccq_dbscan_bounds: bad arguments"); return -1; }
+    int nb = rhccq_pt_blocks(n);
+    if (nb > 1024) nb = 1024;
+    RHCCQ_LAUNCH(rhccq_k_pt_bounds, nb, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, pts, n, dims, grid_dims, (float*)ws);
+    RHCCQ_LAUNCH(rhccq_k_pt_bounds_final, 1, 32, 0, (cudaStream_t)stream, (const float*)ws, nb, out6);
+    return 0;
+}
+
+#define RHCCQ_PT_ARGS(name)                                                                        \
+    if (!P || !ws || ws_bytes < rhccq_pt_carve(P, nullptr, nullptr)) {                             \
+        rhccq_set_error(name ": plan or workspace missing / too small"); return -1; }              \
+    rhccq_pt_ws W; rhccq_pt_carve(P, (unsigned char*)ws, &W);                                      \
+    const rhccq_pt_grid G = rhccq_pt_make_grid(P);                                                 \
+    if (P->n == 0) return 0;
+
+int rhccq_dbscan_bin(const rhccq_dbscan_plan* P, const float* pts, void* ws, size_t ws_bytes, void* stream) {
+    RHCCQ_PT_ARGS("rhccq_dbscan_bin")
+    const long long m = P->n_cells + 1;
+#ifdef RHCCQ_HOST_EMU
+    memset(W.cell_start, 0, (size_t)(m + 1) * 4); memset(W.cell_fill, 0, (size_t)(m + 1) * 4);
+#else
+    cudaMemsetAsync(W.cell_start, 0, (size_t)(m + 1) * 4, (cudaStream_t)stream);
+    cudaMemsetAsync(W.cell_fill, 0, (size_t)(m + 1) * 4, (cudaStream_t)stream);
+#endif
+    RHCCQ_LAUNCH(rhccq_k_pt_cellid, rhccq_pt_blocks(P->n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, pts, G, W.cell_id, W.cell_start);
+    if (m <= RHCCQ_SCAN_TILE) {
+        RHCCQ_LAUNCH(rhccq_k_scan_small, 1, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, W.cell_start, (int)m, (int*)nullptr);
+    } else if (rhccq_scan_i32(W.cell_start, m, W.cell_start, W.scan, stream) != 0) return -1;
+    RHCCQ_LAUNCH(rhccq_k_pt_scatter, rhccq_pt_blocks(P->n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, pts, G, W.cell_id,
+                 W.cell_start, W.cell_fill, W.rec);
+    return 0;
+}
+
+static int rhccq_pt_sweep_launch(int mode, const rhccq_pt_grid& G, const rhccq_dbscan_plan* P, rhccq_pt_ws& W, uint8_t* core,
+                                 void* stream) {
+    const size_t smem = (size_t)2 * RHCCQ_PT_CAP * 32;
+    long long tiles = P->n_tiles;
+    const long long cap = (long long)rhccq_sm_count() * 3 * 8;      // 3 resident CTAs per SM, several waves
+    const int grid = (int)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
+    if (mode == 0) {
+        if (rhccq_smem_optin((const void*)rhccq_k_pt_sweep<0>, smem) != 0) return -1;
+        RHCCQ_LAUNCH(rhccq_k_pt_sweep<0>, grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, G, W.rec, W.cell_start, core, W.parent, W.rootlab);
+    } else if (mode == 1) {
+        if (rhccq_smem_optin((const void*)rhccq_k_pt_sweep<1>, smem) != 0) return -1;
+        RHCCQ_LAUNCH(rhccq_k_pt_sweep<1>, grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, G, W.rec, W.cell_start, core, W.parent, W.rootlab);
+    } else {
+        if (rhccq_smem_optin((const void*)rhccq_k_pt_sweep<2>, smem) != 0) return -1;
+        RHCCQ_LAUNCH(rhccq_k_pt_sweep<2>, grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, G, W.rec, W.cell_start, core, W.parent, W.rootlab);
+    }
+    return 0;
+}
+
+int rhccq_dbscan_count(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, uint8_t* core, void* stream) {
+    RHCCQ_PT_ARGS("rhccq_dbscan_count")
+    return rhccq_pt_sweep_launch(0, G, P, W, core, stream);
+}
+
+int rhccq_dbscan_union(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, uint8_t* core, void* stream) {
+    RHCCQ_PT_ARGS("rhccq_dbscan_union")
+    RHCCQ_LAUNCH(rhccq_k_pt_init_parent, rhccq_pt_blocks(P->n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, P->n, W.parent);
+    return rhccq_pt_sweep_launch(1, G, P, W, core, stream);
+}
+
+int rhccq_dbscan_border(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, uint8_t* core, void* stream) {
+    RHCCQ_PT_ARGS("rhccq_dbscan_border")
+    RHCCQ_LAUNCH(rhccq_k_pt_flatten, rhccq_pt_blocks(P->n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, P->n, W.parent, core, W.rootlab, W.is_root);
+    return rhccq_pt_sweep_launch(2, G, P, W, core, stream);
+}
+
+int rhccq_dbscan_relabel(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, int32_t* labels, void* stream) {
+    RHCCQ_PT_ARGS("rhccq_dbscan_relabel")
+    if (P->n <= RHCCQ_SCAN_TILE) {
+        RHCCQ_LAUNCH(rhccq_k_scan_small, 1, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, W.is_root, P->n, (int*)nullptr);
+    } else if (rhccq_scan_i32(W.is_root, P->n, W.is_root, W.scan, stream) != 0) return -1;
+    RHCCQ_LAUNCH(rhccq_k_pt_labels, rhccq_pt_blocks(P->n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, P->n, W.rootlab, W.is_root, labels);
+    return 0;
+}
+
+}  // extern "C"

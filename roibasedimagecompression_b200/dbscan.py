@@ -1,0 +1,137 @@
+"""DBSCAN of point clouds on the GPU — the operator one level below the reference's quantiser.
+
+The reference calls ``sklearn.cluster.DBSCAN(eps, min_samples, metric='euclidean').fit_predict(X)``
+(/root/reference/encoder/compression/clustering.py:233-235).  ``DBSCAN`` here keeps that operator's
+constructor arguments, ``fit`` / ``fit_predict`` and the ``labels_`` / ``core_sample_indices_``
+attributes for float32 inputs of 2 to 6 columns, e.g. (x, y, R, G, B) pixel features; labels follow
+scikit-learn exactly (clusters numbered by lowest core index, border points in the lowest-numbered
+admissible cluster, noise -1).
+
+``dbscan_points`` is the tensor-level form: device tensor in, device tensors out, phases individually
+timeable (``phases=`` receives the per-phase CUDA-event times when given).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import Backend, DbscanPlan, RhccqError, lib
+
+PHASES = ("bin", "count", "union", "border", "relabel")
+
+
+class PointDbscan:
+    """A plan + workspace for one (n, dims, eps, min_pts, bounds): reusable across calls on same-sized inputs."""
+
+    def __init__(self, be: Backend, n: int, dims: int, eps: float, min_pts: int, lo, hi, grid_dims: int = 2):
+        self.be = be
+        self.plan = DbscanPlan()
+        lo_a = (ctypes.c_double * 3)(*[float(v) for v in list(lo)[:3]] + [0.0] * (3 - len(list(lo)[:3])))
+        hi_a = (ctypes.c_double * 3)(*[float(v) for v in list(hi)[:3]] + [0.0] * (3 - len(list(hi)[:3])))
+        rc = be.cdll.rhccq_dbscan_plan_make(int(n), int(dims), int(grid_dims), float(eps), int(min_pts),
+                                            ctypes.addressof(lo_a), ctypes.addressof(hi_a), ctypes.addressof(self.plan))
+        if rc != 0:
+            raise RhccqError("rhccq_dbscan_plan_make: " + be.cdll.rhccq_last_error().decode(errors="replace"))
+        self.ws_bytes = int(be.cdll.rhccq_dbscan_workspace_bytes(ctypes.addressof(self.plan)))
+        self.ws = be.empty((max(self.ws_bytes, 1),), torch.uint8)
+        self.core = be.empty((max(n, 1),), torch.uint8)
+        self.labels = be.empty((max(n, 1),), torch.int32)
+
+    def _p(self):
+        return ctypes.addressof(self.plan)
+
+    def bin(self, pts):
+        self.be.call("rhccq_dbscan_bin", self._p(), self.be.ptr(pts), self.be.ptr(self.ws), self.ws_bytes, self.be.stream(),
+                     launches=4)
+
+    def count(self):
+        self.be.call("rhccq_dbscan_count", self._p(), self.be.ptr(self.ws), self.ws_bytes, self.be.ptr(self.core),
+                     self.be.stream())
+
+    def union(self):
+        self.be.call("rhccq_dbscan_union", self._p(), self.be.ptr(self.ws), self.ws_bytes, self.be.ptr(self.core),
+                     self.be.stream(), launches=2)
+
+    def border(self):
+        self.be.call("rhccq_dbscan_border", self._p(), self.be.ptr(self.ws), self.ws_bytes, self.be.ptr(self.core),
+                     self.be.stream(), launches=2)
+
+    def relabel(self):
+        self.be.call("rhccq_dbscan_relabel", self._p(), self.be.ptr(self.ws), self.ws_bytes, self.be.ptr(self.labels),
+                     self.be.stream(), launches=3)
+
+    def run(self, pts):
+        """labels int32 [n], core uint8 [n] (views of buffers owned by the plan)."""
+        n = self.plan.n
+        if tuple(pts.shape) != (n, self.plan.dims) or pts.dtype != torch.float32:
+            raise ValueError(f"points must be float32 [{n},{self.plan.dims}]")
+        if n == 0:
+            return self.labels[:0], self.core[:0]
+        self.bin(pts); self.count(); self.union(); self.border(); self.relabel()
+        return self.labels[:n], self.core[:n]
+
+
+def point_bounds(be: Backend, pts, grid_dims: int = 2):
+    """(lo, hi) of the first grid_dims coordinates, computed on the device (one small read-back)."""
+    n, dims = pts.shape
+    out = be.empty((6,), torch.float64)
+    ws = be.empty((1024 * 6 * 4,), torch.uint8)
+    be.call("rhccq_dbscan_bounds", be.ptr(pts), int(n), int(dims), int(grid_dims), be.ptr(out), be.ptr(ws), ws.numel(),
+            be.stream(), launches=2)
+    o = out.cpu().numpy()
+    return o[:3], o[3:]
+
+
+def dbscan_points(be: Backend, pts, eps: float, min_pts: int, grid_dims: int = 2, bounds=None):
+    """labels (int32 [n]) and core flags (uint8 [n]) of DBSCAN(eps, min_pts) on float32 points [n, dims]."""
+    n, dims = pts.shape
+    if n == 0:
+        return be.empty((0,), torch.int32), be.empty((0,), torch.uint8)
+    lo, hi = bounds if bounds is not None else point_bounds(be, pts, grid_dims)
+    plan = PointDbscan(be, n, dims, eps, min_pts, lo, hi, grid_dims)
+    labels, core = plan.run(pts)
+    return labels.clone(), core.clone()
+
+
+class DBSCAN:
+    """sklearn.cluster.DBSCAN's interface for the euclidean metric (the only one the reference uses)."""
+
+    def __init__(self, eps=0.5, *, min_samples=5, metric="euclidean", grid_dims=None, **unsupported):
+        if metric != "euclidean":
+            raise NotImplementedError("only metric='euclidean' (the reference's, clustering.py:233)")
+        bad = {k: v for k, v in unsupported.items() if k not in ("algorithm", "leaf_size", "n_jobs", "p", "metric_params")}
+        if bad:
+            raise TypeError(f"unexpected arguments {sorted(bad)}")
+        self.eps, self.min_samples, self.metric, self.grid_dims = float(eps), int(min_samples), metric, grid_dims
+
+    def fit(self, X, y=None, sample_weight=None):
+        if sample_weight is not None:
+            raise NotImplementedError("sample_weight (the reference never passes it)")
+        be = _backend()
+        x = np.ascontiguousarray(X, dtype=np.float32)
+        if x.ndim != 2 or not 2 <= x.shape[1] <= 6:
+            raise ValueError("X must be [n_samples, 2..6]")
+        gd = self.grid_dims or (3 if x.shape[1] >= 3 and x.shape[0] > 0 and _dense_in_2d(x, self.eps) else 2)
+        labels, core = dbscan_points(be, torch.from_numpy(x).to(be.device), self.eps, self.min_samples, gd)
+        self.labels_ = labels.cpu().numpy().astype(np.int64)
+        self.core_sample_indices_ = np.flatnonzero(core.cpu().numpy())
+        self.components_ = np.asarray(X)[self.core_sample_indices_]
+        return self
+
+    def fit_predict(self, X, y=None, sample_weight=None):
+        return self.fit(X, sample_weight=sample_weight).labels_
+
+
+def _dense_in_2d(x: np.ndarray, eps: float) -> bool:
+    """True when a 2-D grid of eps cells would hold hundreds of points per cell (then bin on 3 coordinates)."""
+    span = (x[:, :2].max(axis=0) - x[:, :2].min(axis=0)) / eps + 1.0
+    return x.shape[0] / float(span[0] * span[1]) > 64.0
+
+
+_BACKEND = None          # tests bind the host-emulation build here
+
+
+def _backend() -> Backend:
+    return _BACKEND if _BACKEND is not None else lib()

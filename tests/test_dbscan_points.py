@@ -1,0 +1,111 @@
+"""Large-N point DBSCAN (bin / count / union / border / relabel) against scikit-learn's golden labels
+and the brute-force oracle.  Labels must be IDENTICAL to scikit-learn's (cluster numbering included)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import rhccq_oracle as O
+from roibasedimagecompression_b200 import dbscan as D
+from roibasedimagecompression_b200.synth import synth, pixel_features
+
+
+def _run(be, pts, eps, mp, gd=2):
+    lab, core = D.dbscan_points(be, torch.from_numpy(np.ascontiguousarray(pts, np.float32)).to(be.device), eps, mp, gd)
+    return lab.cpu().numpy().astype(np.int64), core.cpu().numpy().astype(bool)
+
+
+def test_points_golden_sklearn(backend):
+    g = golden("dbscan_points.npz")
+    pts = g["points"]
+    for i, (eps, mp) in enumerate(g["combos"]):
+        lab, core = _run(backend, pts, float(eps), int(mp))
+        assert np.array_equal(lab, g[f"labels{i}"]), (eps, mp)
+        assert np.array_equal(core, g[f"core{i}"]), (eps, mp)
+    u = g["uniform_points"]
+    for i, (eps, mp) in enumerate(g["uniform_combos"]):
+        for gd in (2, 3):
+            lab, _ = _run(backend, u, float(eps), int(mp), gd)
+            assert np.array_equal(lab, g[f"uniform_labels{i}"]), (eps, mp, gd)
+
+
+def test_points_ties_ragged_and_empty(backend):
+    # integer lattice: many pairs at exactly eps (float64 tie path), eps^2 integer and not
+    yy, xx = np.mgrid[0:23, 0:37]
+    pts = np.stack([xx.ravel(), yy.ravel(), (xx.ravel() * 7 + yy.ravel() * 3) % 5], axis=1).astype(np.float32)
+    for eps, mp in ((1.0, 3), (2.0, 5), (np.sqrt(2.0), 4), (2.2360679774997896, 9), (3.0, 40)):
+        lab, core = _run(backend, pts, float(eps), mp)
+        want = O.dbscan_labels(pts, float(eps), mp)
+        assert np.array_equal(lab, want), (eps, mp)
+    lab, core = _run(backend, np.zeros((0, 5), np.float32), 1.0, 2)
+    assert lab.size == 0 and core.size == 0
+    one = np.array([[3.0, 4.0, 5.0]], np.float32)
+    assert _run(backend, one, 1.0, 1)[0].tolist() == [0] and _run(backend, one, 1.0, 2)[0].tolist() == [-1]
+    same = np.tile(np.array([[1.0, 2.0, 3.0, 4.0, 5.0]], np.float32), (700, 1))       # one cell, many chunks
+    lab, core = _run(backend, same, 0.5, 700)
+    assert (lab == 0).all() and core.all()
+
+
+def test_points_sklearn_interface(backend):
+    D._BACKEND = backend if backend.device.type == "cpu" else None
+    try:
+        img = synth(24, 32, 9)
+        pts = pixel_features(img)
+        m = D.DBSCAN(eps=4.0, min_samples=4).fit(pts)
+        want = O.dbscan_labels(pts, 4.0, 4)
+        assert np.array_equal(m.labels_, want)
+        assert np.array_equal(D.DBSCAN(eps=4.0, min_samples=4).fit_predict(pts), want)
+        assert m.labels_.dtype == np.int64 and m.components_.shape[1] == 5
+    finally:
+        D._BACKEND = None
+
+
+@pytest.mark.gpu
+def test_points_large_properties():
+    """4K-image-sized input: properties that need no O(n^2) oracle — idempotent canonical labels, every
+    core point's neighbours inside its cluster on a sampled subset, cluster ids dense and ordered."""
+    from roibasedimagecompression_b200._lib import lib
+    be = lib()
+    img = synth(1080, 1920, 1234)
+    pts = pixel_features(img)
+    lab, core = _run(be, pts, 3.0, 8)
+    lab2, core2 = _run(be, pts, 3.0, 8)
+    assert np.array_equal(lab, lab2) and np.array_equal(core, core2)             # deterministic despite atomics
+    k = lab.max() + 1
+    first = np.full(k, len(lab), np.int64)
+    cl = np.flatnonzero(core)
+    np.minimum.at(first, lab[cl], cl)
+    assert (np.diff(first) > 0).all()                                            # numbered by lowest core index
+    # window check: brute force inside 40x40 pixel windows (interior points only)
+    H, W = 1080, 1920
+    rng = np.random.default_rng(0)
+    for _ in range(6):
+        r0, c0 = int(rng.integers(0, H - 40)), int(rng.integers(0, W - 40))
+        rows, cols = np.mgrid[r0:r0 + 40, c0:c0 + 40]
+        ids = (rows * W + cols).ravel()
+        sub = pts[ids].astype(np.float64)
+        d2 = ((sub[:, None, :] - sub[None, :, :]) ** 2).sum(-1)
+        inner = ((rows > r0 + 3) & (rows < r0 + 36) & (cols > c0 + 3) & (cols < c0 + 36)).ravel()
+        cnt = (d2 <= 9.0).sum(1)
+        assert np.array_equal(core[ids][inner], (cnt >= 8)[inner])
+        ci = np.flatnonzero(inner & core[ids])
+        for a in ci[:200]:
+            nb = np.flatnonzero((d2[a] <= 9.0) & core[ids])
+            assert (lab[ids][nb] == lab[ids][a]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("eps,mp", [(3.0, 8), (2.0, 4), (5.0, 16)])
+def test_points_quarter_million_vs_sklearn(eps, mp):
+    """Deep union-find trees and multi-block scans only show up at scale: 262 144 points against
+    scikit-learn itself (the operator the reference calls), labels identical."""
+    sk = pytest.importorskip("sklearn.cluster")
+    from roibasedimagecompression_b200._lib import lib
+    be = lib()
+    pts = pixel_features(synth(512, 512, 77))
+    lab, core = _run(be, pts, eps, mp)
+    ref = sk.DBSCAN(eps=eps, min_samples=mp).fit(pts)
+    rc = np.zeros(len(pts), bool)
+    rc[ref.core_sample_indices_] = True
+    assert np.array_equal(core, rc)
+    assert np.array_equal(lab, ref.labels_)
