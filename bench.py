@@ -42,6 +42,8 @@ WORKLOADS = {
     "c5": (1, 4096, 4096, 0, "DBSCAN of 16.8 M 5-D points (x, y, R, G, B) of a 4096x4096 synthetic image"),
     "c5s": (1, 1024, 1024, 0, "DBSCAN of 1.05 M 5-D points (x, y, R, G, B) of a 1024x1024 synthetic image"),
     "c5u": (1, 2048, 2048, 0, "DBSCAN of 4.2 M uniform points in [0,256)^5 (3-D cell grid)"),
+    # BASELINE.json configs[3]: one 7680x4320 image, strips of rows + halo per GPU, NCCL all-gather of boundary edges
+    "c4": (1, 4320, 7680, 0, "DBSCAN of the 33.2 M pixel features of one 7680x4320 synthetic image, strip-sharded"),
 }
 DBSCAN_BYTES_PER_POINT = 24       # 20 B read + 4 B written, both for the count kernel and the whole
 
@@ -260,6 +262,59 @@ def run_dbscan(args, be, rank, world, local, H, W, desc):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- strip-sharded DBSCAN (C4)
+def run_strips(args, be, rank, world, local, H, W, desc):
+    import torch
+    import torch.distributed as dist
+    from roibasedimagecompression_b200 import dbscan as D
+    from roibasedimagecompression_b200.synth import synth
+    eps, min_pts = args.eps, args.min_pts
+    r0, r1, l0, l1, zone = D.strip_rows(H, world, rank, eps)
+    th, tw = 1080, 1920                                             # the image is a 4 x 4 mosaic of synth tiles
+    rows = []
+    for tr in range(l0 // th, (l1 - 1) // th + 1):
+        band = np.concatenate([synth(th, tw, 1234 + tr * (W // tw) + tc) for tc in range(W // tw)], axis=1)
+        rows.append(band[max(l0 - tr * th, 0):min(l1 - tr * th, th)])
+    img = np.concatenate(rows, axis=0)
+    yy, xx = np.mgrid[l0:l1, 0:W]
+    pts_np = np.concatenate([xx[..., None], yy[..., None], img], axis=2).reshape(-1, 5).astype(np.float32)
+    h_pts = torch.from_numpy(pts_np).pin_memory()
+    d_pts = h_pts.cuda()
+    own = ((r0 - l0) * W, (r1 - l0) * W)
+    zone_idx = [((a - l0) * W, (b - l0) * W) for a, b in zone]
+    info = {}
+    for _ in range(args.warmup):
+        labels, core = D.dbscan_strips(be, d_pts, l0 * W, own, zone_idx, eps, min_pts, timings=info)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local); sampler.start()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    l0_launch = be.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        labels, core = D.dbscan_strips(be, d_pts, l0 * W, own, zone_idx, eps, min_pts, timings=info)
+    e1.record(); torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    n = H * W
+    out = {"metric": "DBSCAN points/sec, one image strip-sharded (halo + NCCL boundary-edge merge)", "value": n / (ms / 1e3),
+           "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "c4: " + desc, "eps": eps, "min_pts": min_pts, "rows_per_rank": r1 - r0,
+                      "halo_rows": r0 - l0, "boundary_edges_total": info.get("edges_total"),
+                      "clusters": info.get("roots_total"), "l2": "points larger than L2"},
+           "clocks": clocks, "gpu_launches": be.launches - l0_launch,
+           "e2e": None, "roofline": None}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------- the B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -294,6 +349,8 @@ def main():
     B, H, W, tile, desc = WORKLOADS[args.workload]
     if args.workload.startswith("c5"):
         return run_dbscan(args, be, rank, world, local, H, W, desc)
+    if args.workload == "c4":
+        return run_strips(args, be, rank, world, local, H, W, desc)
     imgs_np, labs_np, table = make_inputs(B, H, W, tile, 1234 + rank * B)
     h_img = torch.from_numpy(imgs_np).pin_memory()
     h_lab = torch.from_numpy(labs_np).pin_memory()

@@ -203,8 +203,35 @@ int rhccq_dbscan_bin(const rhccq_dbscan_plan* host_plan, const float* pts, void*
 int rhccq_dbscan_count(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, uint8_t* core, void* stream);
 /* union-find over core pairs within eps; a set's root is its lowest original index */
 int rhccq_dbscan_union(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, uint8_t* core, void* stream);
-/* flatten + border attachment */
+/* flatten + border attachment (= rhccq_dbscan_flatten followed by rhccq_dbscan_attach) */
 int rhccq_dbscan_border(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, uint8_t* core, void* stream);
+/* root (lowest index of its set) of every core point into the workspace's root array, -1 for the others */
+int rhccq_dbscan_flatten(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, uint8_t* core, void* stream);
+/* non-core points take the lowest root among the core points within eps (reads the root array) */
+int rhccq_dbscan_attach(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, uint8_t* core, void* stream);
+/* byte offset inside the workspace of: 0 the root array (int32 [n]), 1 scan scratch (int32 [n]),
+ * 2 the union-find parents (int32 [n]), 3 the sorted records (8 x float32 [n]) */
+size_t rhccq_dbscan_ws_offset(const rhccq_dbscan_plan* host_plan, int which);
+
+/* ------------------------------------------------------------------ strips of one point set across GPUs
+ * (SURVEY.md 8e).  Every rank runs plan..flatten on its strip plus a halo of 2 eps; local indices are
+ * global index - g0.  emit: for core points i in [lo, hi) of the boundary zone that are not their own root,
+ * append (g0 + i, g0 + root) to edges (int32 pairs; *counter may exceed capacity: then enlarge and repeat).
+ * merge: union-find over the gathered edges of all ranks in an open-addressing table (capacity a power of
+ * two >= 4 n_edges), roots = lowest global index.  lookup: local roots -> global roots, in place (table NULL:
+ * only the shift by g0).  own_roots: global indices of the roots among the rank's own points [own_lo,
+ * own_hi), ascending.  rank_labels: label = position of the point's global root in the sorted list of all
+ * ranks' roots (-1 for noise). */
+int rhccq_uf_emit_edges(const int32_t* rootlab, int lo, int hi, int g0, int32_t* edges, int32_t* counter, int capacity,
+                        void* stream);
+int rhccq_uf_merge_edges(const int32_t* edges, int n_edges, int32_t* table_keys, int32_t* table_parent, int table_cap,
+                         void* stream);
+int rhccq_uf_lookup_roots(int32_t* rootlab, int n, int g0, const int32_t* table_keys, const int32_t* table_parent,
+                          int table_cap, void* stream);
+int rhccq_dbscan_own_roots(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, int own_lo, int own_hi, int g0,
+                           int32_t* out_ids, int32_t* out_count, void* stream);
+int rhccq_uf_rank_labels(const int32_t* sorted_roots, int n_roots, const int32_t* rootlab, int lo, int hi, int32_t* labels,
+                         void* stream);
 /* labels int32 [n], original order */
 int rhccq_dbscan_relabel(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, int32_t* labels, void* stream);
 

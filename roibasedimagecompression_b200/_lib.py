@@ -56,6 +56,14 @@ SIGNATURES = {
     "rhccq_dbscan_union": (_I, [_P, _P, _Z, _P, _P]),
     "rhccq_dbscan_border": (_I, [_P, _P, _Z, _P, _P]),
     "rhccq_dbscan_relabel": (_I, [_P, _P, _Z, _P, _P]),
+    "rhccq_dbscan_flatten": (_I, [_P, _P, _Z, _P, _P]),
+    "rhccq_dbscan_attach": (_I, [_P, _P, _Z, _P, _P]),
+    "rhccq_dbscan_ws_offset": (_Z, [_P, _I]),
+    "rhccq_uf_emit_edges": (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
+    "rhccq_uf_merge_edges": (_I, [_P, _I, _P, _P, _I, _P]),
+    "rhccq_uf_lookup_roots": (_I, [_P, _I, _I, _P, _P, _I, _P]),
+    "rhccq_dbscan_own_roots": (_I, [_P, _P, _Z, _I, _I, _I, _P, _P, _P]),
+    "rhccq_uf_rank_labels": (_I, [_P, _I, _P, _I, _I, _P, _P]),
 }
 
 

@@ -390,6 +390,105 @@ rhccq_k_pt_labels(int n, const int* __restrict__ rootlab, const int* __restrict_
     }
 }
 
+// ---------------------------------------------------------------- strips: boundary edges, merge, lookup
+// A very large point set is split into strips of consecutive points (rows of an image), one per GPU, each
+// with a halo of 2 eps: neighbour counts are then exact for the strip's own points and for the halo points
+// within eps of it, so every edge of the global core graph is seen by at least one rank.  Local components
+// are glued at the points two ranks share: for every core point p of the boundary zone a rank emits the edge
+// (p, local root of p) in global indices; all ranks gather all edges (NCCL) and run the same union-find over
+// them (roots = lowest global index), which maps local roots to global roots.
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_uf_emit(const int* __restrict__ rootlab, int lo, int hi, int g0, int* __restrict__ edges, int* __restrict__ counter,
+                int capacity) {
+    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+        const int r = rootlab[i];
+        if (r < 0 || r == (int)i) continue;                        // not core, or its own root: nothing to glue
+        const int slot = atomicAdd(counter, 1);
+        if (slot < capacity) { edges[2 * slot] = g0 + (int)i; edges[2 * slot + 1] = g0 + r; }
+    }
+}
+
+__device__ __forceinline__ int rhccq_tab_insert(int* keys, int cap_mask, int id) {
+    uint32_t h = ((uint32_t)id * 2654435761u) & (uint32_t)cap_mask;
+    while (true) {
+        const int k = atomicCAS(&keys[h], -1, id);
+        if (k == -1 || k == id) return (int)h;
+        h = (h + 1) & (uint32_t)cap_mask;
+    }
+}
+__device__ __forceinline__ int rhccq_tab_find(const int* keys, int cap_mask, int id) {
+    uint32_t h = ((uint32_t)id * 2654435761u) & (uint32_t)cap_mask;
+    while (true) {
+        const int k = keys[h];
+        if (k == id) return (int)h;
+        if (k == -1) return -1;
+        h = (h + 1) & (uint32_t)cap_mask;
+    }
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_uf_tab_init(int* __restrict__ keys, int* __restrict__ parent, int cap) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (long long)gridDim.x * blockDim.x) {
+        keys[i] = -1; parent[i] = (int)i;
+    }
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_uf_tab_insert(const int* __restrict__ edges, int n_edges, int* __restrict__ keys, int cap_mask) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < 2LL * n_edges; e += (long long)gridDim.x * blockDim.x)
+        rhccq_tab_insert(keys, cap_mask, edges[e]);
+}
+// union by key: the slot whose key (global index) is larger goes under the other
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_uf_tab_union(const int* __restrict__ edges, int n_edges, const int* __restrict__ keys, int* __restrict__ parent,
+                     int cap_mask) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (long long)gridDim.x * blockDim.x) {
+        int a = rhccq_tab_find(keys, cap_mask, edges[2 * e]), b = rhccq_tab_find(keys, cap_mask, edges[2 * e + 1]);
+        while (true) {
+            a = rhccq_pt_find(parent, a);
+            b = rhccq_pt_find(parent, b);
+            if (a == b) break;
+            if (keys[a] < keys[b]) { const int t = a; a = b; b = t; }      // a: larger key
+            if (atomicCAS(&parent[a], a, b) == a) break;
+        }
+    }
+}
+// rootlab (local roots, local indices; -1 = not core) -> global roots (global indices) through the table
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_uf_lookup(int* __restrict__ rootlab, int n, int g0, const int* __restrict__ keys, const int* __restrict__ parent,
+                  int cap_mask) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = rootlab[i];
+        if (r < 0) continue;
+        int gr = g0 + r;
+        if (cap_mask >= 0) {
+            const int s = rhccq_tab_find(keys, cap_mask, gr);
+            if (s >= 0) gr = keys[rhccq_pt_find_ro(parent, s)];
+        }
+        rootlab[i] = gr;
+    }
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_uf_root_flags(const int* __restrict__ rootlab, int n, int lo, int hi, int g0, int* __restrict__ flags) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        flags[i] = (i >= lo && i < hi && rootlab[i] == g0 + (int)i) ? 1 : 0;
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_uf_root_scatter(const int* __restrict__ rootlab, const int* __restrict__ rank, int lo, int hi, int g0,
+                        int* __restrict__ out_ids, int* __restrict__ out_count, int n) {
+    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x)
+        if (rootlab[i] == g0 + (int)i) out_ids[rank[i]] = g0 + (int)i;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = hi < n ? rank[hi] : rank[n - 1] + (rootlab[n - 1] == g0 + n - 1 && n - 1 >= lo ? 1 : 0);
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_uf_rank(const int* __restrict__ sorted_roots, int n_roots, const int* __restrict__ rootlab, int lo, int hi,
+                int* __restrict__ labels) {
+    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+        const int r = rootlab[i];
+        int a = 0, b = n_roots;
+        while (a < b) { const int m = (a + b) >> 1; if (sorted_roots[m] < r) a = m + 1; else b = m; }
+        labels[i - lo] = (r < 0 || a >= n_roots || sorted_roots[a] != r) ? -1 : a;
+    }
+}
+
 // ---------------------------------------------------------------- host side
 struct rhccq_pt_ws {
     float* rec; int* cell_id; int* cell_start; int* cell_fill; int* parent; int* rootlab; int* is_root; int* scan;
@@ -545,10 +644,77 @@ int rhccq_dbscan_union(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, ui
     return rhccq_pt_sweep_launch(1, G, P, W, core, stream);
 }
 
-int rhccq_dbscan_border(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, uint8_t* core, void* stream) {
-    RHCCQ_PT_ARGS("rhccq_dbscan_border")
+int rhccq_dbscan_flatten(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, uint8_t* core, void* stream) {
+    RHCCQ_PT_ARGS("rhccq_dbscan_flatten")
     RHCCQ_LAUNCH(rhccq_k_pt_flatten, rhccq_pt_blocks(P->n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, P->n, W.parent, core, W.rootlab, W.is_root);
+    return 0;
+}
+
+int rhccq_dbscan_attach(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, uint8_t* core, void* stream) {
+    RHCCQ_PT_ARGS("rhccq_dbscan_attach")
     return rhccq_pt_sweep_launch(2, G, P, W, core, stream);
+}
+
+int rhccq_dbscan_border(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, uint8_t* core, void* stream) {
+    if (rhccq_dbscan_flatten(P, ws, ws_bytes, core, stream) != 0) return -1;
+    return rhccq_dbscan_attach(P, ws, ws_bytes, core, stream);
+}
+
+size_t rhccq_dbscan_ws_offset(const rhccq_dbscan_plan* P, int which) {
+    if (!P) return 0;
+    rhccq_pt_ws W;
+    rhccq_pt_carve(P, (unsigned char*)256, &W);                   // offsets relative to a fake non-null base
+    const unsigned char* p = which == 0 ? (unsigned char*)W.rootlab : which == 1 ? (unsigned char*)W.is_root
+                           : which == 2 ? (unsigned char*)W.parent : (unsigned char*)W.rec;
+    return (size_t)(p - (unsigned char*)256);
+}
+
+int rhccq_uf_emit_edges(const int32_t* rootlab, int lo, int hi, int g0, int32_t* edges, int32_t* counter, int capacity,
+                        void* stream) {
+    if (hi <= lo) return 0;
+    RHCCQ_LAUNCH(rhccq_k_uf_emit, rhccq_pt_blocks(hi - lo), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, rootlab, lo, hi, g0,
+                 edges, counter, capacity);
+    return 0;
+}
+
+int rhccq_uf_merge_edges(const int32_t* edges, int n_edges, int32_t* table_keys, int32_t* table_parent, int table_cap,
+                         void* stream) {
+    if (table_cap < 2 || (table_cap & (table_cap - 1)) != 0 || (long long)table_cap < 4LL * n_edges) {
+        rhccq_set_error("rhccq_uf_merge_edges: table capacity must be a power of two >= 4 * n_edges"); return -1;
+    }
+    RHCCQ_LAUNCH(rhccq_k_uf_tab_init, rhccq_pt_blocks(table_cap), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, table_keys, table_parent, table_cap);
+    if (n_edges <= 0) return 0;
+    RHCCQ_LAUNCH(rhccq_k_uf_tab_insert, rhccq_pt_blocks(2LL * n_edges), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, edges, n_edges, table_keys, table_cap - 1);
+    RHCCQ_LAUNCH(rhccq_k_uf_tab_union, rhccq_pt_blocks(n_edges), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, edges, n_edges, table_keys, table_parent, table_cap - 1);
+    return 0;
+}
+
+int rhccq_uf_lookup_roots(int32_t* rootlab, int n, int g0, const int32_t* table_keys, const int32_t* table_parent,
+                          int table_cap, void* stream) {
+    if (n <= 0) return 0;
+    RHCCQ_LAUNCH(rhccq_k_uf_lookup, rhccq_pt_blocks(n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, rootlab, n, g0, table_keys,
+                 table_parent, table_keys ? table_cap - 1 : -1);
+    return 0;
+}
+
+int rhccq_dbscan_own_roots(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, int own_lo, int own_hi, int g0,
+                           int32_t* out_ids, int32_t* out_count, void* stream) {
+    RHCCQ_PT_ARGS("rhccq_dbscan_own_roots")
+    RHCCQ_LAUNCH(rhccq_k_uf_root_flags, rhccq_pt_blocks(P->n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, W.rootlab, P->n, own_lo, own_hi, g0, W.is_root);
+    if (P->n <= RHCCQ_SCAN_TILE) {
+        RHCCQ_LAUNCH(rhccq_k_scan_small, 1, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, W.is_root, P->n, (int*)nullptr);
+    } else if (rhccq_scan_i32(W.is_root, P->n, W.is_root, W.scan, stream) != 0) return -1;
+    RHCCQ_LAUNCH(rhccq_k_uf_root_scatter, rhccq_pt_blocks(own_hi - own_lo), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, W.rootlab,
+                 W.is_root, own_lo, own_hi, g0, out_ids, out_count, P->n);
+    return 0;
+}
+
+int rhccq_uf_rank_labels(const int32_t* sorted_roots, int n_roots, const int32_t* rootlab, int lo, int hi, int32_t* labels,
+                         void* stream) {
+    if (hi <= lo) return 0;
+    RHCCQ_LAUNCH(rhccq_k_uf_rank, rhccq_pt_blocks(hi - lo), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, sorted_roots, n_roots,
+                 rootlab, lo, hi, labels);
+    return 0;
 }
 
 int rhccq_dbscan_relabel(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, int32_t* labels, void* stream) {

@@ -135,3 +135,106 @@ _BACKEND = None          # tests bind the host-emulation build here
 
 def _backend() -> Backend:
     return _BACKEND if _BACKEND is not None else lib()
+
+
+# --------------------------------------------------------------------------- one point set across GPUs
+def strip_rows(H: int, world: int, rank: int, eps: float, w_xy: float = 1.0):
+    """Row ranges of rank `rank` for an H-row raster split into `world` strips.
+
+    Returns (own_r0, own_r1, loc_r0, loc_r1, zone): own rows, the rows the rank reads (own + a halo of
+    ceil(2 eps / w_xy) rows per side, clipped), and the list of row ranges of the boundary zone (rows of
+    the local block within the halo width of an internal strip boundary) — all in image rows.
+    """
+    hz = int(np.ceil(2.0 * eps / w_xy))
+    base, extra = divmod(H, world)
+    r0 = rank * base + min(rank, extra)
+    r1 = r0 + base + (1 if rank < extra else 0)
+    l0, l1 = max(0, r0 - hz), min(H, r1 + hz)
+    zone = []
+    if rank > 0:
+        zone.append((l0, min(r1, r0 + hz)))
+    if rank < world - 1:
+        lo = max(r0, r1 - hz)
+        if zone and lo <= zone[-1][1]:
+            zone[-1] = (zone[-1][0], l1)
+        else:
+            zone.append((lo, l1))
+    return r0, r1, l0, l1, zone
+
+
+def dbscan_strips(be: Backend, pts_local, g0: int, own, zone, eps: float, min_pts: int, group=None, grid_dims: int = 2,
+                  timings: dict | None = None):
+    """DBSCAN of one point set split into strips, one per rank of `group` (torch.distributed).
+
+    pts_local   float32 [n_loc, dims] on the backend's device: the rank's own points plus the halo, a
+                contiguous slice [g0, g0 + n_loc) of the global point order
+    own         (lo, hi) local index range of the rank's own points
+    zone        list of (lo, hi) local index ranges of the boundary zone (halo and the own points within
+                2 eps of an internal boundary)
+    Returns labels int32 [own points] identical to the labels an unsplit run gives those points.
+    """
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    n_loc, dims = pts_local.shape
+    lo, hi = point_bounds(be, pts_local, grid_dims)
+    plan = PointDbscan(be, n_loc, dims, eps, min_pts, lo, hi, grid_dims)
+    p, ws, wsb = plan._p(), plan.ws, plan.ws_bytes
+    plan.bin(pts_local); plan.count(); plan.union()
+    be.call("rhccq_dbscan_flatten", p, be.ptr(ws), wsb, be.ptr(plan.core), be.stream())
+    off = int(be.cdll.rhccq_dbscan_ws_offset(p, 0))
+    rootlab = ws[off:off + 4 * n_loc].view(torch.int32)
+    # ---- boundary edges of this rank
+    cap = max(sum(b - a for a, b in zone), 1)
+    edges = be.empty((cap, 2), torch.int32)
+    counter = be.zeros((1,), torch.int32)
+    for a, b in zone:
+        be.call("rhccq_uf_emit_edges", be.ptr(rootlab), int(a), int(b), int(g0), be.ptr(edges), be.ptr(counter), cap,
+                be.stream())
+    n_e = int(counter.item())                                       # <= cap by construction (one edge per zone point)
+    # ---- the one exchange step: all ranks gather all edges
+    if world > 1:
+        sizes = [torch.zeros(1, dtype=torch.int64, device=be.device) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([n_e], dtype=torch.int64, device=be.device), group=group)
+        sizes = [int(s.item()) for s in sizes]
+        m = max(max(sizes), 1)
+        mine = be.zeros((m, 2), torch.int32)
+        mine[:n_e] = edges[:n_e]
+        bufs = [be.empty((m, 2), torch.int32) for _ in range(world)]
+        dist.all_gather(bufs, mine, group=group)
+        all_edges = torch.cat([b[:s] for b, s in zip(bufs, sizes)]).contiguous()
+    else:
+        all_edges = edges[:n_e].contiguous()
+    E = int(all_edges.shape[0])
+    if E > 0:
+        tcap = 1 << max(4, int(np.ceil(np.log2(4 * E))))
+        tk, tp = be.empty((tcap,), torch.int32), be.empty((tcap,), torch.int32)
+        be.call("rhccq_uf_merge_edges", be.ptr(all_edges), E, be.ptr(tk), be.ptr(tp), tcap, be.stream(), launches=3)
+        be.call("rhccq_uf_lookup_roots", be.ptr(rootlab), n_loc, int(g0), be.ptr(tk), be.ptr(tp), tcap, be.stream())
+    else:
+        be.call("rhccq_uf_lookup_roots", be.ptr(rootlab), n_loc, int(g0), 0, 0, 0, be.stream())
+    # ---- border points against global roots, then the global numbering of roots
+    be.call("rhccq_dbscan_attach", p, be.ptr(ws), wsb, be.ptr(plan.core), be.stream())
+    n_own = own[1] - own[0]
+    ids = be.empty((max(n_own, 1),), torch.int32)
+    cnt = be.zeros((1,), torch.int32)
+    be.call("rhccq_dbscan_own_roots", p, be.ptr(ws), wsb, int(own[0]), int(own[1]), int(g0), be.ptr(ids), be.ptr(cnt),
+            be.stream(), launches=3)
+    n_r = int(cnt.item())
+    if world > 1:
+        sizes = [torch.zeros(1, dtype=torch.int64, device=be.device) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([n_r], dtype=torch.int64, device=be.device), group=group)
+        sizes = [int(s.item()) for s in sizes]
+        m = max(max(sizes), 1)
+        mine = be.zeros((m,), torch.int32)
+        mine[:n_r] = ids[:n_r]
+        bufs = [be.empty((m,), torch.int32) for _ in range(world)]
+        dist.all_gather(bufs, mine, group=group)
+        roots = torch.cat([b[:s] for b, s in zip(bufs, sizes)]).contiguous()     # ascending: strips are ordered
+    else:
+        roots = ids[:n_r].contiguous()
+    labels = be.empty((max(n_own, 1),), torch.int32)
+    be.call("rhccq_uf_rank_labels", be.ptr(roots), int(roots.numel()), be.ptr(rootlab), int(own[0]), int(own[1]),
+            be.ptr(labels), be.stream())
+    if timings is not None:
+        timings.update(edges_local=n_e, edges_total=E, roots_total=int(roots.numel()))
+    return labels[:n_own], plan.core[own[0]:own[1]]
