@@ -344,6 +344,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"                        # the version banner goes to stdout: keep it to one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     be = lib()                                                      # raises without librhccq.so / a B200
     B, H, W, tile, desc = WORKLOADS[args.workload]

@@ -42,7 +42,8 @@ extern "C" {
 #define RHCCQ_ERR_UPSTREAM (-2)      /* an input counter was already negative, or the random table is too short */
 #define RHCCQ_ERR_INDEX_WIDTH (-3)   /* more palette rows than the index type can address */
 #define RHCCQ_ERR_MINIBATCH (-4)     /* >= 10000 non-black colours: the reference switches to MiniBatchKMeans
-                                        (encoder/compression/clustering.py:207-218), not built yet */
+                                        (encoder/compression/clustering.py:207-218); rhccq_palette_dbscan marks
+                                        the palette with this status and rhccq_palette_minibatch clusters it */
 
 int rhccq_abi_version(void);
 const char* rhccq_last_error(void);
@@ -103,6 +104,17 @@ int rhccq_palette_dbscan(const uint32_t* pal_keys, const int32_t* pal_off, const
                          const int32_t* thr, const int32_t* tie, const double* eps, int n_problems,
                          int32_t* labels, int32_t* n_clusters, int max_rows, int max_slots,
                          void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ a3, >= 10 000 colours: MiniBatchKMeans
+ * Replaces MiniBatchKMeans(n_clusters=ceil(n*q/100/10), batch_size=1000, random_state=42, n_init='auto')
+ * .fit_predict(non_black.astype(float)) at clustering.py:207-218 for every palette whose n_clusters[p] is
+ * RHCCQ_ERR_MINIBATCH (as rhccq_palette_dbscan leaves it), in the exact arithmetic of
+ * oracle/minibatch_restated.py.  labels[row] = cluster of the row (-2 for black rows), n_clusters[p] =
+ * number of centres; other palettes are not touched.  quality: double [n_problems] on the device. */
+size_t rhccq_palette_minibatch_workspace_bytes(int max_rows, int n_problems);
+int rhccq_palette_minibatch(const uint32_t* pal_keys, const int32_t* pal_off, const int32_t* pal_cnt,
+                            const double* quality, int n_problems, int32_t* labels, int32_t* n_clusters, int max_rows,
+                            void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ a3/a4: cluster -> new palette rows
  * Replaces clustering.py:253-355 and split_large_cluster (:720-775): black rows first, clusters of at

@@ -14,8 +14,9 @@ requirements.txt:6): ``DBSCAN`` and ``KMeans``.  Both are restated here
 switched to scikit-learn itself (``dbscan_impl='sklearn'``,
 ``kmeans_impl='sklearn'``) so that the tests can tell a disagreement of the
 restatement from a disagreement of the product.  ``MiniBatchKMeans`` (the
->= 10 000-colour branch, clustering.py:207-218) is only available through
-scikit-learn.
+>= 10 000-colour branch, clustering.py:207-218) is restated in
+``oracle/minibatch_restated.py`` (``minibatch_impl='sklearn'`` switches to
+scikit-learn).
 """
 from __future__ import annotations
 
@@ -24,7 +25,7 @@ from typing import Callable, Sequence
 
 import numpy as np
 
-from . import kmeans_restated
+from . import kmeans_restated, minibatch_restated
 
 BLACK_KEY = 0
 
@@ -313,7 +314,8 @@ def split_large_cluster(ids: np.ndarray, colors: np.ndarray, max_cpc: int,
 def cluster_palette_colors_parallel(quality, compressed_data: dict, eps=10.0, min_samples=2,
                                     max_colors_per_cluster=5, num_workers=None, *,
                                     dbscan_impl: str = "restated",
-                                    kmeans_impl: str | Callable = "restated") -> dict:
+                                    kmeans_impl: str | Callable = "restated",
+                                    minibatch_impl: str | Callable = "restated") -> dict:
     """encoder/compression/clustering.py:160-437.
 
     Large clusters are consumed in submission order (ascending DBSCAN label);
@@ -331,13 +333,18 @@ def cluster_palette_colors_parallel(quality, compressed_data: dict, eps=10.0, mi
         return compressed_data
     nb_pal = palette[non_black]
     if non_black.size >= 10000:                                                          # :207-218
-        from sklearn.cluster import MiniBatchKMeans
-        import warnings
         n_clusters = math.ceil(len(nb_pal) * (quality / 100) / 10)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            labels = MiniBatchKMeans(n_clusters=n_clusters, batch_size=1000, random_state=42,
-                                     n_init="auto").fit_predict(nb_pal.astype(float))
+        if minibatch_impl == "sklearn":
+            from sklearn.cluster import MiniBatchKMeans
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                labels = MiniBatchKMeans(n_clusters=n_clusters, batch_size=1000, random_state=42,
+                                         n_init="auto").fit_predict(nb_pal.astype(float))
+        elif callable(minibatch_impl):
+            labels = minibatch_impl(nb_pal, n_clusters)
+        else:
+            labels = minibatch_restated.minibatch_labels(nb_pal, n_clusters)
     elif dbscan_impl == "sklearn":
         labels = _dbscan_sklearn(nb_pal, eps, min_samples)                               # :233-235
     else:

@@ -39,6 +39,8 @@ SIGNATURES = {
     "rhccq_unique_index": (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "rhccq_cluster_params": (_I, [_P, _P, _I, _P, _P]),
     "rhccq_palette_dbscan": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P, _Z, _P]),
+    "rhccq_palette_minibatch_workspace_bytes": (_Z, [_I, _I]),
+    "rhccq_palette_minibatch": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _P, _Z, _P]),
     "rhccq_palette_split": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _P, _Z, _P]),
     "rhccq_palette_finish": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _P, _Z, _P]),
     "rhccq_remap_first": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P]),

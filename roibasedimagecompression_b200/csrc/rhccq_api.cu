@@ -167,6 +167,26 @@ int rhccq_palette_dbscan(const uint32_t* pal_keys, const int32_t* pal_off, const
     return rhccq_after_launch("rhccq_palette_dbscan");
 }
 
+size_t rhccq_palette_minibatch_workspace_bytes(int max_rows, int n_problems) {
+    // status copy + centres of every palette + one working slice per CTA (at most one per SM and per palette)
+    if (max_rows < 1 || n_problems < 1) return 0;
+    const size_t kmax = (size_t)max_rows / 10 + 2;
+    int slices = n_problems < rhccq_sm_count() ? n_problems : rhccq_sm_count();
+    return rhccq_carve_bytes((size_t)n_problems + 4, 4) + rhccq_carve_bytes((size_t)n_problems * 3 * kmax, 8)
+           + (size_t)slices * rhccq_palette_minibatch_ws_bytes(max_rows);
+}
+
+int rhccq_palette_minibatch(const uint32_t* pal_keys, const int32_t* pal_off, const int32_t* pal_cnt,
+                            const double* quality, int n_problems, int32_t* labels, int32_t* n_clusters, int max_rows,
+                            void* ws, size_t ws_bytes, void* stream) {
+    RHCCQ_REQUIRE(pal_keys && pal_off && pal_cnt && quality && labels && n_clusters && ws, "rhccq_palette_minibatch");
+    RHCCQ_REQUIRE(n_problems >= 0 && max_rows >= 1, "rhccq_palette_minibatch");
+    rhccq_palette_batch Bt = {pal_keys, pal_off, pal_cnt, nullptr, nullptr, nullptr, n_problems};
+    rhccq_launch_ws lw = {(unsigned char*)ws, ws_bytes};
+    if (rhccq_launch_palette_minibatch(Bt, quality, labels, n_clusters, max_rows, lw, stream) != 0) return -1;
+    return rhccq_after_launch("rhccq_palette_minibatch");
+}
+
 int rhccq_palette_split(const uint32_t* pal_keys, const int32_t* pal_off, const int32_t* pal_cnt, int n_problems,
                         const int32_t* labels, const int32_t* n_clusters, const int32_t* max_cpc, const double* rng,
                         int rng_len, int32_t* leaf, int32_t* n_leaves, int max_rows, void* ws, size_t ws_bytes,

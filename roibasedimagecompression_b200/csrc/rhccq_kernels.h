@@ -65,6 +65,9 @@ size_t rhccq_merge_level_ws_bytes(int max_entries, int max_comps);
 
 int rhccq_launch_palette_dbscan(const rhccq_palette_batch& B, int* labels, int* n_clusters, int max_rows,
                                 int max_slots, rhccq_launch_ws ws, void* stream);
+size_t rhccq_palette_minibatch_ws_bytes(int max_rows);
+int rhccq_launch_palette_minibatch(const rhccq_palette_batch& B, const double* quality, int* labels, int* n_clusters,
+                                   int max_rows, rhccq_launch_ws ws, void* stream);
 int rhccq_launch_palette_split(const rhccq_palette_batch& B, const int* labels, const int* status_in, const int* max_cpc,
                                const double* rng, int rng_len, int* leaf, int* n_leaves, int max_rows,
                                rhccq_launch_ws ws, void* stream);

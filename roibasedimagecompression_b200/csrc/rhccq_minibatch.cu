@@ -1,0 +1,429 @@
+// The >= 10 000-colour branch of the palette clustering:
+//   MiniBatchKMeans(n_clusters=ceil(n*q/100/10), batch_size=1000, random_state=42, n_init='auto')
+//       .fit_predict(non_black_colours.astype(float))
+// (/root/reference/encoder/compression/clustering.py:207-218), in the exact arithmetic and with the exact
+// consumption of the RandomState(42) stream of oracle/minibatch_restated.py (which cites the scikit-learn
+// lines: _kmeans.py:2056-2229, :1566-1684, :1974-2054, _k_means_minibatch.pyx:68-118).
+//
+// Shape of the work: a handful of palettes per batch (stage 2 of large images), each a strictly sequential
+// chain of ~50-100 mini-batch steps on 1000 points, preceded by a k-means++ seeding on 3000 points and
+// followed by one assignment of all n colours.  One CTA walks the chain of a palette (the Mersenne Twister,
+// numpy's randint / choice / shuffle and the inertia sum are sequential by definition and run on thread 0);
+// the final assignment, which is the only part proportional to n*k, is a separate kernel over all SMs.
+#include "rhccq_common.cuh"
+#include "rhccq_kernels.h"
+
+#define RHCCQ_MB_THREADS 512
+#define RHCCQ_MB_BATCH 1000
+#define RHCCQ_MB_MAXT 12
+
+// ---------------------------------------------------------------- MT19937 as numpy.random.RandomState(42)
+struct rhccq_mt { uint32_t* s; int* pos; };
+__device__ __forceinline__ void rhccq_mt_seed(const rhccq_mt& m, uint32_t seed) {     // init_genrand
+    m.s[0] = seed;
+    for (int i = 1; i < 624; ++i) m.s[i] = 1812433253u * (m.s[i - 1] ^ (m.s[i - 1] >> 30)) + (uint32_t)i;
+    *m.pos = 624;
+}
+__device__ __forceinline__ uint32_t rhccq_mt_next(const rhccq_mt& m) {
+    if (*m.pos >= 624) {
+        for (int k = 0; k < 624; ++k) {
+            const uint32_t y = (m.s[k] & 0x80000000u) | (m.s[(k + 1) % 624] & 0x7fffffffu);
+            m.s[k] = m.s[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        *m.pos = 0;
+    }
+    uint32_t y = m.s[(*m.pos)++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+}
+__device__ __forceinline__ double rhccq_mt_double(const rhccq_mt& m) {                // random_sample
+    const uint32_t a = rhccq_mt_next(m) >> 5, b = rhccq_mt_next(m) >> 6;
+    return __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+}
+__device__ __forceinline__ uint32_t rhccq_mt_below(const rhccq_mt& m, uint32_t max) {  // uniform in [0, max], masked rejection
+    if (max == 0) return 0;
+    uint32_t mask = max;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    uint32_t v;
+    while ((v = (rhccq_mt_next(m) & mask)) > max) {}
+    return v;
+}
+
+__device__ __forceinline__ double rhccq_mb_dist(double x0, double x1, double x2, const double* c) {
+    const double d0 = __dsub_rn(x0, c[0]), d1 = __dsub_rn(x1, c[1]), d2 = __dsub_rn(x2, c[2]);
+    return __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+}
+
+// number of clusters: ceil(n * (q / 100) / 10) as Python evaluates it (clustering.py:210)
+__host__ __device__ static inline int rhccq_mb_k(int n, double q) {
+    return (int)ceil(((double)n * (q / 100.0)) / 10.0);
+}
+__host__ __device__ static inline int rhccq_mb_init_size(int n, int k) {
+    int batch = n < RHCCQ_MB_BATCH ? n : RHCCQ_MB_BATCH;
+    long long s = 3LL * batch;
+    if (s < k) s = 3LL * k;
+    return (int)(s < n ? s : n);
+}
+
+struct rhccq_mb_ws {
+    int* nb;                 // [n] rows of the non-black colours
+    double* cdf;             // [n]
+    int* sub;                // [init] rows (in nb order) of the init subset; later the batch
+    uint32_t* closest;       // [init]
+    unsigned long long* cum; // [init]
+    double* center;          // [3k]
+    double* center_new;      // [3k]
+    double* counts;          // [k]
+    unsigned long long* skey;// [pow2(k)]
+    int* flag;               // [k] to_reassign, then its exclusive scan
+    int* perm;               // [batch]
+};
+__host__ __device__ static inline size_t rhccq_mb_bytes(size_t n, size_t kmax, size_t init_max) {
+    size_t k2 = 1;
+    while (k2 < kmax) k2 <<= 1;
+    return rhccq_carve_bytes(n, 4) + rhccq_carve_bytes(n, 8) + rhccq_carve_bytes(init_max, 4) * 2 + rhccq_carve_bytes(init_max, 8)
+           + rhccq_carve_bytes(3 * kmax, 8) * 2 + rhccq_carve_bytes(kmax, 8) + rhccq_carve_bytes(k2, 8)
+           + rhccq_carve_bytes(kmax + 1, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 4);
+}
+size_t rhccq_palette_minibatch_ws_bytes(int max_rows) {
+    // k <= n / 10 (q <= 100); init subset <= max(3000, 3k)
+    const size_t n = (size_t)(max_rows > 1 ? max_rows : 1), kmax = n / 10 + 2;
+    const size_t init = 3 * kmax > 3 * RHCCQ_MB_BATCH ? 3 * kmax : 3 * RHCCQ_MB_BATCH;
+    return rhccq_mb_bytes(n, kmax, init < n ? init : n);
+}
+
+__device__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, const double* __restrict__ quality,
+                                        int* __restrict__ n_clusters, int max_rows, unsigned char* wsbase,
+                                        double* __restrict__ centers_out) {
+    __shared__ uint32_t s_mt[624];
+    __shared__ int s_mtpos;
+    __shared__ int s_i[RHCCQ_MAX_WARPS + 2 + 16];
+    __shared__ long long s_ll[RHCCQ_MAX_WARPS * RHCCQ_MB_MAXT + 2];
+    __shared__ double s_d[RHCCQ_MAX_WARPS + 2];
+    __shared__ int s_lab[RHCCQ_MB_BATCH];
+    __shared__ double s_own[RHCCQ_MB_BATCH];
+    __shared__ int s_cand[RHCCQ_MB_MAXT];
+    __shared__ int s_flag, s_nre;
+    __shared__ double s_val;
+    const int n_all = B.pal_cnt[p];
+    const uint32_t* keys = B.pal_keys + B.pal_off[p];
+    if (n_all > max_rows) { if (threadIdx.x == 0) n_clusters[p] = -1; return; }
+    const size_t kmax = (size_t)max_rows / 10 + 2;
+    size_t init_max = 3 * kmax > 3 * RHCCQ_MB_BATCH ? 3 * kmax : 3 * RHCCQ_MB_BATCH;
+    if (init_max > (size_t)max_rows) init_max = (size_t)max_rows;
+    rhccq_mb_ws W;
+    {
+        rhccq_carver cv(wsbase);
+        size_t k2 = 1;
+        while (k2 < kmax) k2 <<= 1;
+        W.nb = cv.take<int>(max_rows);
+        W.cdf = cv.take<double>(max_rows);
+        W.sub = cv.take<int>(init_max);
+        W.closest = cv.take<uint32_t>(init_max);
+        W.cum = cv.take<unsigned long long>(init_max);
+        W.center = cv.take<double>(3 * kmax);
+        W.center_new = cv.take<double>(3 * kmax);
+        W.counts = cv.take<double>(kmax);
+        W.skey = cv.take<unsigned long long>(k2);
+        W.flag = cv.take<int>(kmax + 1);
+        W.perm = cv.take<int>(RHCCQ_MB_BATCH);
+    }
+    // non-black rows in row order (clustering.py:185-192)
+    int* mark = reinterpret_cast<int*>(W.cdf);                      // n ints fit into n doubles
+    RHCCQ_PAR_FOR(i, n_all) mark[i] = keys[i] != 0u ? 1 : 0;
+    __syncthreads();
+    const int n = rhccq_block_excl_scan_array<int>(mark, n_all, s_i);
+    RHCCQ_PAR_FOR(i, n_all) if (keys[i] != 0u) W.nb[mark[i]] = i;
+    __syncthreads();
+    const int k = rhccq_mb_k(n, quality[p]);
+    if (k < 1 || k > n || (size_t)k > kmax - 1) { if (threadIdx.x == 0) n_clusters[p] = -1; return; }
+    const int batch = n < RHCCQ_MB_BATCH ? n : RHCCQ_MB_BATCH;
+    const int init_size = rhccq_mb_init_size(n, k);
+    const rhccq_mt mt = {s_mt, &s_mtpos};
+    // ---- RandomState(42); validation indices are drawn and dropped (n_init == 1); init subset
+    if (threadIdx.x == 0) {
+        rhccq_mt_seed(mt, 42u);
+        for (int i = 0; i < init_size; ++i) rhccq_mt_below(mt, (uint32_t)(n - 1));              // _kmeans.py:2110
+        if (init_size < n) for (int i = 0; i < init_size; ++i) W.sub[i] = (int)rhccq_mt_below(mt, (uint32_t)(n - 1));
+    }
+    if (init_size >= n) RHCCQ_PAR_FOR(i, n) W.sub[i] = i;
+    __syncthreads();
+    const int ns = init_size;
+#define RHCCQ_MB_X(j) keys[W.nb[W.sub[j]]]
+    // ---- k-means++ on the subset (_kmeans.py:216-282): first centre by choice(ns, p=uniform)
+    if (threadIdx.x == 0) {
+        // cdf = cumsum(ones / ns) / last;  searchsorted(cdf, u, side='right')
+        const double pi = __ddiv_rn(1.0, (double)ns);
+        double run = 0.0;
+        for (int i = 0; i < ns; ++i) { run = __dadd_rn(run, pi); W.cdf[i] = run; }
+        const double last = W.cdf[ns - 1];
+        const double u = rhccq_mt_double(mt);
+        int lo = 0, hi = ns;                                       // first i with cdf[i] / last > u
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ddiv_rn(W.cdf[mid], last) <= u) lo = mid + 1; else hi = mid; }
+        s_cand[0] = lo < ns - 1 ? lo : ns - 1;
+    }
+    __syncthreads();
+    const int T = 2 + (k >= 3) + (k >= 8) + (k >= 21) + (k >= 55) + (k >= 149) + (k >= 404) + (k >= 1097) + (k >= 2981)
+                  + (k >= 8104) + (k >= 22027);
+    long long pot;
+    {
+        const uint32_t cf = RHCCQ_MB_X(s_cand[0]);
+        long long part = 0;
+        RHCCQ_PAR_FOR(j, ns) { const uint32_t d = (uint32_t)rhccq_d2(RHCCQ_MB_X(j), cf); W.closest[j] = d; part += d; }
+        pot = rhccq_block_sum<long long>(part, s_ll);
+        RHCCQ_PAR_FOR(q, 3) W.center[q] = (double)((cf >> (16 - 8 * q)) & 255u);
+    }
+    for (int c = 1; c < k; ++c) {
+        RHCCQ_PAR_FOR(j, ns) W.cum[j] = W.closest[j];
+        __syncthreads();
+        rhccq_block_excl_scan_array<unsigned long long>(W.cum, ns, reinterpret_cast<unsigned long long*>(s_ll));
+        if (threadIdx.x == 0) {
+            for (int t = 0; t < T; ++t) {
+                const double rv = __dmul_rn(rhccq_mt_double(mt), (double)pot);
+                int lo = 0, hi = ns;                               // first j with inclusive cum[j] >= rv
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((double)(W.cum[mid] + W.closest[mid]) < rv) lo = mid + 1; else hi = mid;
+                }
+                s_cand[t] = lo < ns - 1 ? lo : ns - 1;
+            }
+        }
+        __syncthreads();
+        int best = 0;
+        long long best_pot = 0;
+        for (int t = 0; t < T; ++t) {
+            const uint32_t cc = RHCCQ_MB_X(s_cand[t]);
+            long long ps = 0;
+            RHCCQ_PAR_FOR(j, ns) { const uint32_t d = (uint32_t)rhccq_d2(RHCCQ_MB_X(j), cc), o = W.closest[j]; ps += d < o ? d : o; }
+            const long long tot = rhccq_block_sum<long long>(ps, s_ll);
+            if (t == 0 || tot < best_pot) { best_pot = tot; best = t; }
+        }
+        const uint32_t cs = RHCCQ_MB_X(s_cand[best]);
+        __syncthreads();
+        RHCCQ_PAR_FOR(j, ns) { const uint32_t d = (uint32_t)rhccq_d2(RHCCQ_MB_X(j), cs); if (d < W.closest[j]) W.closest[j] = d; }
+        RHCCQ_PAR_FOR(q, 3) W.center[3 * c + q] = (double)((cs >> (16 - 8 * q)) & 255u);
+        pot = best_pot;
+        __syncthreads();
+    }
+#undef RHCCQ_MB_X
+    // ---- mini-batch steps (_kmeans.py:2160-2215)
+    RHCCQ_PAR_FOR(q, k) W.counts[q] = 0.0;
+    if (threadIdx.x == 0) {                                         // cdf of choice(n, batch, p=ones/n)
+        const double pi = __ddiv_rn(1.0, (double)n);
+        double run = 0.0;
+        for (int i = 0; i < n; ++i) { run = __dadd_rn(run, pi); W.cdf[i] = run; }
+    }
+    __syncthreads();
+    const double cdf_last = W.cdf[n - 1];
+    const long long n_steps = (100LL * n) / batch;
+    int n_since = 0, no_improvement = 0;
+    bool have_ewa = false, have_min = false;
+    double ewa = 0.0, ewa_min = 0.0;
+    int* bidx = W.sub;                                              // the batch's rows (nb order); the subset is dead
+    for (long long step = 0; step < n_steps; ++step) {
+        if (threadIdx.x == 0) for (int i = 0; i < batch; ++i) s_own[i] = rhccq_mt_double(mt);     // uniform_samples
+        __syncthreads();
+        RHCCQ_PAR_FOR(i, batch) {
+            const double u = s_own[i];
+            int lo = 0, hi = n;                                    // searchsorted(cdf / last, u, side='right')
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ddiv_rn(W.cdf[mid], cdf_last) <= u) lo = mid + 1; else hi = mid; }
+            bidx[i] = lo < n ? lo : n - 1;
+        }
+        // _random_reassign (:2039-2054)
+        n_since += batch;
+        int zero = 0;
+        RHCCQ_PAR_FOR(q, k) if (W.counts[q] == 0.0) zero = 1;
+        zero = rhccq_block_or(zero, s_i);
+        const bool reassign = zero || n_since >= 10 * k;
+        if (reassign) n_since = 0;
+        __syncthreads();
+        // labels and distances of the batch
+        RHCCQ_PAR_FOR(i, batch) {
+            const uint32_t c = keys[W.nb[bidx[i]]];
+            const double x0 = (double)rhccq_key_r(c), x1 = (double)rhccq_key_g(c), x2 = (double)rhccq_key_b(c);
+            double bd = rhccq_mb_dist(x0, x1, x2, W.center);
+            int bi = 0;
+            for (int q = 1; q < k; ++q) { const double d = rhccq_mb_dist(x0, x1, x2, W.center + 3 * q); if (d < bd) { bd = d; bi = q; } }
+            s_lab[i] = bi; s_own[i] = bd;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {                                     // inertia in batch order
+            double in = 0.0;
+            for (int i = 0; i < batch; ++i) in = __dadd_rn(in, s_own[i]);
+            s_val = in;
+        }
+        // centre update, members in batch order (_k_means_minibatch.pyx:68-118)
+        RHCCQ_PAR_FOR(q, k) {
+            int members = 0;
+            for (int i = 0; i < batch; ++i) members += s_lab[i] == q;
+            if (members > 0) {
+                const double w = W.counts[q];
+                double c0 = __dmul_rn(W.center[3 * q], w), c1 = __dmul_rn(W.center[3 * q + 1], w), c2 = __dmul_rn(W.center[3 * q + 2], w);
+                for (int i = 0; i < batch; ++i) if (s_lab[i] == q) {
+                    const uint32_t c = keys[W.nb[bidx[i]]];
+                    c0 = __dadd_rn(c0, (double)rhccq_key_r(c)); c1 = __dadd_rn(c1, (double)rhccq_key_g(c)); c2 = __dadd_rn(c2, (double)rhccq_key_b(c));
+                }
+                const double wn = __dadd_rn(w, (double)members);
+                const double alpha = __ddiv_rn(1.0, wn);
+                W.counts[q] = wn;
+                W.center_new[3 * q] = __dmul_rn(c0, alpha); W.center_new[3 * q + 1] = __dmul_rn(c1, alpha); W.center_new[3 * q + 2] = __dmul_rn(c2, alpha);
+            } else {
+                W.center_new[3 * q] = W.center[3 * q]; W.center_new[3 * q + 1] = W.center[3 * q + 1]; W.center_new[3 * q + 2] = W.center[3 * q + 2];
+            }
+        }
+        __syncthreads();
+        const double inertia = s_val;
+        if (reassign) {                                             // :1652-1682
+            double mx = 0.0;
+            RHCCQ_PAR_FOR(q, k) if (W.counts[q] > mx) mx = W.counts[q];
+            mx = rhccq_block_max<double>(mx, s_d);
+            const double lim = __dmul_rn(0.01, mx);
+            int cnt = 0;
+            RHCCQ_PAR_FOR(q, k) { const int f = W.counts[q] < lim ? 1 : 0; W.flag[q] = f; cnt += f; }
+            cnt = rhccq_block_sum<int>(cnt, s_i);
+            if ((double)cnt > 0.5 * (double)batch) {
+                // keep all but the int(0.5 * batch) smallest counts (stable order: ties by index)
+                int k2 = 1;
+                while (k2 < k) k2 <<= 1;
+                for (int q = threadIdx.x; q < k2; q += blockDim.x)
+                    W.skey[q] = q < k ? (((unsigned long long)(long long)W.counts[q] << 24) | (unsigned)q) : ~0ull;
+                __syncthreads();
+                rhccq_block_bitonic_sort<unsigned long long>(W.skey, k2);
+                const int first_kept = (int)(0.5 * (double)batch);
+                RHCCQ_PAR_FOR(r, k) if (r >= first_kept) W.flag[(int)(W.skey[r] & 0xffffffu)] = 0;
+                __syncthreads();
+                cnt = 0;
+                RHCCQ_PAR_FOR(q, k) cnt += W.flag[q];
+                cnt = rhccq_block_sum<int>(cnt, s_i);
+            }
+            __syncthreads();
+            if (cnt > 0) {
+                if (threadIdx.x == 0) {                             // choice(batch, replace=False, size=cnt) == permutation(batch)[:cnt]
+                    for (int i = 0; i < batch; ++i) W.perm[i] = i;
+                    for (int i = batch - 1; i >= 1; --i) {
+                        const int j = (int)rhccq_mt_below(mt, (uint32_t)i);
+                        const int t = W.perm[i]; W.perm[i] = W.perm[j]; W.perm[j] = t;
+                    }
+                }
+                // rank of every flagged centre among the flagged ones, ascending
+                int* rank = reinterpret_cast<int*>(W.skey);
+                RHCCQ_PAR_FOR(q, k) rank[q] = W.flag[q];
+                __syncthreads();
+                rhccq_block_excl_scan_array<int>(rank, k, s_i);
+                RHCCQ_PAR_FOR(q, k) if (W.flag[q]) {
+                    const uint32_t c = keys[W.nb[bidx[W.perm[rank[q]]]]];
+                    W.center_new[3 * q] = (double)rhccq_key_r(c); W.center_new[3 * q + 1] = (double)rhccq_key_g(c); W.center_new[3 * q + 2] = (double)rhccq_key_b(c);
+                }
+            }
+            double mn = 1.0e300;
+            RHCCQ_PAR_FOR(q, k) if (!W.flag[q] && W.counts[q] < mn) mn = W.counts[q];
+            mn = rhccq_block_min<double>(mn, s_d);
+            if (mn < 1.0e300) RHCCQ_PAR_FOR(q, k) if (W.flag[q]) W.counts[q] = mn;
+            __syncthreads();
+        }
+        { double* t = W.center; W.center = W.center_new; W.center_new = t; }
+        __syncthreads();
+        // _mini_batch_convergence (:1974-2037), tol == 0
+        const double bi = __ddiv_rn(inertia, (double)batch);
+        if (step == 0) continue;
+        if (!have_ewa) { ewa = bi; have_ewa = true; }
+        else {
+            double alpha = __ddiv_rn(__dmul_rn((double)batch, 2.0), (double)(n + 1));
+            if (alpha > 1.0) alpha = 1.0;
+            ewa = __dadd_rn(__dmul_rn(ewa, __dsub_rn(1.0, alpha)), __dmul_rn(bi, alpha));
+        }
+        if (!have_min || ewa < ewa_min) { no_improvement = 0; ewa_min = ewa; have_min = true; }
+        else ++no_improvement;
+        if (no_improvement >= 10) break;
+    }
+    __syncthreads();
+    RHCCQ_PAR_FOR(q, 3 * k) centers_out[q] = W.center[q];
+    if (threadIdx.x == 0) n_clusters[p] = k;
+}
+
+// status -4 (set by rhccq_k_palette_dbscan) selects the palettes of this branch
+__global__ void __launch_bounds__(RHCCQ_MB_THREADS)
+rhccq_k_palette_minibatch(rhccq_palette_batch B, const double* __restrict__ quality, int* __restrict__ n_clusters,
+                          int max_rows, unsigned char* gws, size_t gws_stride, double* __restrict__ centers,
+                          size_t centers_stride, int* __restrict__ todo) {
+    __shared__ int s_p;
+    while (true) {
+        if (threadIdx.x == 0) {
+            // next palette that needs the branch: a grid-wide cursor keeps one workspace slice per CTA enough
+            int p;
+            while ((p = atomicAdd(todo, 1)) < B.n_problems && n_clusters[p] != -4) {}
+            s_p = p;
+        }
+        __syncthreads();
+        const int p = s_p;
+        __syncthreads();
+        if (p >= B.n_problems) return;
+        rhccq_minibatch_problem(B, p, quality, n_clusters, max_rows, gws + (size_t)blockIdx.x * gws_stride,
+                                centers + (size_t)p * centers_stride);
+        __syncthreads();
+    }
+}
+
+// labels of all non-black rows: nearest of the palette's k centres, first minimum
+__global__ void __launch_bounds__(RHCCQ_PIXEL_THREADS)
+rhccq_k_minibatch_assign(rhccq_palette_batch B, const int* __restrict__ n_clusters_before, const int* __restrict__ n_clusters,
+                         const double* __restrict__ centers, size_t centers_stride, int* __restrict__ labels, int chunks) {
+    for (int w = blockIdx.x; w < B.n_problems * chunks; w += gridDim.x) {
+        const int p = w / chunks, ch = w % chunks;
+        if (n_clusters_before[p] != -4 || n_clusters[p] <= 0) continue;
+        const int n = B.pal_cnt[p], k = n_clusters[p];
+        const uint32_t* keys = B.pal_keys + B.pal_off[p];
+        int* lab = labels + B.pal_off[p];
+        const double* C = centers + (size_t)p * centers_stride;
+        const int per = (n + chunks - 1) / chunks;
+        const int lo = ch * per, hi = lo + per < n ? lo + per : n;
+        for (int i = lo + (int)threadIdx.x; i < hi; i += (int)blockDim.x) {
+            const uint32_t c = keys[i];
+            if (c == 0u) { lab[i] = -2; continue; }
+            const double x0 = (double)rhccq_key_r(c), x1 = (double)rhccq_key_g(c), x2 = (double)rhccq_key_b(c);
+            double bd = rhccq_mb_dist(x0, x1, x2, C);
+            int bi = 0;
+            for (int q = 1; q < k; ++q) { const double d = rhccq_mb_dist(x0, x1, x2, C + 3 * q); if (d < bd) { bd = d; bi = q; } }
+            lab[i] = bi;
+        }
+    }
+}
+
+int rhccq_launch_palette_minibatch(const rhccq_palette_batch& B, const double* quality, int* labels, int* n_clusters,
+                                   int max_rows, rhccq_launch_ws ws, void* stream) {
+    if (B.n_problems <= 0) return 0;
+    const size_t slice = rhccq_palette_minibatch_ws_bytes(max_rows);
+    const size_t kmax = (size_t)max_rows / 10 + 2;
+    const size_t cstride = 3 * kmax;
+    // workspace: [todo cursor + copy of the status vector][centres of every palette][one slice per CTA]
+    const size_t head = rhccq_carve_bytes((size_t)B.n_problems + 4, 4);
+    const size_t cbytes = rhccq_carve_bytes((size_t)B.n_problems * cstride, 8);
+    if (!ws.ws || ws.ws_bytes < head + cbytes + slice) {
+        rhccq_set_error("rhccq_palette_minibatch: workspace of %zu bytes is smaller than %zu", ws.ws_bytes, head + cbytes + slice);
+        return -1;
+    }
+    int grid = (int)((ws.ws_bytes - head - cbytes) / slice);
+    if (grid > B.n_problems) grid = B.n_problems;
+    const int cap = rhccq_sm_count();
+    if (grid > cap) grid = cap;
+    int* todo = (int*)ws.ws;
+    int* before = todo + 4;
+    double* centers = (double*)(ws.ws + head);
+    unsigned char* slices = ws.ws + head + cbytes;
+#ifdef RHCCQ_HOST_EMU
+    memset(todo, 0, 16);
+    memcpy(before, n_clusters, (size_t)B.n_problems * 4);
+#else
+    cudaMemsetAsync(todo, 0, 16, (cudaStream_t)stream);
+    cudaMemcpyAsync(before, n_clusters, (size_t)B.n_problems * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+#endif
+    RHCCQ_LAUNCH(rhccq_k_palette_minibatch, grid, RHCCQ_MB_THREADS, 0, (cudaStream_t)stream, B, quality, n_clusters, max_rows,
+                 slices, slice, centers, cstride, todo);
+    const int chunks = 64;
+    int g2 = B.n_problems * chunks;
+    const int cap2 = rhccq_sm_count() * 8;
+    if (g2 > cap2) g2 = cap2;
+    RHCCQ_LAUNCH(rhccq_k_minibatch_assign, g2, RHCCQ_PIXEL_THREADS, 0, (cudaStream_t)stream, B, before, n_clusters, centers, cstride,
+                 labels, chunks);
+    return 0;
+}

@@ -83,7 +83,7 @@ def compute_clustering_params(n_colors, quality, color_space="rgb"):
     return eps, min_samples, max_colors_per_cluster
 
 
-def _cluster_device(be, keys_np: np.ndarray, eps: float, max_cpc: int, leaf_override=None):
+def _cluster_device(be, keys_np: np.ndarray, eps: float, max_cpc: int, leaf_override=None, quality: float = 0.0):
     """Run a3' + a3/a4 + means for one palette; returns (labels, leaf, n_leaves, new_keys) as numpy."""
     n = len(keys_np)
     dev = be.device
@@ -96,6 +96,9 @@ def _cluster_device(be, keys_np: np.ndarray, eps: float, max_cpc: int, leaf_over
         be, keys, off, cnt, torch.tensor([thr], dtype=torch.int32, device=dev),
         torch.tensor([tie], dtype=torch.int32, device=dev), torch.tensor([float(eps)], dtype=torch.float64, device=dev),
         max_rows=n, max_slots=slots)
+    if n >= 10000:                                                   # clustering.py:207-218 may apply
+        ops.palette_minibatch(be, keys, off, cnt, torch.tensor([float(quality)], dtype=torch.float64, device=dev),
+                              labels, ncl, max_rows=n)
     ops.check_counts("cluster_palette_colors_parallel (DBSCAN)", ncl[:1])
     if leaf_override is None:
         mc = torch.tensor([int(max_cpc)], dtype=torch.int32, device=dev)
@@ -138,7 +141,8 @@ def cluster_palette_colors_parallel(quality, compressed_data, eps=10.0, min_samp
     if len(np.unique(keys)) != n_orig:
         raise ValueError("palette rows must be distinct (true for every reference call site: the output of "
                          "get_all_unique_colors and of merge_region_components_simple)")
-    _, leaf, m, new_keys = _cluster_device(be, keys, float(eps), int(max_colors_per_cluster), leaf_override)
+    _, leaf, m, new_keys = _cluster_device(be, keys, float(eps), int(max_colors_per_cluster), leaf_override,
+                                           quality=float(quality))
     new_palette = _keys_to_rgb(new_keys)
     lut = leaf.astype(np.uint16)                                                       # :373 (uint16 table)
     new_indices = lut[indices.astype(np.int64).ravel()].astype(np.int64)              # :377

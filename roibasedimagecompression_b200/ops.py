@@ -73,6 +73,16 @@ def palette_dbscan(be: Backend, pal_keys, pal_off, pal_cnt, thr, tie, eps, *, ma
     return labels, ncl
 
 
+def palette_minibatch(be: Backend, pal_keys, pal_off, pal_cnt, quality, labels, n_clusters, *, max_rows: int):
+    """a3, >= 10 000 colours — rhccq_palette_minibatch; labels / n_clusters of the palettes that
+    rhccq_palette_dbscan marked with status -4 are filled in place."""
+    P = pal_cnt.numel()
+    ws_bytes = int(be.cdll.rhccq_palette_minibatch_workspace_bytes(int(max_rows), int(P)))
+    ws = be.empty((max(ws_bytes, 1),), torch.uint8)
+    be.call("rhccq_palette_minibatch", be.ptr(pal_keys), be.ptr(pal_off), be.ptr(pal_cnt), be.ptr(quality), P,
+            be.ptr(labels), be.ptr(n_clusters), int(max_rows), be.ptr(ws), ws_bytes, be.stream(), launches=2)
+
+
 def palette_split(be: Backend, pal_keys, pal_off, pal_cnt, labels, n_clusters, max_cpc, *, max_rows: int):
     """a3/a4 — rhccq_palette_split.  Returns (leaf, n_leaves)."""
     P = pal_cnt.numel()
@@ -115,8 +125,11 @@ def cluster_palettes(be: Backend, pal_keys, pal_off, pal_cnt, quality, *, max_ro
     eps = _as_dev(be, eps_h, torch.float64)
     labels, ncl = palette_dbscan(be, pal_keys, pal_off, pal_cnt, thr, tie, eps, max_rows=max_rows,
                                  max_slots=max_slots)
+    q_dev = _as_dev(be, q, torch.float64)
+    if max_rows >= 10000:                                           # clustering.py:207: the MiniBatchKMeans branch can occur
+        palette_minibatch(be, pal_keys, pal_off, pal_cnt, q_dev, labels, ncl, max_rows=max_rows)
     if max_cpc is None:
-        max_cpc = cluster_params(be, pal_cnt, _as_dev(be, q, torch.float64))
+        max_cpc = cluster_params(be, pal_cnt, q_dev)
     leaf, nl = palette_split(be, pal_keys, pal_off, pal_cnt, labels, ncl, max_cpc, max_rows=max_rows)
     new_keys = palette_finish(be, pal_keys, pal_off, pal_cnt, leaf, nl, max_rows=max_rows)
     return {"labels": labels, "n_clusters": ncl, "leaf": leaf, "n_leaves": nl, "new_keys": new_keys,
@@ -196,6 +209,6 @@ def check_counts(name: str, counts) -> None:
         code = int(bad[0])
         why = {-1: "capacity bound exceeded", -2: "upstream error / random table too short",
                -3: "more palette rows than the index type can address",
-               -4: ">= 10000 non-black colours: the reference's MiniBatchKMeans branch "
-                   "(encoder/compression/clustering.py:207-218) is not built yet"}.get(code, "unknown")
+               -4: ">= 10000 non-black colours: the palette needs rhccq_palette_minibatch "
+                   "(encoder/compression/clustering.py:207-218) before the split"}.get(code, "unknown")
         raise RhccqError(f"{name}: {bad.numel()} problem(s) refused, first code {code} ({why})")

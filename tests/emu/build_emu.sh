@@ -6,6 +6,6 @@ src=$here/../../roibasedimagecompression_b200/csrc
 out=$here/_build
 mkdir -p "$out"
 g++ -O2 -g -std=c++17 -fPIC -shared -ffp-contract=off -DRHCCQ_HOST_EMU -x c++ \
-    "$src/rhccq_api.cu" "$src/rhccq_palette.cu" "$src/rhccq_split.cu" "$src/rhccq_points.cu" "$src/rhccq_pixels.cu" "$src/rhccq_merge.cu" \
+    "$src/rhccq_api.cu" "$src/rhccq_palette.cu" "$src/rhccq_split.cu" "$src/rhccq_minibatch.cu" "$src/rhccq_points.cu" "$src/rhccq_pixels.cu" "$src/rhccq_merge.cu" \
     -o "$out/librhccq_emu.so"
 echo "$out/librhccq_emu.so"

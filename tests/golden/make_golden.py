@@ -311,5 +311,42 @@ def main():
         print(f"  {name}: palette {len(arr_pal(final))}, psnr {float(d['psnr']):.2f} dB, stage sizes {sizes}")
 
 
+def main_minibatch():
+    """G7: the >= 10 000-colour branch (clustering.py:207-218): MiniBatchKMeans labels recorded."""
+    _orig_mb = sklearn.cluster.MiniBatchKMeans.fit_predict
+    log = {}
+
+    def _logged(self, X, y=None, sample_weight=None):
+        labels = _orig_mb(self, X, y, sample_weight)
+        log[km_key(X, self.n_clusters)] = np.asarray(labels).astype(np.int32)
+        return labels
+    sklearn.cluster.MiniBatchKMeans.fit_predict = _logged
+    ref_clustering.MiniBatchKMeans = sklearn.cluster.MiniBatchKMeans
+    d = {}
+    img = synth(256, 256, 3, sigma=3.0)
+    pal = np.unique(img.reshape(-1, 3), axis=0)
+    pal = pal[np.sort(np.random.default_rng(5).choice(len(pal), 10500, replace=False))]
+    pal = np.concatenate([np.zeros((1, 3), np.uint8), pal])
+    take_km_log()
+    for case, q in enumerate([10, 40]):
+        comp = {"palette": pal.tolist(), "indices": list(range(len(pal))), "shape": (1, len(pal)), "top_left": (0, 0)}
+        eps, ms, mcpc = ref_clustering.compute_clustering_params(len(pal), q, "lab")
+        with quiet():
+            r = ref_clustering.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=mcpc)
+        d[f"q{case}"] = np.array(q)
+        d[f"out_palette{case}"] = arr_pal(r)
+        d[f"out_indices{case}"] = arr_idx(r).astype(np.int32)
+    d["in_palette"] = pal
+    d["n_cases"] = np.array(2)
+    for k, v in take_km_log().items():
+        d["km_" + k] = v.astype(np.int16)
+    for k, v in log.items():
+        d["mb_" + k] = v.astype(np.int16)
+    save("minibatch_palette.npz", **d)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "minibatch":
+        main_minibatch()
+    else:
+        main()

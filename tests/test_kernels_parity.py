@@ -309,3 +309,26 @@ def test_split_kernel_stress_equals_oracle(backend, kind):
                                                 as_arrays=True)
         assert np.array_equal(got["palette"], want["palette"]), (kind, trial, n, q, m)
         assert np.array_equal(got["indices"], want["indices"]), (kind, trial, n, q, m)
+
+
+# --------------------------------------------------------------------------- >= 10 000 colours
+def _big_palette(seed, n):
+    img = synth(256, 256, seed, sigma=3.0)
+    pal = np.unique(img.reshape(-1, 3), axis=0)
+    assert len(pal) >= n
+    return pal[np.sort(np.random.default_rng(seed).choice(len(pal), n, replace=False))]
+
+
+@pytest.mark.parametrize("n,q,black", [(10000, 10, False), (12000, 40, True), (10003, 20, False)])
+def test_minibatch_branch_equals_restated_oracle(backend, n, q, black):
+    """clustering.py:207-218: MiniBatchKMeans for >= 10 000 non-black colours, then the usual split of
+    clusters larger than max_colors_per_cluster.  Kernel == oracle/minibatch_restated.py bit for bit."""
+    pal = _big_palette(11 + n, n)
+    if black:
+        pal = np.concatenate([np.zeros((1, 3), np.uint8), pal])
+    comp = {"palette": pal, "indices": np.arange(len(pal)), "shape": (1, len(pal)), "top_left": (0, 0)}
+    eps, _, m = O.compute_clustering_params(len(pal), q)
+    want = O.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m)
+    got = C.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m, as_arrays=True)
+    assert np.array_equal(got["palette"], want["palette"])
+    assert np.array_equal(got["indices"], want["indices"])

@@ -107,3 +107,42 @@ def test_kmeans_restated_seeding_and_agreement_with_sklearn():
             warnings.simplefilter("ignore")
             sk = KMeans(n_clusters=k, random_state=42, n_init="auto").fit_predict(X)
         assert (lab == sk).mean() > 0.9                                # ties / last-ulp differences only
+
+
+def test_minibatch_branch_with_sklearn_labels_injected():
+    """clustering.py:207-218 through the reference itself (tests/golden/make_golden.py minibatch): with
+    scikit-learn's recorded MiniBatchKMeans / KMeans labels injected the oracle reproduces the reference's
+    palette (order included) and indices."""
+    from conftest import km_key
+    g = golden("minibatch_palette.npz")
+    pal = g["in_palette"]
+    km = injected_kmeans(g)
+    mb_table = {k[3:]: g[k] for k in g.files if k.startswith("mb_")}
+
+    def mb(colors, k):
+        return np.asarray(mb_table[km_key(colors, k)]).astype(np.int64)
+    for c in range(int(g["n_cases"])):
+        q = int(g[f"q{c}"])
+        comp = {"palette": pal, "indices": np.arange(len(pal)), "shape": (1, len(pal)), "top_left": (0, 0)}
+        eps, _, m = O.compute_clustering_params(len(pal), q, "lab")
+        r = O.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m,
+                                              kmeans_impl=km, minibatch_impl=mb)
+        assert np.array_equal(r["palette"], g[f"out_palette{c}"]), c
+        assert np.array_equal(r["indices"], g[f"out_indices{c}"]), c
+
+
+def test_minibatch_restated_agreement_with_sklearn():
+    pytest.importorskip("sklearn")
+    import warnings
+    from sklearn.cluster import MiniBatchKMeans
+    from oracle import minibatch_restated as MB
+    g = golden("minibatch_palette.npz")
+    pal = g["in_palette"][1:]
+    for q in (10, 40):
+        k = MB.n_clusters_for(len(pal), q)
+        lab, info = MB.minibatch_labels(pal, k, return_info=True)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = MiniBatchKMeans(n_clusters=k, batch_size=1000, random_state=42, n_init="auto").fit(pal.astype(float))
+        assert info["steps"] == m.n_steps_                         # same random stream, same early stop
+        assert (lab == m.labels_).mean() > 0.97                    # distance ties / GEMM rounding only
