@@ -22,18 +22,32 @@ def _stale() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into librhccq.so.  Raises if nvcc is missing or the compile fails."""
+    """Compile csrc/*.cu into librhccq.so (one nvcc per source, in parallel, then one link).
+    Raises if nvcc is missing or a compile fails."""
     if not force and not _stale():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: librhccq.so must be built with the CUDA 12.9 toolkit for sm_100a")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT + ".tmp"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        r = subprocess.run([nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + r.stdout + r.stderr)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        done = list(ex.map(compile_one, SOURCES))
+    r = subprocess.run([nvcc, "-shared", "-Xcompiler", "-fPIC"] + [o for o, _ in done] + ["-o", OUT + ".tmp"],
+                       capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     os.replace(OUT + ".tmp", OUT)
     if verbose:
-        print(r.stderr)
+        print("".join(e for _, e in done))
     return OUT

@@ -33,7 +33,8 @@
 #define RHCCQ_KW 8                     // centres of a warp-level K-Means
 #define RHCCQ_WARP_RANGE 1024          // largest range a single warp splits
 #define RHCCQ_KPRIV 32                 // k up to which the CTA-level M step uses per-warp histograms
-#define RHCCQ_SPLIT_MAX_WARPS (RHCCQ_SPLIT_THREADS / 32)
+#define RHCCQ_SPLIT_THREADS_BIG 512     // few, large palettes (stage 2): one CTA per SM, twice the warps
+#define RHCCQ_SPLIT_MAX_WARPS (RHCCQ_SPLIT_THREADS_BIG / 32)
 
 // ---------------------------------------------------------------- index types
 // Small: palettes of up to 32 767 rows (every palette the DBSCAN branch can see:
@@ -659,7 +660,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     typedef typename Cfg::q_t q_t;
     __shared__ long long s_ll[RHCCQ_MAX_WARPS * RHCCQ_KM_MAXT + 2];
     __shared__ int s_scan[RHCCQ_MAX_WARPS + 2];
-    __shared__ int s_tail, s_err, s_base;
+    __shared__ int s_tail, s_err, s_base, s_claim;
     const int n = B.pal_cnt[p];
     const uint32_t* keys = B.pal_keys + B.pal_off[p];
     const int* lab = labels + B.pal_off[p];
@@ -814,8 +815,14 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
         }
         __syncthreads();
         if (s_err) break;
-        // ranges for single warps, concurrently
-        for (int e = head + RHCCQ_WARP; e < tail; e += RHCCQ_NWARPS) {
+        // ranges for single warps, concurrently; warps claim the next range when they are done with one
+        if (threadIdx.x == 0) s_claim = head;
+        __syncthreads();
+        while (true) {
+            int e = 0;
+            if (RHCCQ_LANE == 0) e = atomicAdd(&s_claim, 1);
+            e = rhccq_shfl(e, 0);
+            if (e >= tail) break;
             const q_t qe = W.queue[e];
             const int lo = Cfg::q_lo(qe), hi = Cfg::q_hi(qe), cnt = hi - lo;
             int k = (cnt + mcpc - 1) / mcpc;
@@ -861,8 +868,8 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     if (threadIdx.x == 0) n_leaves[p] = s_base + n_split_leaves;
 }
 
-template <class Cfg, bool ROWS_SMEM>
-__global__ void __launch_bounds__(RHCCQ_SPLIT_THREADS, 2)
+template <class Cfg, bool ROWS_SMEM, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == RHCCQ_SPLIT_THREADS ? 2 : 1)
 rhccq_k_palette_split(rhccq_palette_batch B, const int* __restrict__ labels, const int* __restrict__ status_in,
                       const int* __restrict__ max_cpc, const double* __restrict__ rng, int rng_len,
                       int* __restrict__ leaf, int* __restrict__ n_leaves, int max_rows, int kc_s,
@@ -913,17 +920,18 @@ static int rhccq_launch_split_cfg(const rhccq_palette_batch& B, const int* label
     if (!rows_in_smem) { const int cap = rhccq_sm_count() * 2; if (grid > cap) grid = cap; }
     const size_t smem = small + (rows_in_smem ? row_bytes : 0) + cent_s;
     unsigned char* gws = slices > 0 ? ws.ws : nullptr;
-    if (rows_in_smem) {
-        if (rhccq_smem_optin((const void*)rhccq_k_palette_split<Cfg, true>, smem) != 0) return -1;
-        RHCCQ_LAUNCH((rhccq_k_palette_split<Cfg, true>), grid, RHCCQ_SPLIT_THREADS, smem, (cudaStream_t)stream,
-                     B, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves, max_rows, (int)kc_s,
-                     gws, slice, small, row_bytes);
-    } else {
-        if (rhccq_smem_optin((const void*)rhccq_k_palette_split<Cfg, false>, smem) != 0) return -1;
-        RHCCQ_LAUNCH((rhccq_k_palette_split<Cfg, false>), grid, RHCCQ_SPLIT_THREADS, smem, (cudaStream_t)stream,
-                     B, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves, max_rows, (int)kc_s,
-                     gws, slice, small, row_bytes);
-    }
+    // few palettes (less than one per SM slot): a CTA of 512 threads each, they are latency-bound
+    const bool big = B.n_problems <= rhccq_sm_count() * 2 && max_rows > 4200;
+#define RHCCQ_SPLIT_GO(ROWS, THREADS)                                                                                  \
+    do {                                                                                                               \
+        if (rhccq_smem_optin((const void*)rhccq_k_palette_split<Cfg, ROWS, THREADS>, smem) != 0) return -1;            \
+        RHCCQ_LAUNCH((rhccq_k_palette_split<Cfg, ROWS, THREADS>), grid, THREADS, smem, (cudaStream_t)stream,           \
+                     B, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves, max_rows, (int)kc_s,                 \
+                     gws, slice, small, row_bytes);                                                                    \
+    } while (0)
+    if (rows_in_smem) { if (big) RHCCQ_SPLIT_GO(true, RHCCQ_SPLIT_THREADS_BIG); else RHCCQ_SPLIT_GO(true, RHCCQ_SPLIT_THREADS); }
+    else { if (big) RHCCQ_SPLIT_GO(false, RHCCQ_SPLIT_THREADS_BIG); else RHCCQ_SPLIT_GO(false, RHCCQ_SPLIT_THREADS); }
+#undef RHCCQ_SPLIT_GO
     return 0;
 }
 
