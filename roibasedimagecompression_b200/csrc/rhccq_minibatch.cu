@@ -54,6 +54,32 @@ __device__ __forceinline__ double rhccq_mb_dist(double x0, double x1, double x2,
     return __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
 }
 
+// v[0..cnt) <- block sums (integers: the order of additions is immaterial); sll holds RHCCQ_MAX_WARPS * MAXT
+__device__ __forceinline__ void rhccq_mb_sum_vec(long long* v, int cnt, long long* sll) {
+#ifndef RHCCQ_HOST_EMU
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < RHCCQ_MB_MAXT; ++t) {
+        if (t < cnt) {
+            long long x = v[t];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+            if (lane == 0) sll[warp * RHCCQ_MB_MAXT + t] = x;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < RHCCQ_MB_MAXT; ++t) {
+        if (t < cnt) {
+            long long x = 0;
+            for (int w = 0; w < nwarp; ++w) x += sll[w * RHCCQ_MB_MAXT + t];
+            v[t] = x;
+        }
+    }
+#endif
+}
+
 // number of clusters: ceil(n * (q / 100) / 10) as Python evaluates it (clustering.py:210)
 __host__ __device__ static inline int rhccq_mb_k(int n, double q) {
     return (int)ceil(((double)n * (q / 100.0)) / 10.0);
@@ -77,13 +103,14 @@ struct rhccq_mb_ws {
     unsigned long long* skey;// [pow2(k)]
     int* flag;               // [k] to_reassign, then its exclusive scan
     int* perm;               // [batch]
+    uint32_t* perm_xs;       // [init] colours of the init subset
 };
 __host__ __device__ static inline size_t rhccq_mb_bytes(size_t n, size_t kmax, size_t init_max) {
     size_t k2 = 1;
     while (k2 < kmax) k2 <<= 1;
     return rhccq_carve_bytes(n, 4) + rhccq_carve_bytes(n, 8) + rhccq_carve_bytes(init_max, 4) * 2 + rhccq_carve_bytes(init_max, 8)
            + rhccq_carve_bytes(3 * kmax, 8) * 2 + rhccq_carve_bytes(kmax, 8) + rhccq_carve_bytes(k2, 8)
-           + rhccq_carve_bytes(kmax + 1, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 4);
+           + rhccq_carve_bytes(kmax + 1, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 4) + rhccq_carve_bytes(init_max, 4);
 }
 size_t rhccq_palette_minibatch_ws_bytes(int max_rows) {
     // k <= n / 10 (q <= 100); init subset <= max(3000, 3k)
@@ -127,6 +154,7 @@ __device__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, con
         W.skey = cv.take<unsigned long long>(k2);
         W.flag = cv.take<int>(kmax + 1);
         W.perm = cv.take<int>(RHCCQ_MB_BATCH);
+        W.perm_xs = cv.take<uint32_t>(init_max);
     }
     // non-black rows in row order (clustering.py:185-192)
     int* mark = reinterpret_cast<int*>(W.cdf);                      // n ints fit into n doubles
@@ -149,7 +177,9 @@ __device__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, con
     if (init_size >= n) RHCCQ_PAR_FOR(i, n) W.sub[i] = i;
     __syncthreads();
     const int ns = init_size;
-#define RHCCQ_MB_X(j) keys[W.nb[W.sub[j]]]
+    // colours of the subset, contiguous (the k-means++ passes below read them k * (T + 2) times)
+    uint32_t* xs = reinterpret_cast<uint32_t*>(W.perm_xs);
+    RHCCQ_PAR_FOR(j, ns) xs[j] = keys[W.nb[W.sub[j]]];
     // ---- k-means++ on the subset (_kmeans.py:216-282): first centre by choice(ns, p=uniform)
     if (threadIdx.x == 0) {
         // cdf = cumsum(ones / ns) / last;  searchsorted(cdf, u, side='right')
@@ -165,47 +195,60 @@ __device__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, con
     __syncthreads();
     const int T = 2 + (k >= 3) + (k >= 8) + (k >= 21) + (k >= 55) + (k >= 149) + (k >= 404) + (k >= 1097) + (k >= 2981)
                   + (k >= 8104) + (k >= 22027);
-    long long pot;
+    // every thread owns a contiguous chunk of the subset (the cumulative sum needs a fixed order)
+    const int per = (ns + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int c_lo = (int)threadIdx.x * per < ns ? (int)threadIdx.x * per : ns;
+    const int c_hi = c_lo + per < ns ? c_lo + per : ns;
+    long long acc[RHCCQ_MB_MAXT];
+    unsigned long long chunk_sum = 0;
     {
-        const uint32_t cf = RHCCQ_MB_X(s_cand[0]);
-        long long part = 0;
-        RHCCQ_PAR_FOR(j, ns) { const uint32_t d = (uint32_t)rhccq_d2(RHCCQ_MB_X(j), cf); W.closest[j] = d; part += d; }
-        pot = rhccq_block_sum<long long>(part, s_ll);
+        const uint32_t cf = xs[s_cand[0]];
+        for (int j = c_lo; j < c_hi; ++j) { const uint32_t d = (uint32_t)rhccq_d2(xs[j], cf); W.closest[j] = d; chunk_sum += d; }
         RHCCQ_PAR_FOR(q, 3) W.center[q] = (double)((cf >> (16 - 8 * q)) & 255u);
     }
+    long long pot = rhccq_block_sum<long long>((long long)chunk_sum, s_ll);
     for (int c = 1; c < k; ++c) {
-        RHCCQ_PAR_FOR(j, ns) W.cum[j] = W.closest[j];
+        unsigned long long total;
+        unsigned long long run = rhccq_block_excl_scan<unsigned long long>(chunk_sum, &total, reinterpret_cast<unsigned long long*>(s_ll));
+        for (int j = c_lo; j < c_hi; ++j) { run += W.closest[j]; W.cum[j] = run; }          // inclusive
         __syncthreads();
-        rhccq_block_excl_scan_array<unsigned long long>(W.cum, ns, reinterpret_cast<unsigned long long*>(s_ll));
         if (threadIdx.x == 0) {
             for (int t = 0; t < T; ++t) {
                 const double rv = __dmul_rn(rhccq_mt_double(mt), (double)pot);
-                int lo = 0, hi = ns;                               // first j with inclusive cum[j] >= rv
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if ((double)(W.cum[mid] + W.closest[mid]) < rv) lo = mid + 1; else hi = mid;
-                }
+                int lo = 0, hi = ns;                               // first j with cum[j] >= rv
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)W.cum[mid] < rv) lo = mid + 1; else hi = mid; }
                 s_cand[t] = lo < ns - 1 ? lo : ns - 1;
             }
         }
         __syncthreads();
-        int best = 0;
-        long long best_pot = 0;
-        for (int t = 0; t < T; ++t) {
-            const uint32_t cc = RHCCQ_MB_X(s_cand[t]);
-            long long ps = 0;
-            RHCCQ_PAR_FOR(j, ns) { const uint32_t d = (uint32_t)rhccq_d2(RHCCQ_MB_X(j), cc), o = W.closest[j]; ps += d < o ? d : o; }
-            const long long tot = rhccq_block_sum<long long>(ps, s_ll);
-            if (t == 0 || tot < best_pot) { best_pot = tot; best = t; }
+        uint32_t xc[RHCCQ_MB_MAXT];
+#pragma unroll
+        for (int t = 0; t < RHCCQ_MB_MAXT; ++t) { acc[t] = 0; xc[t] = t < T ? xs[s_cand[t]] : 0u; }
+        for (int j = c_lo; j < c_hi; ++j) {
+            const uint32_t cj = xs[j], o = W.closest[j];
+#pragma unroll
+            for (int t = 0; t < RHCCQ_MB_MAXT; ++t)
+                if (t < T) { const uint32_t d = (uint32_t)rhccq_d2(cj, xc[t]); acc[t] += d < o ? d : o; }
         }
-        const uint32_t cs = RHCCQ_MB_X(s_cand[best]);
-        __syncthreads();
-        RHCCQ_PAR_FOR(j, ns) { const uint32_t d = (uint32_t)rhccq_d2(RHCCQ_MB_X(j), cs); if (d < W.closest[j]) W.closest[j] = d; }
+        rhccq_mb_sum_vec(acc, T, s_ll);
+        int best = 0;
+        long long best_pot = acc[0];
+#pragma unroll
+        for (int t = 1; t < RHCCQ_MB_MAXT; ++t) if (t < T && acc[t] < best_pot) { best_pot = acc[t]; best = t; }
+        uint32_t cs = xc[0];
+#pragma unroll
+        for (int t = 1; t < RHCCQ_MB_MAXT; ++t) if (t == best) cs = xc[t];
+        chunk_sum = 0;
+        for (int j = c_lo; j < c_hi; ++j) {
+            const uint32_t d = (uint32_t)rhccq_d2(xs[j], cs), o = W.closest[j];
+            const uint32_t m = d < o ? d : o;
+            W.closest[j] = m;
+            chunk_sum += m;
+        }
         RHCCQ_PAR_FOR(q, 3) W.center[3 * c + q] = (double)((cs >> (16 - 8 * q)) & 255u);
         pot = best_pot;
-        __syncthreads();
     }
-#undef RHCCQ_MB_X
+    __syncthreads();
     // ---- mini-batch steps (_kmeans.py:2160-2215)
     RHCCQ_PAR_FOR(q, k) W.counts[q] = 0.0;
     if (threadIdx.x == 0) {                                         // cdf of choice(n, batch, p=ones/n)

@@ -690,12 +690,13 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     rhccq_carve_centers(CG, cent_g, (size_t)kc_g);
     // small shared tables: per-warp centre sets, per-warp M-step histograms, candidate slots
     rhccq_carver sv(small_base);
-    int* hist = sv.take<int>((size_t)RHCCQ_SPLIT_MAX_WARPS * 4 * RHCCQ_KPRIV);
-    int* cand = sv.take<int>((size_t)(RHCCQ_SPLIT_MAX_WARPS + 1) * RHCCQ_KM_MAXT);
-    double* wcent = sv.take<double>((size_t)RHCCQ_SPLIT_MAX_WARPS * 7 * RHCCQ_KW);
-    int* wint = sv.take<int>((size_t)RHCCQ_SPLIT_MAX_WARPS * 5 * RHCCQ_KW);
-    int* poff = sv.take<int>((size_t)RHCCQ_SPLIT_MAX_WARPS * RHCCQ_KC);
-    CS.cand = CG.cand = cand + RHCCQ_SPLIT_MAX_WARPS * RHCCQ_KM_MAXT;
+    const size_t nw = (size_t)RHCCQ_NWARPS;                        // the tables are sized for the launch's warps
+    int* hist = sv.take<int>(nw * 4 * RHCCQ_KPRIV);
+    int* cand = sv.take<int>((nw + 1) * RHCCQ_KM_MAXT);
+    double* wcent = sv.take<double>(nw * 7 * RHCCQ_KW);
+    int* wint = sv.take<int>(nw * 5 * RHCCQ_KW);
+    int* poff = sv.take<int>(nw * RHCCQ_KC);
+    CS.cand = CG.cand = cand + nw * RHCCQ_KM_MAXT;
 
     // ---- entries that need no K-Means.  csize / crank live in the (still unused) seeding arrays.
     int* csize = reinterpret_cast<int*>(W.A.x);
@@ -888,12 +889,15 @@ rhccq_k_palette_split(rhccq_palette_batch B, const int* __restrict__ labels, con
     }
 }
 
-static size_t rhccq_split_small_bytes() {
-    return rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * 4 * RHCCQ_KPRIV, 4)
-           + rhccq_carve_bytes((size_t)(RHCCQ_SPLIT_MAX_WARPS + 1) * RHCCQ_KM_MAXT, 4)
-           + rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * 7 * RHCCQ_KW, 8)
-           + rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * 5 * RHCCQ_KW, 4)
-           + rhccq_carve_bytes((size_t)RHCCQ_SPLIT_MAX_WARPS * RHCCQ_KC, 4);
+static size_t rhccq_split_small_bytes(int threads) {
+#ifdef RHCCQ_HOST_EMU
+    const size_t nw = 1; (void)threads;
+#else
+    const size_t nw = (size_t)threads / 32;
+#endif
+    return rhccq_carve_bytes(nw * 4 * RHCCQ_KPRIV, 4) + rhccq_carve_bytes((nw + 1) * RHCCQ_KM_MAXT, 4)
+           + rhccq_carve_bytes(nw * 7 * RHCCQ_KW, 8) + rhccq_carve_bytes(nw * 5 * RHCCQ_KW, 4)
+           + rhccq_carve_bytes(nw * RHCCQ_KC, 4);
 }
 
 template <class Cfg>
@@ -901,7 +905,9 @@ static int rhccq_launch_split_cfg(const rhccq_palette_batch& B, const int* label
                                   const int* max_cpc, const double* rng, int rng_len, int* leaf, int* n_leaves,
                                   int max_rows, rhccq_launch_ws ws, void* stream) {
     const size_t rows = (size_t)(max_rows > 1 ? max_rows : 1);
-    const size_t small = rhccq_split_small_bytes();
+    // few palettes (less than one per SM slot): a CTA of 512 threads each, they are latency-bound
+    const bool big = B.n_problems <= rhccq_sm_count() * 2 && max_rows > 4200;
+    const size_t small = rhccq_split_small_bytes(big ? RHCCQ_SPLIT_THREADS_BIG : RHCCQ_SPLIT_THREADS);
     const size_t row_bytes = rhccq_split_row_bytes<Cfg>(rows);
     const size_t kc_s = rows < RHCCQ_KC ? rows : RHCCQ_KC;
     const size_t cent_s = rhccq_split_center_bytes(kc_s);
@@ -920,8 +926,6 @@ static int rhccq_launch_split_cfg(const rhccq_palette_batch& B, const int* label
     if (!rows_in_smem) { const int cap = rhccq_sm_count() * 2; if (grid > cap) grid = cap; }
     const size_t smem = small + (rows_in_smem ? row_bytes : 0) + cent_s;
     unsigned char* gws = slices > 0 ? ws.ws : nullptr;
-    // few palettes (less than one per SM slot): a CTA of 512 threads each, they are latency-bound
-    const bool big = B.n_problems <= rhccq_sm_count() * 2 && max_rows > 4200;
 #define RHCCQ_SPLIT_GO(ROWS, THREADS)                                                                                  \
     do {                                                                                                               \
         if (rhccq_smem_optin((const void*)rhccq_k_palette_split<Cfg, ROWS, THREADS>, smem) != 0) return -1;            \
