@@ -36,6 +36,47 @@ __device__ __forceinline__ uint32_t rhccq_mt_next(const rhccq_mt& m) {
     y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
     return y;
 }
+__device__ __forceinline__ uint32_t rhccq_mt_temper(uint32_t y) {
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+}
+// The next `count` outputs of the generator into raw[], by the whole CTA: tempering is independent per
+// element; the state refill ("twist") has a dependency structure that one warp resolves in four phases
+// (elements 0..226 read only old values, 227..453 and 454..622 read values renewed one phase earlier,
+// element 623 reads the renewed elements 0 and 396).  Every thread must call.
+__device__ void rhccq_mt_fill_raw(const rhccq_mt& m, uint32_t* raw, int count) {
+    int done = 0;
+    while (done < count) {
+        __syncthreads();
+        int pos = *m.pos;
+        if (pos >= 624) {
+            if (RHCCQ_WARP == 0) {
+                const int lo[4] = {0, 227, 454, 623}, hi[4] = {227, 454, 623, 624};
+                for (int ph = 0; ph < 4; ++ph) {
+                    for (int k0 = lo[ph]; k0 < hi[ph]; k0 += RHCCQ_WARP_SIZE) {
+                        const int k = k0 + RHCCQ_LANE;
+                        uint32_t v = 0;
+                        if (k < hi[ph]) {
+                            const uint32_t y = (m.s[k] & 0x80000000u) | (m.s[(k + 1) % 624] & 0x7fffffffu);
+                            v = m.s[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+                        }
+                        __syncwarp();                              // all reads of this round before its writes
+                        if (k < hi[ph]) m.s[k] = v;
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncthreads();
+            pos = 0;
+        }
+        const int take = 624 - pos < count - done ? 624 - pos : count - done;
+        RHCCQ_PAR_FOR(i, take) raw[done + i] = rhccq_mt_temper(m.s[pos + i]);
+        __syncthreads();
+        if (threadIdx.x == 0) *m.pos = pos + take;
+        done += take;
+    }
+    __syncthreads();
+}
 __device__ __forceinline__ double rhccq_mt_double(const rhccq_mt& m) {                // random_sample
     const uint32_t a = rhccq_mt_next(m) >> 5, b = rhccq_mt_next(m) >> 6;
     return __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
@@ -119,9 +160,10 @@ size_t rhccq_palette_minibatch_ws_bytes(int max_rows) {
     return rhccq_mb_bytes(n, kmax, init < n ? init : n);
 }
 
-__device__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, const double* __restrict__ quality,
+template <bool SMEMC>
+__device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, const double* __restrict__ quality,
                                         int* __restrict__ n_clusters, int max_rows, unsigned char* wsbase,
-                                        double* __restrict__ centers_out) {
+                                        double* __restrict__ centers_out, double* smem_centers) {
     __shared__ uint32_t s_mt[624];
     __shared__ int s_mtpos;
     __shared__ int s_i[RHCCQ_MAX_WARPS + 2 + 16];
@@ -155,6 +197,7 @@ __device__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, con
         W.flag = cv.take<int>(kmax + 1);
         W.perm = cv.take<int>(RHCCQ_MB_BATCH);
         W.perm_xs = cv.take<uint32_t>(init_max);
+        if (SMEMC) { W.center = smem_centers; W.center_new = smem_centers + 3 * kmax; }     // compile-time: LDS in the E step
     }
     // non-black rows in row order (clustering.py:185-192)
     int* mark = reinterpret_cast<int*>(W.cdf);                      // n ints fit into n doubles
@@ -264,7 +307,12 @@ __device__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, con
     double ewa = 0.0, ewa_min = 0.0;
     int* bidx = W.sub;                                              // the batch's rows (nb order); the subset is dead
     for (long long step = 0; step < n_steps; ++step) {
-        if (threadIdx.x == 0) for (int i = 0; i < batch; ++i) s_own[i] = rhccq_mt_double(mt);     // uniform_samples
+        // uniform_samples = random_sample(batch): two raw outputs per double, converted in place
+        rhccq_mt_fill_raw(mt, reinterpret_cast<uint32_t*>(s_own), 2 * batch);
+        RHCCQ_PAR_FOR(i, batch) {
+            const uint32_t a = reinterpret_cast<uint32_t*>(s_own)[2 * i] >> 5, b = reinterpret_cast<uint32_t*>(s_own)[2 * i + 1] >> 6;
+            s_own[i] = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+        }
         __syncthreads();
         RHCCQ_PAR_FOR(i, batch) {
             const double u = s_own[i];
@@ -280,14 +328,25 @@ __device__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, con
         const bool reassign = zero || n_since >= 10 * k;
         if (reassign) n_since = 0;
         __syncthreads();
-        // labels and distances of the batch
-        RHCCQ_PAR_FOR(i, batch) {
-            const uint32_t c = keys[W.nb[bidx[i]]];
-            const double x0 = (double)rhccq_key_r(c), x1 = (double)rhccq_key_g(c), x2 = (double)rhccq_key_b(c);
-            double bd = rhccq_mb_dist(x0, x1, x2, W.center);
-            int bi = 0;
-            for (int q = 1; q < k; ++q) { const double d = rhccq_mb_dist(x0, x1, x2, W.center + 3 * q); if (d < bd) { bd = d; bi = q; } }
-            s_lab[i] = bi; s_own[i] = bd;
+        // labels and distances of the batch: two points per thread against every centre
+        for (int i0 = (int)threadIdx.x; i0 < batch; i0 += 2 * (int)blockDim.x) {
+            const int i1 = i0 + (int)blockDim.x;
+            const uint32_t ca = keys[W.nb[bidx[i0]]], cb = keys[W.nb[bidx[i1 < batch ? i1 : i0]]];
+            const double a0 = (double)rhccq_key_r(ca), a1 = (double)rhccq_key_g(ca), a2 = (double)rhccq_key_b(ca);
+            const double b0 = (double)rhccq_key_r(cb), b1 = (double)rhccq_key_g(cb), b2 = (double)rhccq_key_b(cb);
+            double da = rhccq_mb_dist(a0, a1, a2, W.center), db = rhccq_mb_dist(b0, b1, b2, W.center);
+            int la = 0, lb = 0;
+            for (int q = 1; q < k; ++q) {
+                const double c0 = W.center[3 * q], c1 = W.center[3 * q + 1], c2 = W.center[3 * q + 2];
+                const double u0 = __dsub_rn(a0, c0), u1 = __dsub_rn(a1, c1), u2 = __dsub_rn(a2, c2);
+                const double v0 = __dsub_rn(b0, c0), v1 = __dsub_rn(b1, c1), v2 = __dsub_rn(b2, c2);
+                const double ea = __dadd_rn(__dadd_rn(__dmul_rn(u0, u0), __dmul_rn(u1, u1)), __dmul_rn(u2, u2));
+                const double eb = __dadd_rn(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1)), __dmul_rn(v2, v2));
+                if (ea < da) { da = ea; la = q; }
+                if (eb < db) { db = eb; lb = q; }
+            }
+            s_lab[i0] = la; s_own[i0] = da;
+            if (i1 < batch) { s_lab[i1] = lb; s_own[i1] = db; }
         }
         __syncthreads();
         if (threadIdx.x == 0) {                                     // inertia in batch order
@@ -385,10 +444,12 @@ __device__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, con
 }
 
 // status -4 (set by rhccq_k_palette_dbscan) selects the palettes of this branch
+template <bool SMEMC>
 __global__ void __launch_bounds__(RHCCQ_MB_THREADS)
 rhccq_k_palette_minibatch(rhccq_palette_batch B, const double* __restrict__ quality, int* __restrict__ n_clusters,
                           int max_rows, unsigned char* gws, size_t gws_stride, double* __restrict__ centers,
                           size_t centers_stride, int* __restrict__ todo) {
+    RHCCQ_DYN_SMEM(dyn);
     __shared__ int s_p;
     while (true) {
         if (threadIdx.x == 0) {
@@ -401,8 +462,8 @@ rhccq_k_palette_minibatch(rhccq_palette_batch B, const double* __restrict__ qual
         const int p = s_p;
         __syncthreads();
         if (p >= B.n_problems) return;
-        rhccq_minibatch_problem(B, p, quality, n_clusters, max_rows, gws + (size_t)blockIdx.x * gws_stride,
-                                centers + (size_t)p * centers_stride);
+        rhccq_minibatch_problem<SMEMC>(B, p, quality, n_clusters, max_rows, gws + (size_t)blockIdx.x * gws_stride,
+                                       centers + (size_t)p * centers_stride, reinterpret_cast<double*>(dyn));
         __syncthreads();
     }
 }
@@ -460,8 +521,15 @@ int rhccq_launch_palette_minibatch(const rhccq_palette_batch& B, const double* q
     cudaMemsetAsync(todo, 0, 16, (cudaStream_t)stream);
     cudaMemcpyAsync(before, n_clusters, (size_t)B.n_problems * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
 #endif
-    RHCCQ_LAUNCH(rhccq_k_palette_minibatch, grid, RHCCQ_MB_THREADS, 0, (cudaStream_t)stream, B, quality, n_clusters, max_rows,
-                 slices, slice, centers, cstride, todo);
+    const size_t csmem = 2 * 3 * kmax * sizeof(double);             // centre tables of the steps, in shared memory if they fit
+    if (csmem + 20 * 1024 <= RHCCQ_SMEM_BUDGET) {
+        if (rhccq_smem_optin((const void*)rhccq_k_palette_minibatch<true>, csmem) != 0) return -1;
+        RHCCQ_LAUNCH(rhccq_k_palette_minibatch<true>, grid, RHCCQ_MB_THREADS, csmem, (cudaStream_t)stream, B, quality, n_clusters,
+                     max_rows, slices, slice, centers, cstride, todo);
+    } else {
+        RHCCQ_LAUNCH(rhccq_k_palette_minibatch<false>, grid, RHCCQ_MB_THREADS, 0, (cudaStream_t)stream, B, quality, n_clusters,
+                     max_rows, slices, slice, centers, cstride, todo);
+    }
     const int chunks = 64;
     int g2 = B.n_problems * chunks;
     const int cap2 = rhccq_sm_count() * 8;

@@ -252,27 +252,43 @@ class HostEncoder:
     index planes in HOST memory out (the boundary of encoder/compression/test.py:100-151, where the
     reference holds numpy arrays and hands `shape` / `palette` / `indices` to the container writer).
 
-    Device and pinned staging buffers are allocated once per table shape; every `encode` call copies
-    the inputs host->device, runs `encode_batch`, and copies the results device->host.
+    Device and pinned staging buffers are allocated once per table shape (two sets).  `encode` handles
+    one batch; `encode_many` streams batches: the host->device copy of batch i+1 runs on a copy stream
+    while batch i is being encoded, so a stream of batches runs at max(copy, compute) per batch.
     """
 
     def __init__(self, be: Backend, table: SegmentTable):
         self.be, self.table = be, table
         B, K, H, W = table.B, table.K, table.H, table.W
-        pin = be.device.type == "cuda"
-        self.d_img = be.empty((B, H, W, 3), torch.uint8)
-        self.d_lab = be.empty((K, B, H, W), torch.int32)
-        self.h_idx = torch.empty((B, H, W), dtype=torch.int16, pin_memory=pin)
-        self.h2d_bytes = self.d_img.numel() + 4 * self.d_lab.numel()
-        self.d2h_bytes = 2 * self.h_idx.numel()
+        self.cuda = be.device.type == "cuda"
+        self.d_img = [be.empty((B, H, W, 3), torch.uint8) for _ in range(2)]
+        self.d_lab = [be.empty((K, B, H, W), torch.int32) for _ in range(2)]
+        self.h_idx = [torch.empty((B, H, W), dtype=torch.int16, pin_memory=self.cuda) for _ in range(2)]
+        self.h2d_bytes = self.d_img[0].numel() + 4 * self.d_lab[0].numel()
+        self.d2h_bytes = 2 * self.h_idx[0].numel()
+        if self.cuda:
+            self.copy_stream = torch.cuda.Stream(device=be.device)
+            self.ev_ready = [torch.cuda.Event() for _ in range(2)]
+            self.ev_free = [torch.cuda.Event() for _ in range(2)]
 
-    def encode(self, images_host: torch.Tensor, labels_host: torch.Tensor):
-        """images uint8 [B,H,W,3], labels int32 [K,B,H,W] (pinned host tensors for full copy speed).
-        Returns (palettes: list of uint8 [m,3] arrays, indices: uint16 [B,H,W] array view of pinned memory)."""
-        self.d_img.copy_(images_host, non_blocking=True)
-        self.d_lab.copy_(labels_host, non_blocking=True)
-        res = encode_batch(self.be, self.d_img, self.d_lab, self.table)
-        self.h_idx.copy_(res.indices, non_blocking=True)
+    def _upload(self, slot: int, images_host, labels_host, first_use: bool):
+        if not self.cuda:
+            self.d_img[slot].copy_(images_host); self.d_lab[slot].copy_(labels_host)
+            return
+        with torch.cuda.stream(self.copy_stream):
+            if not first_use:
+                self.copy_stream.wait_event(self.ev_free[slot])    # the encode that last read this slot is done
+            self.d_img[slot].copy_(images_host, non_blocking=True)
+            self.d_lab[slot].copy_(labels_host, non_blocking=True)
+            self.ev_ready[slot].record(self.copy_stream)
+
+    def _encode_slot(self, slot: int):
+        if self.cuda:
+            torch.cuda.current_stream(self.be.device).wait_event(self.ev_ready[slot])
+        res = encode_batch(self.be, self.d_img[slot], self.d_lab[slot], self.table)
+        if self.cuda:
+            self.ev_free[slot].record(torch.cuda.current_stream(self.be.device))
+        self.h_idx[slot].copy_(res.indices, non_blocking=True)
         off = res.palette_off.cpu().numpy()                       # synchronises the stream
         cnt = res.palette_cnt.cpu().numpy()
         ops.check_counts("final palette", torch.from_numpy(cnt))
@@ -282,4 +298,27 @@ class HostEncoder:
         for b in range(len(cnt)):
             k = keys[off[b]:off[b] + cnt[b]]
             pals.append(np.stack([(k >> 16) & 255, (k >> 8) & 255, k & 255], axis=-1).astype(np.uint8))
-        return pals, self.h_idx.numpy().view(np.uint16)
+        return pals, self.h_idx[slot].numpy().view(np.uint16)
+
+    def encode(self, images_host: torch.Tensor, labels_host: torch.Tensor):
+        """images uint8 [B,H,W,3], labels int32 [K,B,H,W] (pinned host tensors for full copy speed).
+        Returns (palettes: list of uint8 [m,3] arrays, indices: uint16 [B,H,W] array view of pinned memory)."""
+        self._upload(0, images_host, labels_host, first_use=True)
+        return self._encode_slot(0)
+
+    def encode_many(self, batches):
+        """Generator over (palettes, indices) for an iterable of (images_host, labels_host) batches of the
+        table's shape.  The result of a batch stays valid until two more batches have been produced."""
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        self._upload(0, cur[0], cur[1], first_use=True)
+        i = 0
+        while cur is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                self._upload((i + 1) & 1, nxt[0], nxt[1], first_use=(i == 0))
+            yield self._encode_slot(i & 1)
+            cur = nxt
+            i += 1
