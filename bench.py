@@ -41,6 +41,7 @@ WORKLOADS = {
     # DBSCAN-only (BASELINE.json configs[4]): images per GPU, H, W, unused, description
     "c5": (1, 4096, 4096, 0, "DBSCAN of 16.8 M 5-D points (x, y, R, G, B) of a 4096x4096 synthetic image"),
     "c5s": (1, 1024, 1024, 0, "DBSCAN of 1.05 M 5-D points (x, y, R, G, B) of a 1024x1024 synthetic image"),
+    "c5l": (1, 4096, 4096, 0, "DBSCAN of 16.8 M 5-D points (x, y, R, G, B) of a 4096x4096 synthetic image, lattice kernels"),
     "c5u": (1, 2048, 2048, 0, "DBSCAN of 4.2 M uniform points in [0,256)^5 (3-D cell grid)"),
     # BASELINE.json configs[3]: one 7680x4320 image, strips of rows + halo per GPU, NCCL all-gather of boundary edges
     "c4": (1, 4320, 7680, 0, "DBSCAN of the 33.2 M pixel features of one 7680x4320 synthetic image, strip-sharded"),
@@ -196,8 +197,14 @@ def run_dbscan(args, be, rank, world, local, H, W, desc):
         gd = 2
     h_pts = torch.from_numpy(pts_np).pin_memory()
     d_pts = h_pts.cuda()
-    lo, hi = D.point_bounds(be, d_pts, gd)
-    plan = D.PointDbscan(be, n, 5, eps, min_pts, lo, hi, gd)
+    lattice = args.workload == "c5l"
+    if lattice:
+        plan = D.LatticeDbscan(be, H, W, eps, min_pts)
+        count_name = "rhccq_dbscan_lattice_count"
+    else:
+        lo, hi = D.point_bounds(be, d_pts, gd)
+        plan = D.PointDbscan(be, n, 5, eps, min_pts, lo, hi, gd)
+        count_name = "rhccq_dbscan_count"
     for _ in range(args.warmup):
         labels, core = plan.run(d_pts)
     torch.cuda.synchronize()
@@ -216,7 +223,7 @@ def run_dbscan(args, be, rank, world, local, H, W, desc):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     kt = be.kernel_times_ms(); launches = be.launches - l0; be.kernel_timing(False)
     peak, peak_src = _peaks()
-    cnt_n, cnt_ms = kt["rhccq_dbscan_count"]
+    cnt_n, cnt_ms = kt[count_name]
     ach = DBSCAN_BYTES_PER_POINT * n / 1e9 / ((cnt_ms / cnt_n) / 1e3)
     # end to end: host points in, host labels out
     h_lab = torch.empty(n, dtype=torch.int32).pin_memory()
@@ -238,7 +245,7 @@ def run_dbscan(args, be, rank, world, local, H, W, desc):
            "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": "points/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": n * 20 * world, "d2h_bytes_per_step": n * 4 * world},
-           "roofline": {"kernel": "rhccq_dbscan_count (rhccq_k_pt_sweep<0>)", "bound": "hbm", "achieved": ach, "peak": peak,
+           "roofline": {"kernel": count_name + (" (rhccq_k_lt_sweep<0,0>)" if lattice else " (rhccq_k_pt_sweep<0>)"), "bound": "hbm", "achieved": ach, "peak": peak,
                         "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": DBSCAN_BYTES_PER_POINT * n, "avg_launch_ms": cnt_ms / cnt_n,
                         "share_of_step": (cnt_ms / args.steps) / ms},

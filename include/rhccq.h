@@ -225,6 +225,20 @@ int rhccq_dbscan_attach(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_
  * 2 the union-find parents (int32 [n]), 3 the sorted records (8 x float32 [n]) */
 size_t rhccq_dbscan_ws_offset(const rhccq_dbscan_plan* host_plan, int which);
 
+/* ------------------------------------------------------------------ the same operator on an image lattice
+ * X[i] = (x, y, R, G, B) of pixel i of an H x W image in raster order (the pixel features of BASELINE.json
+ * configs 3-5): neighbours come from a (2 floor(eps) + 1)^2 stencil over packed 8-bit colours in a
+ * shared-memory tile.  src_kind 0: float32 points [H*W, 5] (checked: *status = 1 when they are not such a
+ * lattice — then use the generic path), 1: uint8 image [H, W, 3].  count: int32 [H*W], core: uint8 [H*W].
+ * Labels are identical to the generic path's and to scikit-learn's. */
+size_t rhccq_dbscan_lattice_workspace_bytes(int H, int W);
+int rhccq_dbscan_lattice_count(const void* src, int src_kind, int H, int W, double eps, int min_pts, int32_t* count,
+                               uint8_t* core, int32_t* status, void* ws, size_t ws_bytes, void* stream);
+int rhccq_dbscan_lattice_union(int H, int W, double eps, int min_pts, void* ws, size_t ws_bytes, void* stream);
+int rhccq_dbscan_lattice_border(int H, int W, double eps, int min_pts, const uint8_t* core, void* ws, size_t ws_bytes,
+                                void* stream);
+int rhccq_dbscan_lattice_relabel(int H, int W, void* ws, size_t ws_bytes, int32_t* labels, void* stream);
+
 /* ------------------------------------------------------------------ strips of one point set across GPUs
  * (SURVEY.md 8e).  Every rank runs plan..flatten on its strip plus a halo of 2 eps; local indices are
  * global index - g0.  emit: for core points i in [lo, hi) of the boundary zone that are not their own root,

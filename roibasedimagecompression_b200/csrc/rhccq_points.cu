@@ -727,3 +727,236 @@ int rhccq_dbscan_relabel(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, 
 }
 
 }  // extern "C"
+
+// ================================================================= image lattice
+// The same operator when the points ARE an image: X[i] = (x, y, R, G, B) of pixel i in raster order (the
+// reference's pixel features; BASELINE.json configs 3-5).  Then the cell grid is the pixel lattice itself:
+// two pixels are within eps iff (dx^2 + dy^2) + |dRGB|^2 <= eps^2, all integers, so a pixel's neighbours are
+// found with a (2 floor(eps) + 1)^2 stencil and a colour budget per offset on packed 8-bit colours
+// (two instructions per candidate), from a shared-memory tile with halo.  The count pass reads the 20-byte
+// points once, coalesced, checks that they really are a lattice of 8-bit colours (status flag otherwise: the
+// caller then takes the generic path), and writes the count and a packed colour (+ core bit) per pixel — its
+// HBM traffic is the algorithmic 24 bytes per point plus 4.
+#define RHCCQ_LT_W 64
+#define RHCCQ_LT_H 16
+#define RHCCQ_LT_MAXR 16
+#define RHCCQ_LT_INVALID 0xFF000000u
+#define RHCCQ_LT_CORE 0x01000000u
+
+struct rhccq_lt_args {
+    int H, W, R, thr, min_pts, n_off;
+};
+
+__device__ __forceinline__ int rhccq_lt_build_offsets(int* offs, int R, int thr, bool forward_only) {
+    // (dy, dx, colour budget) of the stencil, raster order; built by one thread (a few hundred entries)
+    int n = 0;
+    for (int dy = -R; dy <= R; ++dy)
+        for (int dx = -R; dx <= R; ++dx) {
+            const int s = dy * dy + dx * dx;
+            if (s > thr) continue;
+            if (forward_only && !(dy > 0 || (dy == 0 && dx > 0))) continue;
+            offs[n++] = ((dy + 64) << 24) | ((dx + 64) << 16) | (thr - s);       // budget < 65536
+        }
+    return n;
+}
+
+// tile of packed colours (top byte: 0xFF outside the image, bit 24 = core) with a halo of R pixels
+template <int SRC>   // 0: float32 points [H*W,5], 1: uint8 image [H,W,3], 2: packed uint32 [H*W]
+__device__ __forceinline__ void rhccq_lt_load_tile(const void* src, const rhccq_lt_args& A, int ty0, int tx0, uint32_t* tile,
+                                                   int tw, int th, int* bad) {
+    RHCCQ_PAR_FOR(t, tw * th) {
+        const int y = ty0 - A.R + t / tw, x = tx0 - A.R + t % tw;
+        uint32_t v = RHCCQ_LT_INVALID;
+        if (y >= 0 && y < A.H && x >= 0 && x < A.W) {
+            const size_t i = (size_t)y * A.W + x;
+            if (SRC == 0) {
+                const float* p = reinterpret_cast<const float*>(src) + i * 5;
+                const float fx = p[0], fy = p[1], r = p[2], g = p[3], b = p[4];
+                const int ir = (int)r, ig = (int)g, ib = (int)b;
+                if (fx != (float)x || fy != (float)y || (float)ir != r || (float)ig != g || (float)ib != b ||
+                    (unsigned)ir > 255u || (unsigned)ig > 255u || (unsigned)ib > 255u) *bad = 1;
+                v = rhccq_pack_rgb((unsigned)ir & 255u, (unsigned)ig & 255u, (unsigned)ib & 255u);
+            } else if (SRC == 1) {
+                const uint8_t* p = reinterpret_cast<const uint8_t*>(src) + i * 3;
+                v = rhccq_pack_rgb(p[0], p[1], p[2]);
+            } else {
+                v = reinterpret_cast<const uint32_t*>(src)[i];
+            }
+        }
+        tile[t] = v;
+    }
+}
+
+// MODE 0: count (+ packed colours with the core bit), 1: union, 2: border attachment
+template <int MODE, int SRC>
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_lt_sweep(const void* __restrict__ src, rhccq_lt_args A, int* __restrict__ count, uint32_t* __restrict__ packed,
+                 uint8_t* __restrict__ core, int* __restrict__ parent, int* __restrict__ rootlab, int* __restrict__ status) {
+    RHCCQ_DYN_SMEM(dyn);
+    __shared__ int s_noff, s_bad;
+    const int tw = RHCCQ_LT_W + 2 * A.R, th = RHCCQ_LT_H + 2 * A.R;
+    uint32_t* tile = reinterpret_cast<uint32_t*>(dyn);
+    int* offs = reinterpret_cast<int*>(tile + (size_t)tw * th);
+    if (threadIdx.x == 0) { s_noff = rhccq_lt_build_offsets(offs, A.R, A.thr, MODE == 1); s_bad = 0; }
+    __syncthreads();
+    const int n_off = s_noff;
+    const int tiles_x = (A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W, tiles_y = (A.H + RHCCQ_LT_H - 1) / RHCCQ_LT_H;
+    for (int tI = blockIdx.x; tI < tiles_x * tiles_y; tI += gridDim.x) {
+        const int ty0 = (tI / tiles_x) * RHCCQ_LT_H, tx0 = (tI % tiles_x) * RHCCQ_LT_W;
+        rhccq_lt_load_tile<SRC>(src, A, ty0, tx0, tile, tw, th, &s_bad);
+        __syncthreads();
+        RHCCQ_PAR_FOR(t, RHCCQ_LT_W * RHCCQ_LT_H) {
+            const int ly = t / RHCCQ_LT_W, lx = t % RHCCQ_LT_W;
+            const int y = ty0 + ly, x = tx0 + lx;
+            if (y >= A.H || x >= A.W) continue;
+            const int ci = (ly + A.R) * tw + lx + A.R;
+            const uint32_t me = tile[ci];
+            const uint32_t c = me & 0x00ffffffu;
+            const int id = y * A.W + x;
+            if (MODE == 0) {
+                int acc = 0;
+                for (int o = 0; o < n_off; ++o) {
+                    const int e = offs[o];
+                    const uint32_t nb = tile[ci + ((e >> 24) - 64) * tw + (((e >> 16) & 255) - 64)];
+                    acc += (int)((unsigned)rhccq_d2(c, nb) <= (unsigned)(e & 0xffff));     // 0xFF top byte: never within
+                }
+                count[id] = acc;
+                const int is_core = acc >= A.min_pts;
+                core[id] = (uint8_t)is_core;
+                packed[id] = c | (is_core ? RHCCQ_LT_CORE : 0u);
+            } else if (MODE == 1) {
+                if (!(me & RHCCQ_LT_CORE)) continue;
+                int my_root = id;
+                for (int o = 0; o < n_off; ++o) {
+                    const int e = offs[o];
+                    const int dy = (e >> 24) - 64, dx = ((e >> 16) & 255) - 64;
+                    const uint32_t nb = tile[ci + dy * tw + dx];
+                    if ((nb >> 24) != 1u) continue;                                        // outside, or not core
+                    if ((unsigned)rhccq_d2(c, nb & 0x00ffffffu) > (unsigned)(e & 0xffff)) continue;
+                    const int nid = id + dy * A.W + dx;                                    // forward: nid > id
+                    if (((volatile int*)parent)[nid] != my_root) {
+                        rhccq_pt_union(parent, nid, id);
+                        my_root = rhccq_pt_find(parent, id);
+                    }
+                }
+            } else {
+                if (me & RHCCQ_LT_CORE) continue;                                          // core pixels keep their root
+                int best = 0x7fffffff;
+                for (int o = 0; o < n_off; ++o) {
+                    const int e = offs[o];
+                    const int dy = (e >> 24) - 64, dx = ((e >> 16) & 255) - 64;
+                    const uint32_t nb = tile[ci + dy * tw + dx];
+                    if ((nb >> 24) != 1u) continue;
+                    if ((unsigned)rhccq_d2(c, nb & 0x00ffffffu) > (unsigned)(e & 0xffff)) continue;
+                    const int r = rootlab[id + dy * A.W + dx];
+                    best = r < best ? r : best;
+                }
+                rootlab[id] = best == 0x7fffffff ? -1 : best;
+            }
+        }
+        __syncthreads();
+    }
+    if (MODE == 0 && SRC == 0 && threadIdx.x == 0 && s_bad) *status = 1;
+}
+
+static int rhccq_lt_args_make(int H, int W, double eps, int min_pts, rhccq_lt_args* A) {
+    if (H < 1 || W < 1 || (long long)H * W > 2000000000LL || !(eps > 0.0) || min_pts < 1) {
+        rhccq_set_error("rhccq_dbscan_lattice: need 1 <= H*W <= 2e9, eps > 0, min_pts >= 1");
+        return -1;
+    }
+    const double r2 = eps * eps;
+    int R = 0;
+    while ((double)(R + 1) * (R + 1) <= r2) ++R;
+    if (R > RHCCQ_LT_MAXR || r2 >= 65000.0) {
+        rhccq_set_error("rhccq_dbscan_lattice: eps %.3f needs a stencil radius above %d; use the generic path", eps, RHCCQ_LT_MAXR);
+        return -1;
+    }
+    A->H = H; A->W = W; A->R = R; A->thr = (int)floor(r2); A->min_pts = min_pts; A->n_off = 0;
+    return 0;
+}
+static size_t rhccq_lt_smem(const rhccq_lt_args& A) {
+    const size_t side = 2 * (size_t)A.R + 1;
+    return ((size_t)(RHCCQ_LT_W + 2 * A.R) * (RHCCQ_LT_H + 2 * A.R) + side * side + 4) * 4;
+}
+static int rhccq_lt_grid(const rhccq_lt_args& A) {
+    const long long tiles = (long long)((A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W) * ((A.H + RHCCQ_LT_H - 1) / RHCCQ_LT_H);
+    const long long cap = (long long)rhccq_sm_count() * 32;
+    return (int)(tiles < cap ? tiles : cap);
+}
+
+extern "C" {
+
+size_t rhccq_dbscan_lattice_workspace_bytes(int H, int W) {
+    const size_t n = (size_t)H * W;
+    return rhccq_al(n * 4) * 4 + rhccq_al(rhccq_scan_scratch_ints((long long)n) * 4 + 64) + 256;
+}
+
+struct rhccq_lt_ws { uint32_t* packed; int* parent; int* rootlab; int* is_root; int* scan; int* status; };
+static void rhccq_lt_carve(int H, int W, void* ws, rhccq_lt_ws* L) {
+    const size_t n = (size_t)H * W;
+    unsigned char* p = (unsigned char*)ws;
+    L->packed = (uint32_t*)p; p += rhccq_al(n * 4);
+    L->parent = (int*)p; p += rhccq_al(n * 4);
+    L->rootlab = (int*)p; p += rhccq_al(n * 4);
+    L->is_root = (int*)p; p += rhccq_al(n * 4);
+    L->scan = (int*)p; p += rhccq_al(rhccq_scan_scratch_ints((long long)n) * 4 + 64);
+    L->status = (int*)p;
+}
+
+#define RHCCQ_LT_PROLOGUE(name)                                                                         \
+    rhccq_lt_args A;                                                                                    \
+    if (rhccq_lt_args_make(H, W, eps, min_pts, &A) != 0) return -1;                                     \
+    if (!ws || ws_bytes < rhccq_dbscan_lattice_workspace_bytes(H, W)) {                                 \
+        rhccq_set_error(name ": workspace missing or too small"); return -1; }                          \
+    rhccq_lt_ws L; rhccq_lt_carve(H, W, ws, &L);                                                        \
+    const size_t smem = rhccq_lt_smem(A); const int grid = rhccq_lt_grid(A);
+
+int rhccq_dbscan_lattice_count(const void* src, int src_kind, int H, int W, double eps, int min_pts, int32_t* count,
+                               uint8_t* core, int32_t* status, void* ws, size_t ws_bytes, void* stream) {
+    RHCCQ_LT_PROLOGUE("rhccq_dbscan_lattice_count")
+    if (!src || !count || !core || !status || (src_kind != 0 && src_kind != 1)) { rhccq_set_error("rhccq_dbscan_lattice_count: bad arguments"); return -1; }
+#ifdef RHCCQ_HOST_EMU
+    *status = 0;
+#else
+    cudaMemsetAsync(status, 0, 4, (cudaStream_t)stream);
+#endif
+    if (src_kind == 0) {
+        if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<0, 0>, smem) != 0) return -1;
+        RHCCQ_LAUNCH((rhccq_k_lt_sweep<0, 0>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, src, A, count, L.packed, core, L.parent, L.rootlab, status);
+    } else {
+        if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<0, 1>, smem) != 0) return -1;
+        RHCCQ_LAUNCH((rhccq_k_lt_sweep<0, 1>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, src, A, count, L.packed, core, L.parent, L.rootlab, status);
+    }
+    return 0;
+}
+
+int rhccq_dbscan_lattice_union(int H, int W, double eps, int min_pts, void* ws, size_t ws_bytes, void* stream) {
+    RHCCQ_LT_PROLOGUE("rhccq_dbscan_lattice_union")
+    RHCCQ_LAUNCH(rhccq_k_pt_init_parent, rhccq_pt_blocks((long long)H * W), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, H * W, L.parent);
+    if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<1, 2>, smem) != 0) return -1;
+    RHCCQ_LAUNCH((rhccq_k_lt_sweep<1, 2>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, (const void*)L.packed, A, (int*)nullptr, L.packed,
+                 (uint8_t*)nullptr, L.parent, L.rootlab, (int*)nullptr);
+    return 0;
+}
+
+int rhccq_dbscan_lattice_border(int H, int W, double eps, int min_pts, const uint8_t* core, void* ws, size_t ws_bytes, void* stream) {
+    RHCCQ_LT_PROLOGUE("rhccq_dbscan_lattice_border")
+    RHCCQ_LAUNCH(rhccq_k_pt_flatten, rhccq_pt_blocks((long long)H * W), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, H * W, L.parent, core, L.rootlab, L.is_root);
+    if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<2, 2>, smem) != 0) return -1;
+    RHCCQ_LAUNCH((rhccq_k_lt_sweep<2, 2>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, (const void*)L.packed, A, (int*)nullptr, L.packed,
+                 (uint8_t*)nullptr, L.parent, L.rootlab, (int*)nullptr);
+    return 0;
+}
+
+int rhccq_dbscan_lattice_relabel(int H, int W, void* ws, size_t ws_bytes, int32_t* labels, void* stream) {
+    if (!ws || ws_bytes < rhccq_dbscan_lattice_workspace_bytes(H, W) || !labels) { rhccq_set_error("rhccq_dbscan_lattice_relabel: bad arguments"); return -1; }
+    rhccq_lt_ws L; rhccq_lt_carve(H, W, ws, &L);
+    const long long n = (long long)H * W;
+    if (n <= RHCCQ_SCAN_TILE) {
+        RHCCQ_LAUNCH(rhccq_k_scan_small, 1, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, L.is_root, (int)n, (int*)nullptr);
+    } else if (rhccq_scan_i32(L.is_root, n, L.is_root, L.scan, stream) != 0) return -1;
+    RHCCQ_LAUNCH(rhccq_k_pt_labels, rhccq_pt_blocks(n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, (int)n, L.rootlab, L.is_root, labels);
+    return 0;
+}
+
+}  // extern "C"

@@ -238,3 +238,59 @@ def dbscan_strips(be: Backend, pts_local, g0: int, own, zone, eps: float, min_pt
     if timings is not None:
         timings.update(edges_local=n_e, edges_total=E, roots_total=int(roots.numel()))
     return labels[:n_own], plan.core[own[0]:own[1]]
+
+
+# --------------------------------------------------------------------------- image lattice fast path
+class LatticeDbscan:
+    """DBSCAN of the pixel features (x, y, R, G, B) of an H x W image (w_xy = 1) through the lattice
+    kernels: stencil + packed 8-bit colours instead of cell binning.  Same labels as `PointDbscan`."""
+
+    def __init__(self, be: Backend, H: int, W: int, eps: float, min_pts: int):
+        self.be, self.H, self.W, self.eps, self.min_pts = be, int(H), int(W), float(eps), int(min_pts)
+        n = self.H * self.W
+        self.ws_bytes = int(be.cdll.rhccq_dbscan_lattice_workspace_bytes(self.H, self.W))
+        self.ws = be.empty((self.ws_bytes,), torch.uint8)
+        self.count_out = be.empty((n,), torch.int32)
+        self.core = be.empty((n,), torch.uint8)
+        self.labels = be.empty((n,), torch.int32)
+        self.status = be.zeros((1,), torch.int32)
+
+    def count(self, src):
+        """src: float32 points [H*W, 5] or uint8 image [H, W, 3] on the device."""
+        kind = 0 if src.dtype == torch.float32 else 1
+        if kind == 0 and tuple(src.shape) != (self.H * self.W, 5):
+            raise ValueError("points must be float32 [H*W, 5]")
+        if kind == 1 and (src.dtype != torch.uint8 or tuple(src.shape) != (self.H, self.W, 3)):
+            raise ValueError("image must be uint8 [H, W, 3]")
+        self.be.call("rhccq_dbscan_lattice_count", self.be.ptr(src), kind, self.H, self.W, self.eps, self.min_pts,
+                     self.be.ptr(self.count_out), self.be.ptr(self.core), self.be.ptr(self.status), self.be.ptr(self.ws),
+                     self.ws_bytes, self.be.stream())
+
+    def union(self):
+        self.be.call("rhccq_dbscan_lattice_union", self.H, self.W, self.eps, self.min_pts, self.be.ptr(self.ws), self.ws_bytes,
+                     self.be.stream(), launches=2)
+
+    def border(self):
+        self.be.call("rhccq_dbscan_lattice_border", self.H, self.W, self.eps, self.min_pts, self.be.ptr(self.core),
+                     self.be.ptr(self.ws), self.ws_bytes, self.be.stream(), launches=2)
+
+    def relabel(self):
+        self.be.call("rhccq_dbscan_lattice_relabel", self.H, self.W, self.be.ptr(self.ws), self.ws_bytes,
+                     self.be.ptr(self.labels), self.be.stream(), launches=3)
+
+    def run(self, src, check: bool = True):
+        """labels int32 [H*W], core uint8 [H*W].  With float32 points the kernel verifies that they are the
+        lattice of an 8-bit image; `check` reads that flag back and raises if they are not."""
+        self.count(src); self.union(); self.border(); self.relabel()
+        if check and src.dtype == torch.float32 and int(self.status.item()) != 0:
+            raise RhccqError("points are not the pixel lattice of an 8-bit image (x = column, y = row, integer "
+                             "colours 0..255): use dbscan_points")
+        return self.labels, self.core
+
+
+def dbscan_image(be: Backend, image_u8, eps: float, min_pts: int):
+    """Labels [H, W] and core flags of DBSCAN over the (x, y, R, G, B) features of an image on the device."""
+    H, W, _ = image_u8.shape
+    plan = LatticeDbscan(be, H, W, eps, min_pts)
+    labels, core = plan.run(image_u8)
+    return labels.view(H, W).clone(), core.view(H, W).clone()

@@ -109,3 +109,44 @@ def test_points_quarter_million_vs_sklearn(eps, mp):
     rc[ref.core_sample_indices_] = True
     assert np.array_equal(core, rc)
     assert np.array_equal(lab, ref.labels_)
+
+
+# --------------------------------------------------------------------------- image lattice fast path
+def test_lattice_golden_sklearn(backend):
+    g = golden("dbscan_points.npz")
+    img, pts = g["image"], g["points"]
+    H, W, _ = img.shape
+    be = backend
+    for i, (eps, mp) in enumerate(g["combos"]):
+        lab, core = D.dbscan_image(be, torch.from_numpy(img.copy()).to(be.device), float(eps), int(mp))
+        assert np.array_equal(lab.cpu().numpy().reshape(-1), g[f"labels{i}"]), (eps, mp)
+        assert np.array_equal(core.cpu().numpy().reshape(-1).astype(bool), g[f"core{i}"]), (eps, mp)
+        plan = D.LatticeDbscan(be, H, W, float(eps), int(mp))          # the float32-point entry of the same kernels
+        lab2, _ = plan.run(torch.from_numpy(pts).to(be.device))
+        assert np.array_equal(lab2.cpu().numpy(), g[f"labels{i}"])
+
+
+def test_lattice_rejects_non_lattice_points_and_ragged_sizes(backend):
+    be = backend
+    img = synth(19, 67, 5)                                              # not a multiple of the 64 x 16 tile
+    pts = pixel_features(img)
+    for eps, mp in ((1.0, 2), (2.5, 5), (4.0, 30)):
+        lab, core = D.dbscan_image(be, torch.from_numpy(img.copy()).to(be.device), eps, mp)
+        assert np.array_equal(lab.cpu().numpy().reshape(-1), O.dbscan_labels(pts, eps, mp)), (eps, mp)
+    bad = pts.copy()
+    bad[100, 2] += 0.5
+    plan = D.LatticeDbscan(be, 19, 67, 2.0, 3)
+    with pytest.raises(Exception):
+        plan.run(torch.from_numpy(bad).to(be.device))
+
+
+@pytest.mark.gpu
+def test_lattice_equals_generic_on_1080p():
+    from roibasedimagecompression_b200._lib import lib
+    be = lib()
+    img = synth(1080, 1920, 4321)
+    pts = torch.from_numpy(pixel_features(img)).cuda()
+    for eps, mp in ((3.0, 8), (2.0, 3), (5.0, 20)):
+        lab, core = D.dbscan_image(be, torch.from_numpy(img.copy()).cuda(), eps, mp)
+        lab_g, core_g = D.dbscan_points(be, pts, eps, mp)
+        assert torch.equal(lab.view(-1), lab_g) and torch.equal(core.view(-1), core_g), (eps, mp)
