@@ -38,7 +38,7 @@ static int rhccq_after_launch(const char*) { return 0; }
 extern "C" int rhccq_device_check(void) { return 0; }
 #else
 int rhccq_smem_optin(const void* kernel, size_t bytes) {
-    if (bytes <= 48 * 1024) return 0;
+    if (bytes <= 8 * 1024) return 0;                               // static + dynamic must stay below 48 KiB without the opt-in
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
         rhccq_set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu): %s", bytes, cudaGetErrorString(e));

@@ -255,13 +255,13 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         unsigned long long run = rhccq_block_excl_scan<unsigned long long>(chunk_sum, &total, reinterpret_cast<unsigned long long*>(s_ll));
         for (int j = c_lo; j < c_hi; ++j) { run += W.closest[j]; W.cum[j] = run; }          // inclusive
         __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int t = 0; t < T; ++t) {
-                const double rv = __dmul_rn(rhccq_mt_double(mt), (double)pot);
-                int lo = 0, hi = ns;                               // first j with cum[j] >= rv
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)W.cum[mid] < rv) lo = mid + 1; else hi = mid; }
-                s_cand[t] = lo < ns - 1 ? lo : ns - 1;
-            }
+        if (threadIdx.x == 0) for (int t = 0; t < T; ++t) s_own[t] = rhccq_mt_double(mt);       // uniform(size=T), in order
+        __syncthreads();
+        RHCCQ_PAR_FOR(t, T) {                                      // the T searches side by side
+            const double rv = __dmul_rn(s_own[t], (double)pot);
+            int lo = 0, hi = ns;                                   // first j with cum[j] >= rv
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)W.cum[mid] < rv) lo = mid + 1; else hi = mid; }
+            s_cand[t] = lo < ns - 1 ? lo : ns - 1;
         }
         __syncthreads();
         uint32_t xc[RHCCQ_MB_MAXT];

@@ -33,6 +33,9 @@ def eps_threshold(eps: float):
 def _as_dev(be: Backend, x, dtype):
     if isinstance(x, torch.Tensor):
         return x.to(device=be.device, dtype=dtype).contiguous()
+    import numpy as np
+    if isinstance(x, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(x)).to(dtype).to(be.device).contiguous()
     return torch.as_tensor(x, dtype=dtype).to(be.device).contiguous()
 
 
@@ -108,25 +111,37 @@ def palette_finish(be: Backend, pal_keys, pal_off, pal_cnt, leaf, n_leaves, *, m
     return new_keys
 
 
-def cluster_palettes(be: Backend, pal_keys, pal_off, pal_cnt, quality, *, max_rows: int, max_cpc=None):
+def quality_params(be: Backend, quality, max_rows: int) -> dict:
+    """Device-resident radius parameters of a batch of problems from their qualities (host sequence):
+    eps = 128 - 1.28 q (0 -> 1, clustering.py:127,131-132), its integer threshold and tie flag, and the
+    slot bound of the DBSCAN cell table.  Worth caching: it only depends on the qualities."""
+    import numpy as np
+    q = np.asarray(quality, dtype=np.float64).reshape(-1)
+    uq, inv = np.unique(q, return_inverse=True)
+    eps_u = np.array([(128 - 1.28 * float(x)) or 1 for x in uq], dtype=np.float64)
+    tt_u = [eps_threshold(float(e)) for e in eps_u]
+    max_slots = max([be.cdll.rhccq_palette_dbscan_slots(t[0], int(max_rows)) for t in tt_u] + [1])
+    thr = np.array([t[0] for t in tt_u], dtype=np.int32)[inv]
+    tie = np.array([t[1] for t in tt_u], dtype=np.int32)[inv]
+    return {"q": _as_dev(be, q, torch.float64), "eps": _as_dev(be, eps_u[inv], torch.float64),
+            "thr": _as_dev(be, thr, I32), "tie": _as_dev(be, tie, I32), "max_slots": int(max_slots), "n": int(q.size)}
+
+
+def cluster_palettes(be: Backend, pal_keys, pal_off, pal_cnt, quality, *, max_rows: int, max_cpc=None, params=None):
     """a2 + a3' + a3/a4 + means for a batch of palettes on the device.
 
     ``quality``: host sequence, one per problem (eps and the slot bound come
-    from it on the host; max_cpc from the device-resident counts).
+    from it on the host; max_cpc from the device-resident counts); or pass
+    ``params`` = a cached `quality_params` result.
     Returns dict(labels, n_clusters, leaf, n_leaves, new_keys, max_cpc).
     """
     P = pal_cnt.numel()
-    q = [float(x) for x in quality]
-    eps_h = [(128 - 1.28 * x) or 1 for x in q]                      # clustering.py:127,131-132
-    tt = [eps_threshold(e) for e in eps_h]
-    max_slots = max([be.cdll.rhccq_palette_dbscan_slots(t[0], int(max_rows)) for t in set(tt)] + [1])
-    thr = _as_dev(be, [t[0] for t in tt], I32)
-    tie = _as_dev(be, [t[1] for t in tt], I32)
-    eps = _as_dev(be, eps_h, torch.float64)
-    labels, ncl = palette_dbscan(be, pal_keys, pal_off, pal_cnt, thr, tie, eps, max_rows=max_rows,
-                                 max_slots=max_slots)
-    q_dev = _as_dev(be, q, torch.float64)
-    if max_rows >= 10000:                                           # clustering.py:207: the MiniBatchKMeans branch can occur
+    if params is None:
+        params = quality_params(be, quality, max_rows)
+    labels, ncl = palette_dbscan(be, pal_keys, pal_off, pal_cnt, params["thr"], params["tie"], params["eps"],
+                                 max_rows=max_rows, max_slots=params["max_slots"])
+    q_dev = params["q"]
+    if max_rows >= 10000:                                          # clustering.py:207: the MiniBatchKMeans branch can occur
         palette_minibatch(be, pal_keys, pal_off, pal_cnt, q_dev, labels, ncl, max_rows=max_rows)
     if max_cpc is None:
         max_cpc = cluster_params(be, pal_cnt, q_dev)

@@ -52,6 +52,14 @@ class SegmentTable:
     n_valid: np.ndarray
     qualities: tuple = (20.0, 10.0)      # stage-1 quality per class (ROI, non-ROI)
 
+    def dev(self, be, name: str, make):
+        """Device copy of a host-side constant of this table, made once per backend."""
+        cache = self.__dict__.setdefault("_dev_cache", {})
+        key = (id(be), name)
+        if key not in cache:
+            cache[key] = make()
+        return cache[key]
+
     @property
     def P(self) -> int:
         return int(self.crops.shape[0])
@@ -171,12 +179,13 @@ def stage1(be: Backend, images, labels, table: SegmentTable) -> dict:
     if pal_off_h[-1] >= 2 ** 31:
         raise RhccqError("batch too large for int32 palette offsets; split the batch")
     max_valid = int(table.n_valid.max())
-    crops = _dev(be, crops_h)
-    pal_off = _dev(be, pal_off_h[:-1])
+    crops = table.dev(be, "crops", lambda: _dev(be, crops_h))
+    pal_off = table.dev(be, "pal_off", lambda: _dev(be, pal_off_h[:-1]))
     pal_keys, pal_cnt, plane = ops.unique_index(be, images, labels, crops, pal_off, int(pal_off_h[-1]),
                                                 idx_bytes=2, repaint_black=True, max_valid=max_valid,
                                                 n_classes=K)
-    s1 = ops.cluster_palettes(be, pal_keys, pal_off, pal_cnt, q1[cls_h], max_rows=max_valid + 1)
+    s1 = ops.cluster_palettes(be, pal_keys, pal_off, pal_cnt, None, max_rows=max_valid + 1,
+                              params=table.dev(be, "q1", lambda: ops.quality_params(be, q1[cls_h], max_valid + 1)))
     nl1_h = s1["n_leaves"][:P].cpu().numpy()                        # the one host synchronisation
     ops.check_counts("stage 1", torch.from_numpy(nl1_h))
     ent_off_h = np.zeros(P + 1, dtype=np.int64)
@@ -189,7 +198,8 @@ def stage1(be: Backend, images, labels, table: SegmentTable) -> dict:
     # merge level A: segments -> region (subregions.py:639-650)
     reg_first = np.searchsorted(table.seg_region, np.arange(R + 1)).astype(np.int32)   # segments of region r
     ent_per_region = ent_off_h[reg_first[1:]] - ent_off_h[reg_first[:-1]]
-    A = ops.merge_level(be, ent_color0, ent_fpos0, ent_off0, s1["n_leaves"], _dev(be, reg_first), R, E + R + 1,
+    A = ops.merge_level(be, ent_color0, ent_fpos0, ent_off0, s1["n_leaves"],
+                        table.dev(be, "reg_first", lambda: _dev(be, reg_first)), R, E + R + 1,
                         max_entries=int(max(ent_per_region.max(), 1)),
                         max_comps=int(max(np.diff(reg_first).max(), 1)))
     return {"pal_keys": pal_keys, "pal_off": pal_off, "pal_cnt": pal_cnt, "plane": plane, "s1": s1, "nl1": nl1_h,
@@ -213,25 +223,30 @@ def encode_batch(be: Backend, images, labels, table: SegmentTable, *, keep_stage
     grp_first = np.searchsorted(region_group_h, np.arange(G + 1)).astype(np.int32)   # regions of group g
     capA_cum = np.concatenate([[0], np.cumsum(ent_per_region + 1)])
     ent_per_group = capA_cum[grp_first[1:]] - capA_cum[grp_first[:-1]]
-    Bm = ops.merge_level(be, A["color"], A["fpos"], A["off"], A["cnt"], _dev(be, grp_first), G, E + R + G + 1,
+    Bm = ops.merge_level(be, A["color"], A["fpos"], A["off"], A["cnt"],
+                         table.dev(be, "grp_first", lambda: _dev(be, grp_first)), G, E + R + G + 1,
                          max_entries=int(max(ent_per_group.max(), 1)),
                          max_comps=int(max(np.diff(grp_first).max(), 1)))
     # ---- stage 2: cluster the class canvases (regions.py:45-68)
-    s2 = ops.cluster_palettes(be, Bm["color"], Bm["off"][:G], Bm["cnt"], np.tile(q2, B),
-                              max_rows=int(max(ent_per_group.max(), 1)) + 1)
+    mr2 = int(max(ent_per_group.max(), 1)) + 1
+    s2 = ops.cluster_palettes(be, Bm["color"], Bm["off"][:G], Bm["cnt"], None, max_rows=mr2,
+                              params=ops.quality_params(be, np.tile(q2, B), mr2))
     fpos2 = ops.first_min(be, Bm["off"], Bm["cnt"], s2["n_leaves"], s2["leaf"], Bm["fpos"])
     # ---- merge level C: classes -> image (image.py:246-256)
     img_first = (np.arange(B + 1) * K).astype(np.int32)
     ent_per_image = (ent_per_group + 1).reshape(B, K).sum(axis=1)
-    Cm = ops.merge_level(be, s2["new_keys"], fpos2, Bm["off"], s2["n_leaves"], _dev(be, img_first), B,
+    Cm = ops.merge_level(be, s2["new_keys"], fpos2, Bm["off"], s2["n_leaves"],
+                         table.dev(be, "img_first", lambda: _dev(be, img_first)), B,
                          E + R + G + B + 1, max_entries=int(ent_per_image.max()), max_comps=K)
     # ---- stage 3 (image.py:261-286)
     s3 = ops.cluster_palettes(be, Cm["color"], Cm["off"][:B], Cm["cnt"], [q3] * B,
                               max_rows=int(ent_per_image.max()) + 1)
     # ---- compose and paint (last listed class first: merging.py:52)
     group_image_h = (np.arange(G) // K).astype(np.int32)
-    ent_final = ops.compose_final(be, P, s1["n_leaves"], ent_off0, _dev(be, table.seg_region),
-                                  _dev(be, region_group_h), _dev(be, group_image_h), A, Bm, s2["leaf"],
+    ent_final = ops.compose_final(be, P, s1["n_leaves"], ent_off0,
+                                  table.dev(be, "seg_region", lambda: _dev(be, table.seg_region)),
+                                  table.dev(be, "region_group", lambda: _dev(be, region_group_h)),
+                                  table.dev(be, "group_image", lambda: _dev(be, group_image_h)), A, Bm, s2["leaf"],
                                   s2["new_keys"], Cm, s3["leaf"], E)
     out = be.zeros((B, H, W), torch.int16)
     for k in range(K - 1, -1, -1):
