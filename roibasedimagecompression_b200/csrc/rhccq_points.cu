@@ -738,7 +738,6 @@ int rhccq_dbscan_relabel(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, 
 // caller then takes the generic path), and writes the count and a packed colour (+ core bit) per pixel — its
 // HBM traffic is the algorithmic 24 bytes per point plus 4.
 #define RHCCQ_LT_W 64
-#define RHCCQ_LT_H 16
 #define RHCCQ_LT_MAXR 16
 #define RHCCQ_LT_INVALID 0xFF000000u
 #define RHCCQ_LT_CORE 0x01000000u
@@ -747,15 +746,18 @@ struct rhccq_lt_args {
     int H, W, R, thr, min_pts, n_off;
 };
 
-__device__ __forceinline__ int rhccq_lt_build_offsets(int* offs, int R, int thr, bool forward_only) {
-    // (dy, dx, colour budget) of the stencil, raster order; built by one thread (a few hundred entries)
+// stencil entries, raster order: x = (dy + 64) << 8 | (dx + 64), y = colour budget thr - (dy^2 + dx^2).
+// Built by one thread (a few hundred entries at most).
+__device__ __forceinline__ int rhccq_lt_build_offsets(int2* offs, int R, int thr, bool forward_only) {
     int n = 0;
     for (int dy = -R; dy <= R; ++dy)
         for (int dx = -R; dx <= R; ++dx) {
             const int s = dy * dy + dx * dx;
             if (s > thr) continue;
             if (forward_only && !(dy > 0 || (dy == 0 && dx > 0))) continue;
-            offs[n++] = ((dy + 64) << 24) | ((dx + 64) << 16) | (thr - s);       // budget < 65536
+            offs[n].x = ((dy + 64) << 8) | (dx + 64);
+            offs[n].y = thr - s;
+            ++n;
         }
     return n;
 }
@@ -787,77 +789,117 @@ __device__ __forceinline__ void rhccq_lt_load_tile(const void* src, const rhccq_
     }
 }
 
-// MODE 0: count (+ packed colours with the core bit), 1: union, 2: border attachment
-template <int MODE, int SRC>
+#define RHCCQ_LT_PPT 4        // pixels per thread of the count pass: rows ly, ly + TH/4, ...
+
+// MODE 0: count (+ packed colours with the core bit)
+//      1: union inside the tile (shared-memory union-find), result as a star forest in `parent`
+//      3: union across tile borders (global union-find), after every tile has finished mode 1
+//      2: border attachment
+template <int MODE, int SRC, int TH>
 __global__ void __launch_bounds__(RHCCQ_PT_THREADS)
 rhccq_k_lt_sweep(const void* __restrict__ src, rhccq_lt_args A, int* __restrict__ count, uint32_t* __restrict__ packed,
                  uint8_t* __restrict__ core, int* __restrict__ parent, int* __restrict__ rootlab, int* __restrict__ status) {
     RHCCQ_DYN_SMEM(dyn);
     __shared__ int s_noff, s_bad;
-    const int tw = RHCCQ_LT_W + 2 * A.R, th = RHCCQ_LT_H + 2 * A.R;
+    const int tw = RHCCQ_LT_W + 2 * A.R, th = TH + 2 * A.R;
     uint32_t* tile = reinterpret_cast<uint32_t*>(dyn);
-    int* offs = reinterpret_cast<int*>(tile + (size_t)tw * th);
-    if (threadIdx.x == 0) { s_noff = rhccq_lt_build_offsets(offs, A.R, A.thr, MODE == 1); s_bad = 0; }
+    int2* offs = reinterpret_cast<int2*>(tile + (((size_t)tw * th + 1) & ~(size_t)1));
+    int* lpar = reinterpret_cast<int*>(offs + (2 * A.R + 1) * (2 * A.R + 1));      // MODE 1: local parents
+    if (threadIdx.x == 0) { s_noff = rhccq_lt_build_offsets(offs, A.R, A.thr, MODE == 1 || MODE == 3); s_bad = 0; }
     __syncthreads();
     const int n_off = s_noff;
-    const int tiles_x = (A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W, tiles_y = (A.H + RHCCQ_LT_H - 1) / RHCCQ_LT_H;
+    const int tiles_x = (A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W, tiles_y = (A.H + TH - 1) / TH;
     for (int tI = blockIdx.x; tI < tiles_x * tiles_y; tI += gridDim.x) {
-        const int ty0 = (tI / tiles_x) * RHCCQ_LT_H, tx0 = (tI % tiles_x) * RHCCQ_LT_W;
+        const int ty0 = (tI / tiles_x) * TH, tx0 = (tI % tiles_x) * RHCCQ_LT_W;
         rhccq_lt_load_tile<SRC>(src, A, ty0, tx0, tile, tw, th, &s_bad);
+        if (MODE == 1) RHCCQ_PAR_FOR(t, RHCCQ_LT_W * TH) lpar[t] = t;
         __syncthreads();
-        RHCCQ_PAR_FOR(t, RHCCQ_LT_W * RHCCQ_LT_H) {
-            const int ly = t / RHCCQ_LT_W, lx = t % RHCCQ_LT_W;
-            const int y = ty0 + ly, x = tx0 + lx;
-            if (y >= A.H || x >= A.W) continue;
-            const int ci = (ly + A.R) * tw + lx + A.R;
-            const uint32_t me = tile[ci];
-            const uint32_t c = me & 0x00ffffffu;
-            const int id = y * A.W + x;
-            if (MODE == 0) {
-                int acc = 0;
-                for (int o = 0; o < n_off; ++o) {
-                    const int e = offs[o];
-                    const uint32_t nb = tile[ci + ((e >> 24) - 64) * tw + (((e >> 16) & 255) - 64)];
-                    acc += (int)((unsigned)rhccq_d2(c, nb) <= (unsigned)(e & 0xffff));     // 0xFF top byte: never within
+        if (MODE == 0) {
+            // every thread owns RHCCQ_LT_PPT pixels of one column: a stencil entry is decoded once for all of them
+            RHCCQ_PAR_FOR(t, RHCCQ_LT_W * (TH / RHCCQ_LT_PPT)) {
+                const int ly = t / RHCCQ_LT_W, lx = t % RHCCQ_LT_W;
+                int ci[RHCCQ_LT_PPT], acc[RHCCQ_LT_PPT];
+                uint32_t c[RHCCQ_LT_PPT];
+#pragma unroll
+                for (int u = 0; u < RHCCQ_LT_PPT; ++u) {
+                    ci[u] = (ly + u * (TH / RHCCQ_LT_PPT) + A.R) * tw + lx + A.R;
+                    c[u] = tile[ci[u]] & 0x00ffffffu;
+                    acc[u] = 0;
                 }
-                count[id] = acc;
-                const int is_core = acc >= A.min_pts;
-                core[id] = (uint8_t)is_core;
-                packed[id] = c | (is_core ? RHCCQ_LT_CORE : 0u);
-            } else if (MODE == 1) {
-                if (!(me & RHCCQ_LT_CORE)) continue;
-                int my_root = id;
                 for (int o = 0; o < n_off; ++o) {
-                    const int e = offs[o];
-                    const int dy = (e >> 24) - 64, dx = ((e >> 16) & 255) - 64;
+                    const int2 e = offs[o];
+                    const int delta = ((e.x >> 8) - 64) * tw + ((e.x & 255) - 64);
+#pragma unroll
+                    for (int u = 0; u < RHCCQ_LT_PPT; ++u)                 // 0xFF top byte (outside): never within
+                        acc[u] += (int)((unsigned)rhccq_d2(c[u], tile[ci[u] + delta]) <= (unsigned)e.y);
+                }
+#pragma unroll
+                for (int u = 0; u < RHCCQ_LT_PPT; ++u) {
+                    const int y = ty0 + ly + u * (TH / RHCCQ_LT_PPT), x = tx0 + lx;
+                    if (y >= A.H || x >= A.W) continue;
+                    const int id = y * A.W + x;
+                    const int is_core = acc[u] >= A.min_pts;
+                    count[id] = acc[u];
+                    core[id] = (uint8_t)is_core;
+                    packed[id] = c[u] | (is_core ? RHCCQ_LT_CORE : 0u);
+                }
+            }
+        } else {
+            RHCCQ_PAR_FOR(t, RHCCQ_LT_W * TH) {
+                const int ly = t / RHCCQ_LT_W, lx = t % RHCCQ_LT_W;
+                const int y = ty0 + ly, x = tx0 + lx;
+                if (y >= A.H || x >= A.W) continue;
+                const int ci = (ly + A.R) * tw + lx + A.R;
+                const uint32_t me = tile[ci];
+                const uint32_t c = me & 0x00ffffffu;
+                const int id = y * A.W + x;
+                const bool me_core = (me & RHCCQ_LT_CORE) != 0u;
+                if ((MODE == 2) == me_core) continue;                   // unions: core pixels; attachment: the others
+                int best = 0x7fffffff, my_root = id;
+                for (int o = 0; o < n_off; ++o) {
+                    const int2 e = offs[o];
+                    const int dy = (e.x >> 8) - 64, dx = (e.x & 255) - 64;
+                    const bool inside = (unsigned)(ly + dy) < (unsigned)TH && (unsigned)(lx + dx) < (unsigned)RHCCQ_LT_W;
+                    if (MODE == 1 && !inside) continue;                 // the cross-border pass links those
+                    if (MODE == 3 && inside) continue;
                     const uint32_t nb = tile[ci + dy * tw + dx];
-                    if ((nb >> 24) != 1u) continue;                                        // outside, or not core
-                    if ((unsigned)rhccq_d2(c, nb & 0x00ffffffu) > (unsigned)(e & 0xffff)) continue;
-                    const int nid = id + dy * A.W + dx;                                    // forward: nid > id
-                    if (((volatile int*)parent)[nid] != my_root) {
-                        rhccq_pt_union(parent, nid, id);
-                        my_root = rhccq_pt_find(parent, id);
+                    if ((nb >> 24) != 1u) continue;                     // outside the image, or not core
+                    if ((unsigned)rhccq_d2(c, nb & 0x00ffffffu) > (unsigned)e.y) continue;
+                    if (MODE == 1) {
+                        rhccq_pt_union(lpar, t + dy * RHCCQ_LT_W + dx, t);
+                    } else if (MODE == 3) {
+                        const int nid = id + dy * A.W + dx;
+                        if (((volatile int*)parent)[nid] != my_root) {
+                            rhccq_pt_union(parent, nid, id);
+                            my_root = rhccq_pt_find(parent, id);
+                        }
+                    } else {
+                        const int r = rootlab[id + dy * A.W + dx];
+                        best = r < best ? r : best;
                     }
                 }
-            } else {
-                if (me & RHCCQ_LT_CORE) continue;                                          // core pixels keep their root
-                int best = 0x7fffffff;
-                for (int o = 0; o < n_off; ++o) {
-                    const int e = offs[o];
-                    const int dy = (e >> 24) - 64, dx = ((e >> 16) & 255) - 64;
-                    const uint32_t nb = tile[ci + dy * tw + dx];
-                    if ((nb >> 24) != 1u) continue;
-                    if ((unsigned)rhccq_d2(c, nb & 0x00ffffffu) > (unsigned)(e & 0xffff)) continue;
-                    const int r = rootlab[id + dy * A.W + dx];
-                    best = r < best ? r : best;
+                if (MODE == 2) rootlab[id] = best == 0x7fffffff ? -1 : best;
+            }
+            if (MODE == 1) {
+                // local sets -> stars in the global forest: local raster order is global index order inside a tile,
+                // so a set's local root is its lowest global index
+                __syncthreads();
+                RHCCQ_PAR_FOR(t, RHCCQ_LT_W * TH) {
+                    const int ly = t / RHCCQ_LT_W, lx = t % RHCCQ_LT_W;
+                    const int y = ty0 + ly, x = tx0 + lx;
+                    if (y >= A.H || x >= A.W) continue;
+                    const int r = rhccq_pt_find_ro(lpar, t);
+                    parent[y * A.W + x] = (ty0 + r / RHCCQ_LT_W) * A.W + tx0 + r % RHCCQ_LT_W;
                 }
-                rootlab[id] = best == 0x7fffffff ? -1 : best;
             }
         }
         __syncthreads();
     }
     if (MODE == 0 && SRC == 0 && threadIdx.x == 0 && s_bad) *status = 1;
 }
+
+#define RHCCQ_LT_H 16         // tile height of the count and attachment passes
+#define RHCCQ_LT_UH 32        // tile height of the union passes: fewer edges cross tile borders
 
 static int rhccq_lt_args_make(int H, int W, double eps, int min_pts, rhccq_lt_args* A) {
     if (H < 1 || W < 1 || (long long)H * W > 2000000000LL || !(eps > 0.0) || min_pts < 1) {
@@ -874,12 +916,12 @@ static int rhccq_lt_args_make(int H, int W, double eps, int min_pts, rhccq_lt_ar
     A->H = H; A->W = W; A->R = R; A->thr = (int)floor(r2); A->min_pts = min_pts; A->n_off = 0;
     return 0;
 }
-static size_t rhccq_lt_smem(const rhccq_lt_args& A) {
+static size_t rhccq_lt_smem(const rhccq_lt_args& A, int TH) {
     const size_t side = 2 * (size_t)A.R + 1;
-    return ((size_t)(RHCCQ_LT_W + 2 * A.R) * (RHCCQ_LT_H + 2 * A.R) + side * side + 4) * 4;
+    return ((size_t)(RHCCQ_LT_W + 2 * A.R) * (TH + 2 * A.R) + 2) * 4 + side * side * 8 + (size_t)RHCCQ_LT_W * TH * 4;
 }
-static int rhccq_lt_grid(const rhccq_lt_args& A) {
-    const long long tiles = (long long)((A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W) * ((A.H + RHCCQ_LT_H - 1) / RHCCQ_LT_H);
+static int rhccq_lt_grid(const rhccq_lt_args& A, int TH) {
+    const long long tiles = (long long)((A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W) * ((A.H + TH - 1) / TH);
     const long long cap = (long long)rhccq_sm_count() * 32;
     return (int)(tiles < cap ? tiles : cap);
 }
@@ -909,7 +951,8 @@ static void rhccq_lt_carve(int H, int W, void* ws, rhccq_lt_ws* L) {
     if (!ws || ws_bytes < rhccq_dbscan_lattice_workspace_bytes(H, W)) {                                 \
         rhccq_set_error(name ": workspace missing or too small"); return -1; }                          \
     rhccq_lt_ws L; rhccq_lt_carve(H, W, ws, &L);                                                        \
-    const size_t smem = rhccq_lt_smem(A); const int grid = rhccq_lt_grid(A);
+    const size_t smem = rhccq_lt_smem(A, RHCCQ_LT_H); const int grid = rhccq_lt_grid(A, RHCCQ_LT_H);                       \
+    (void)smem; (void)grid;
 
 int rhccq_dbscan_lattice_count(const void* src, int src_kind, int H, int W, double eps, int min_pts, int32_t* count,
                                uint8_t* core, int32_t* status, void* ws, size_t ws_bytes, void* stream) {
@@ -921,11 +964,11 @@ int rhccq_dbscan_lattice_count(const void* src, int src_kind, int H, int W, doub
     cudaMemsetAsync(status, 0, 4, (cudaStream_t)stream);
 #endif
     if (src_kind == 0) {
-        if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<0, 0>, smem) != 0) return -1;
-        RHCCQ_LAUNCH((rhccq_k_lt_sweep<0, 0>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, src, A, count, L.packed, core, L.parent, L.rootlab, status);
+        if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<0, 0, RHCCQ_LT_H>, smem) != 0) return -1;
+        RHCCQ_LAUNCH((rhccq_k_lt_sweep<0, 0, RHCCQ_LT_H>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, src, A, count, L.packed, core, L.parent, L.rootlab, status);
     } else {
-        if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<0, 1>, smem) != 0) return -1;
-        RHCCQ_LAUNCH((rhccq_k_lt_sweep<0, 1>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, src, A, count, L.packed, core, L.parent, L.rootlab, status);
+        if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<0, 1, RHCCQ_LT_H>, smem) != 0) return -1;
+        RHCCQ_LAUNCH((rhccq_k_lt_sweep<0, 1, RHCCQ_LT_H>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, src, A, count, L.packed, core, L.parent, L.rootlab, status);
     }
     return 0;
 }
@@ -933,17 +976,23 @@ int rhccq_dbscan_lattice_count(const void* src, int src_kind, int H, int W, doub
 int rhccq_dbscan_lattice_union(int H, int W, double eps, int min_pts, void* ws, size_t ws_bytes, void* stream) {
     RHCCQ_LT_PROLOGUE("rhccq_dbscan_lattice_union")
     RHCCQ_LAUNCH(rhccq_k_pt_init_parent, rhccq_pt_blocks((long long)H * W), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, H * W, L.parent);
-    if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<1, 2>, smem) != 0) return -1;
-    RHCCQ_LAUNCH((rhccq_k_lt_sweep<1, 2>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, (const void*)L.packed, A, (int*)nullptr, L.packed,
-                 (uint8_t*)nullptr, L.parent, L.rootlab, (int*)nullptr);
+    // (the init above is overwritten for every pixel by the tile-local pass; it keeps the array defined)
+    const size_t usmem = rhccq_lt_smem(A, RHCCQ_LT_UH);
+    const int ugrid = rhccq_lt_grid(A, RHCCQ_LT_UH);
+    if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<1, 2, RHCCQ_LT_UH>, usmem) != 0) return -1;
+    RHCCQ_LAUNCH((rhccq_k_lt_sweep<1, 2, RHCCQ_LT_UH>), ugrid, RHCCQ_PT_THREADS, usmem, (cudaStream_t)stream, (const void*)L.packed, A,
+                 (int*)nullptr, L.packed, (uint8_t*)nullptr, L.parent, L.rootlab, (int*)nullptr);
+    if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<3, 2, RHCCQ_LT_UH>, usmem) != 0) return -1;
+    RHCCQ_LAUNCH((rhccq_k_lt_sweep<3, 2, RHCCQ_LT_UH>), ugrid, RHCCQ_PT_THREADS, usmem, (cudaStream_t)stream, (const void*)L.packed, A,
+                 (int*)nullptr, L.packed, (uint8_t*)nullptr, L.parent, L.rootlab, (int*)nullptr);
     return 0;
 }
 
 int rhccq_dbscan_lattice_border(int H, int W, double eps, int min_pts, const uint8_t* core, void* ws, size_t ws_bytes, void* stream) {
     RHCCQ_LT_PROLOGUE("rhccq_dbscan_lattice_border")
     RHCCQ_LAUNCH(rhccq_k_pt_flatten, rhccq_pt_blocks((long long)H * W), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, H * W, L.parent, core, L.rootlab, L.is_root);
-    if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<2, 2>, smem) != 0) return -1;
-    RHCCQ_LAUNCH((rhccq_k_lt_sweep<2, 2>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, (const void*)L.packed, A, (int*)nullptr, L.packed,
+    if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<2, 2, RHCCQ_LT_H>, smem) != 0) return -1;
+    RHCCQ_LAUNCH((rhccq_k_lt_sweep<2, 2, RHCCQ_LT_H>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, (const void*)L.packed, A, (int*)nullptr, L.packed,
                  (uint8_t*)nullptr, L.parent, L.rootlab, (int*)nullptr);
     return 0;
 }
