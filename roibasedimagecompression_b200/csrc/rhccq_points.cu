@@ -789,7 +789,7 @@ __device__ __forceinline__ void rhccq_lt_load_tile(const void* src, const rhccq_
     }
 }
 
-#define RHCCQ_LT_PPT 4        // pixels per thread of the count pass: rows ly, ly + TH/4, ...
+#define RHCCQ_LT_PPT 8        // pixels per thread of the count pass: rows ly, ly + TH/8, ...
 
 // MODE 0: count (+ packed colours with the core bit)
 //      1: union inside the tile (shared-memory union-find), result as a star forest in `parent`
@@ -826,12 +826,14 @@ rhccq_k_lt_sweep(const void* __restrict__ src, rhccq_lt_args A, int* __restrict_
                     c[u] = tile[ci[u]] & 0x00ffffffu;
                     acc[u] = 0;
                 }
+                const uint32_t* base = tile + ci[0];
+                const int rstep = (TH / RHCCQ_LT_PPT) * tw;
                 for (int o = 0; o < n_off; ++o) {
                     const int2 e = offs[o];
-                    const int delta = ((e.x >> 8) - 64) * tw + ((e.x & 255) - 64);
+                    const uint32_t* nbp = base + ((e.x >> 8) - 64) * tw + ((e.x & 255) - 64);
 #pragma unroll
                     for (int u = 0; u < RHCCQ_LT_PPT; ++u)                 // 0xFF top byte (outside): never within
-                        acc[u] += (int)((unsigned)rhccq_d2(c[u], tile[ci[u] + delta]) <= (unsigned)e.y);
+                        acc[u] += (int)((unsigned)rhccq_d2(c[u], nbp[u * rstep]) <= (unsigned)e.y);
                 }
 #pragma unroll
                 for (int u = 0; u < RHCCQ_LT_PPT; ++u) {
@@ -963,12 +965,14 @@ int rhccq_dbscan_lattice_count(const void* src, int src_kind, int H, int W, doub
 #else
     cudaMemsetAsync(status, 0, 4, (cudaStream_t)stream);
 #endif
+    const size_t csmem = rhccq_lt_smem(A, RHCCQ_LT_UH);
+    const int cgrid = rhccq_lt_grid(A, RHCCQ_LT_UH);
     if (src_kind == 0) {
-        if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<0, 0, RHCCQ_LT_H>, smem) != 0) return -1;
-        RHCCQ_LAUNCH((rhccq_k_lt_sweep<0, 0, RHCCQ_LT_H>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, src, A, count, L.packed, core, L.parent, L.rootlab, status);
+        if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<0, 0, RHCCQ_LT_UH>, csmem) != 0) return -1;
+        RHCCQ_LAUNCH((rhccq_k_lt_sweep<0, 0, RHCCQ_LT_UH>), cgrid, RHCCQ_PT_THREADS, csmem, (cudaStream_t)stream, src, A, count, L.packed, core, L.parent, L.rootlab, status);
     } else {
-        if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<0, 1, RHCCQ_LT_H>, smem) != 0) return -1;
-        RHCCQ_LAUNCH((rhccq_k_lt_sweep<0, 1, RHCCQ_LT_H>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, src, A, count, L.packed, core, L.parent, L.rootlab, status);
+        if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<0, 1, RHCCQ_LT_UH>, csmem) != 0) return -1;
+        RHCCQ_LAUNCH((rhccq_k_lt_sweep<0, 1, RHCCQ_LT_UH>), cgrid, RHCCQ_PT_THREADS, csmem, (cudaStream_t)stream, src, A, count, L.packed, core, L.parent, L.rootlab, status);
     }
     return 0;
 }

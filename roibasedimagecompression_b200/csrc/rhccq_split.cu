@@ -212,6 +212,7 @@ struct rhccq_km_centers {
     int* hist;                          // [nsub * 4k] per-warp (r, g, b, count) accumulators, or nullptr
     int* cand;                          // [RHCCQ_KM_MAXT]
     int* poff;                          // [k * nsub] offsets of the counting partition, or nullptr (sort instead)
+    int* wl;                            // worklist counter of the pruned E step, or nullptr (evaluate every centre)
 };
 
 __device__ __forceinline__ double rhccq_dist3(double x0, double x1, double x2, const double* c) {
@@ -240,6 +241,22 @@ __device__ __forceinline__ void rhccq_nearest_centers(const uint32_t (&c)[RHCCQ_
             const double d = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
             if (d < best[u]) { best[u] = d; bi[u] = q; }
         }
+    }
+}
+
+// M-step accumulation of one point into a table of (r, g, b, count) rows / into the sums and counts.
+// Plain shared-memory atomics: summing equal labels inside the warp first (match_any + reduce_add) was
+// measured twice as slow on B200 as letting the atomic unit serialise the conflicts.
+__device__ __forceinline__ void rhccq_acc_rows(int* rows, int stride, int bi, uint32_t c, bool valid) {
+    if (valid) {
+        int* h = rows + stride * bi;
+        atomicAdd(h, rhccq_key_r(c)); atomicAdd(h + 1, rhccq_key_g(c)); atomicAdd(h + 2, rhccq_key_b(c)); atomicAdd(h + 3, 1);
+    }
+}
+__device__ __forceinline__ void rhccq_acc_split(int* sums, int* cnt, int bi, uint32_t c, bool valid) {
+    if (valid) {
+        atomicAdd(&sums[3 * bi], rhccq_key_r(c)); atomicAdd(&sums[3 * bi + 1], rhccq_key_g(c));
+        atomicAdd(&sums[3 * bi + 2], rhccq_key_b(c)); atomicAdd(&cnt[bi], 1);
     }
 }
 
@@ -357,30 +374,69 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
     g.sync();
     bool strict = false;
     for (int it = 0; it < 300; ++it) {
-        // E step fused with the accumulation of the M step
+        // E step fused with the accumulation of the M step.
+        //
+        // A point whose distance to the centre of its previous cluster is (safely) less than half the
+        // distance from that centre to the nearest other centre keeps its cluster by the triangle
+        // inequality — every other centre is strictly farther by a margin far above the rounding of the
+        // distance evaluation — so it skips the loop over the centres.  The result is identical to
+        // evaluating every centre; only points near a cluster border (about 40 %) go to the full loop,
+        // compacted into a worklist so that the warps of that loop stay full.
         int changed = 0;
-        for (int j0 = tid; j0 < n; j0 += RHCCQ_EB * gsz) {
+        const bool prune = it > 0 && C.wl != nullptr && (long long)n * k >= 200000;    // small problems: the extra pass costs more than it saves
+        uint32_t* wl = reinterpret_cast<uint32_t*>(closest);       // dead after the seeding; positions of this range
+        if (prune) {
+            for (int q = tid; q < k; q += gsz) {
+                const double* cq = C.center + 3 * q;
+                double m = 1.0e300;
+                for (int r = 0; r < k; ++r) {
+                    if (r == q) continue;
+                    const double d = rhccq_dist3(cq[0], cq[1], cq[2], C.center + 3 * r);
+                    m = d < m ? d : m;
+                }
+                // usable only when the centres are at least 1 apart: then the margin below (1e-6 relative)
+                // is thousands of times the rounding error of a distance (< 1e-9 absolute)
+                C.term[q] = m >= 1.0 ? __dmul_rn(__dmul_rn(0.25, m), 0.999999) : 0.0;
+            }
+            if (tid == 0) *C.wl = 0;
+            g.sync();
+            for (int j = tid; j - RHCCQ_LANE < n; j += gsz) {           // warp-uniform trip count
+                const bool have = j < n;
+                const uint32_t c = x[have ? j : 0];
+                const int a = have ? (int)label[j] : 0;
+                const double u = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c), (double)rhccq_key_b(c),
+                                             C.center + 3 * a);
+                const bool keep = have && u < C.term[a];
+                if (acc_base) rhccq_acc_rows(acc_base, 4, a, c, keep);
+                else rhccq_acc_split(C.sums, C.cnt, a, c, keep);
+                if (have && !keep) wl[atomicAdd(C.wl, 1)] = (uint32_t)j;
+            }
+            g.sync();
+        }
+        const int n_work = prune ? *C.wl : n;
+        for (int i0 = tid; i0 - RHCCQ_LANE < n_work; i0 += RHCCQ_EB * gsz) {      // warp-uniform trip count
             uint32_t cb[RHCCQ_EB];
-            int bb[RHCCQ_EB];
+            int bb[RHCCQ_EB], jj[RHCCQ_EB];
 #pragma unroll
-            for (int u = 0; u < RHCCQ_EB; ++u) { const int j = j0 + u * gsz; cb[u] = x[j < n ? j : j0]; }
+            for (int u = 0; u < RHCCQ_EB; ++u) {
+                const int i = i0 + u * gsz;
+                const int is = i < n_work ? i : 0;                      // lanes past the end recompute entry 0 and drop it
+                jj[u] = prune ? (int)wl[is] : is;
+                cb[u] = x[jj[u]];
+            }
             rhccq_nearest_centers(cb, C.center, k, bb);
 #pragma unroll
             for (int u = 0; u < RHCCQ_EB; ++u) {
-                const int j = j0 + u * gsz;
-                if (j >= n) continue;
+                const bool have = i0 + u * gsz < n_work;
+                const int j = jj[u];
                 const uint32_t c = cb[u];
                 const int bi = bb[u];
-                if ((int)label[j] != bi) changed = 1;
-                label[j] = (idx_t)bi;
-                if (acc_base) {
-                    int* h = acc_base + 4 * bi;
-                    atomicAdd(h, rhccq_key_r(c)); atomicAdd(h + 1, rhccq_key_g(c)); atomicAdd(h + 2, rhccq_key_b(c));
-                    atomicAdd(h + 3, 1);
-                } else {
-                    atomicAdd(&C.sums[3 * bi], rhccq_key_r(c)); atomicAdd(&C.sums[3 * bi + 1], rhccq_key_g(c));
-                    atomicAdd(&C.sums[3 * bi + 2], rhccq_key_b(c)); atomicAdd(&C.cnt[bi], 1);
+                if (have) {
+                    if ((int)label[j] != bi) changed = 1;
+                    label[j] = (idx_t)bi;
                 }
+                if (acc_base) rhccq_acc_rows(acc_base, 4, bi, c, have);
+                else rhccq_acc_split(C.sums, C.cnt, bi, c, have);
             }
         }
         changed = g.any(changed);
@@ -660,7 +716,8 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     typedef typename Cfg::q_t q_t;
     __shared__ long long s_ll[RHCCQ_MAX_WARPS * RHCCQ_KM_MAXT + 2];
     __shared__ int s_scan[RHCCQ_MAX_WARPS + 2];
-    __shared__ int s_tail, s_err, s_base, s_claim;
+    __shared__ int s_tail, s_err, s_base, s_claim, s_wl;
+    __shared__ int wlc[RHCCQ_MAX_WARPS];
     const int n = B.pal_cnt[p];
     const uint32_t* keys = B.pal_keys + B.pal_off[p];
     const int* lab = labels + B.pal_off[p];
@@ -806,11 +863,13 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
                 rhccq_km_centers C = CS;
                 C.hist = k <= RHCCQ_KPRIV ? hist : nullptr;
                 C.poff = poff;
+                C.wl = &s_wl;
                 rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
             } else {
                 rhccq_km_centers C = CG;
                 C.hist = nullptr;
                 C.poff = nullptr;
+                C.wl = nullptr;
                 rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
             }
         }
@@ -838,6 +897,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
             C.sums = wi; C.cnt = wi + 3 * RHCCQ_KW; C.poff = wi + 4 * RHCCQ_KW;
             C.hist = nullptr;
             C.cand = cand + RHCCQ_WARP * RHCCQ_KM_MAXT;
+            C.wl = wlc + RHCCQ_WARP;
             rhccq_split_range<rhccq_grp_warp, Cfg>(gw, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
         }
         head = tail;
