@@ -27,6 +27,17 @@
 #include "rhccq_common.cuh"
 #include "rhccq_kernels.h"
 
+// Optional phase timers (cycles summed over all CTAs into rhccq_split_prof[8]); compiled in with
+// -DRHCCQ_SPLIT_PROFILE by tools/split_phases.py only.
+#if defined(RHCCQ_SPLIT_PROFILE) && !defined(RHCCQ_HOST_EMU)
+__device__ unsigned long long rhccq_split_prof[8];
+#define RHCCQ_PROF_T0() long long prof_t_ = clock64()
+#define RHCCQ_PROF(slot) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&rhccq_split_prof[slot], (unsigned long long)(n_ - prof_t_)); prof_t_ = n_; } } while (0)
+#else
+#define RHCCQ_PROF_T0() do {} while (0)
+#define RHCCQ_PROF(slot) do {} while (0)
+#endif
+
 #define RHCCQ_SPLIT_THREADS 256
 #define RHCCQ_KM_MAXT 12               // 2 + int(log(k)) for k < 22027
 #define RHCCQ_KC 128                   // centres of a CTA-level K-Means kept in shared memory
@@ -80,6 +91,14 @@ struct rhccq_grp_cta {
     __device__ __forceinline__ int nsub() const { return RHCCQ_NWARPS; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
     __device__ __forceinline__ int any(int v) const { return rhccq_block_or(v, (int*)sll); }
+    // number of true flags over the group (every thread holds 0 or 1): one barrier
+    __device__ __forceinline__ int count(int v) const {
+#ifdef RHCCQ_HOST_EMU
+        return v;
+#else
+        return __syncthreads_count(v);
+#endif
+    }
     template <class T> __device__ __forceinline__ T excl_scan(T v, T* total) const {
         return rhccq_block_excl_scan<T>(v, total, reinterpret_cast<T*>(sll));
     }
@@ -135,6 +154,7 @@ struct rhccq_grp_warp {
     __device__ __forceinline__ double max_d(double v) const { return v; }
     __device__ __forceinline__ int min_i(int v) const { return v; }
     __device__ __forceinline__ int sum_i(int v) const { return v; }
+    __device__ __forceinline__ int count(int v) const { return v; }
     __device__ __forceinline__ void sum_vec(long long*, int) const {}
     __device__ __forceinline__ double bcast_d(double v) const { return v; }
 #else
@@ -170,6 +190,7 @@ struct rhccq_grp_warp {
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
         return v;
     }
+    __device__ __forceinline__ int count(int v) const { return sum_i(v); }
     __device__ __forceinline__ void sum_vec(long long* v, int cnt) const {
         __syncwarp();
 #pragma unroll
@@ -278,6 +299,7 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
     const int c_lo = tid * per < n ? tid * per : n;
     const int c_hi = c_lo + per < n ? c_lo + per : n;
 
+    RHCCQ_PROF_T0();
     // ---- k-means++ seeding (kmeans_restated.kmeans_pp_seeds)
     const int T = rhccq_kmeans_local_trials(k);
     int first = (int)__dmul_rn(rng[0], (double)n);
@@ -356,6 +378,7 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
         // the next pass writes cum / cand only after a collective, which orders it after the reads above
     }
 
+    if (g.size() > RHCCQ_WARP_SIZE) RHCCQ_PROF(1);
     // ---- tolerance (kmeans_restated.tolerance)
     double tol;
     {
@@ -366,32 +389,37 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
     }
 
     // ---- Lloyd (kmeans_restated.kmeans_labels)
+    //
+    // The cluster sums of the M step are kept incrementally: a point only touches them when its label
+    // changes (- old cluster, + new cluster; integers, so the result is the sum over the members exactly).
+    // After the first few iterations a few percent of the points move, which takes the shared-memory
+    // atomics — the main cost next to the distances — off the critical path.  An empty-cluster relocation
+    // edits the sums without changing labels, so the iteration after one recounts from scratch.
     const idx_t NOLABEL = (idx_t)(Cfg::FLAG - 1u);                  // never a real label (k < FLAG - 1)
     for (int j = tid; j < n; j += gsz) label[j] = NOLABEL;
-    int* acc_base = C.hist ? C.hist + (size_t)g.sub() * 4 * k : nullptr;
-    if (C.hist) { for (int q = tid; q < g.nsub() * 4 * k; q += gsz) C.hist[q] = 0; }
-    else { for (int q = tid; q < k; q += gsz) { C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0; } }
+    for (int q = tid; q < k; q += gsz) { C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0; }
+    double* cen = C.center;                                         // current / next centre tables, swapped per iteration
+    double* cen_new = C.center_new;
     g.sync();
-    bool strict = false;
+    bool strict = false, recount = true;                            // recount: add every point, subtract none
     for (int it = 0; it < 300; ++it) {
-        // E step fused with the accumulation of the M step.
-        //
-        // A point whose distance to the centre of its previous cluster is (safely) less than half the
-        // distance from that centre to the nearest other centre keeps its cluster by the triangle
+        // E step.  A point whose distance to the centre of its previous cluster is (safely) less than half
+        // the distance from that centre to the nearest other centre keeps its cluster by the triangle
         // inequality — every other centre is strictly farther by a margin far above the rounding of the
         // distance evaluation — so it skips the loop over the centres.  The result is identical to
-        // evaluating every centre; only points near a cluster border (about 40 %) go to the full loop,
-        // compacted into a worklist so that the warps of that loop stay full.
+        // evaluating every centre; the other points (about 40 %) are compacted into a worklist so that the
+        // warps of the full loop stay full.  Worth its extra pass only for large problems.
         int changed = 0;
-        const bool prune = it > 0 && C.wl != nullptr && (long long)n * k >= 200000;    // small problems: the extra pass costs more than it saves
+        const bool prune = it > 0 && !recount && C.wl != nullptr && (long long)n * k >= 200000;
         uint32_t* wl = reinterpret_cast<uint32_t*>(closest);       // dead after the seeding; positions of this range
         if (prune) {
+            g.sync();                                               // slower threads may still be summing the last shift from term
             for (int q = tid; q < k; q += gsz) {
-                const double* cq = C.center + 3 * q;
+                const double* cq = cen + 3 * q;
                 double m = 1.0e300;
                 for (int r = 0; r < k; ++r) {
                     if (r == q) continue;
-                    const double d = rhccq_dist3(cq[0], cq[1], cq[2], C.center + 3 * r);
+                    const double d = rhccq_dist3(cq[0], cq[1], cq[2], cen + 3 * r);
                     m = d < m ? d : m;
                 }
                 // usable only when the centres are at least 1 apart: then the margin below (1e-6 relative)
@@ -400,60 +428,48 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
             }
             if (tid == 0) *C.wl = 0;
             g.sync();
-            for (int j = tid; j - RHCCQ_LANE < n; j += gsz) {           // warp-uniform trip count
-                const bool have = j < n;
-                const uint32_t c = x[have ? j : 0];
-                const int a = have ? (int)label[j] : 0;
-                const double u = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c), (double)rhccq_key_b(c),
-                                             C.center + 3 * a);
-                const bool keep = have && u < C.term[a];
-                if (acc_base) rhccq_acc_rows(acc_base, 4, a, c, keep);
-                else rhccq_acc_split(C.sums, C.cnt, a, c, keep);
-                if (have && !keep) wl[atomicAdd(C.wl, 1)] = (uint32_t)j;
+            for (int j = tid; j < n; j += gsz) {
+                const uint32_t c = x[j];
+                const int a = (int)label[j];
+                const double u = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c), (double)rhccq_key_b(c), cen + 3 * a);
+                if (!(u < C.term[a])) wl[atomicAdd(C.wl, 1)] = (uint32_t)j;
             }
             g.sync();
         }
         const int n_work = prune ? *C.wl : n;
-        for (int i0 = tid; i0 - RHCCQ_LANE < n_work; i0 += RHCCQ_EB * gsz) {      // warp-uniform trip count
+        for (int i0 = tid; i0 < n_work; i0 += RHCCQ_EB * gsz) {
             uint32_t cb[RHCCQ_EB];
             int bb[RHCCQ_EB], jj[RHCCQ_EB];
 #pragma unroll
             for (int u = 0; u < RHCCQ_EB; ++u) {
                 const int i = i0 + u * gsz;
-                const int is = i < n_work ? i : 0;                      // lanes past the end recompute entry 0 and drop it
+                const int is = i < n_work ? i : i0;                     // lanes past the end redo an entry and drop it
                 jj[u] = prune ? (int)wl[is] : is;
                 cb[u] = x[jj[u]];
             }
-            rhccq_nearest_centers(cb, C.center, k, bb);
+            rhccq_nearest_centers(cb, cen, k, bb);
 #pragma unroll
             for (int u = 0; u < RHCCQ_EB; ++u) {
-                const bool have = i0 + u * gsz < n_work;
-                const int j = jj[u];
-                const uint32_t c = cb[u];
-                const int bi = bb[u];
-                if (have) {
-                    if ((int)label[j] != bi) changed = 1;
-                    label[j] = (idx_t)bi;
+                if (i0 + u * gsz >= n_work) continue;
+                const int j = jj[u], bi = bb[u], old = (int)label[j];
+                if (old != bi) { changed = 1; label[j] = (idx_t)bi; }
+                if (old != bi || recount) {
+                    const uint32_t c = cb[u];
+                    const int r = rhccq_key_r(c), gg = rhccq_key_g(c), b = rhccq_key_b(c);
+                    if (!recount && old != (int)NOLABEL) {
+                        atomicAdd(&C.sums[3 * old], -r); atomicAdd(&C.sums[3 * old + 1], -gg); atomicAdd(&C.sums[3 * old + 2], -b);
+                        atomicAdd(&C.cnt[old], -1);
+                    }
+                    atomicAdd(&C.sums[3 * bi], r); atomicAdd(&C.sums[3 * bi + 1], gg); atomicAdd(&C.sums[3 * bi + 2], b);
+                    atomicAdd(&C.cnt[bi], 1);
                 }
-                if (acc_base) rhccq_acc_rows(acc_base, 4, bi, c, have);
-                else rhccq_acc_split(C.sums, C.cnt, bi, c, have);
             }
         }
+        recount = false;
         changed = g.any(changed);
         int empty = 0;
-        for (int q = tid; q < k; q += gsz) {
-            if (C.hist) {
-                int s0 = 0, s1 = 0, s2 = 0, cn = 0;
-                for (int w = 0; w < g.nsub(); ++w) {
-                    int* h = C.hist + ((size_t)w * k + q) * 4;
-                    s0 += h[0]; s1 += h[1]; s2 += h[2]; cn += h[3];
-                    h[0] = 0; h[1] = 0; h[2] = 0; h[3] = 0;
-                }
-                C.sums[3 * q] = s0; C.sums[3 * q + 1] = s1; C.sums[3 * q + 2] = s2; C.cnt[q] = cn;
-            }
-            if (C.cnt[q] == 0) ++empty;
-        }
-        const int n_empty = g.sum_i(empty);
+        for (int q = tid; q < k; q += gsz) if (C.cnt[q] == 0) ++empty;
+        const int n_empty = k <= gsz ? g.count(empty) : g.sum_i(empty);    // k <= gsz: at most one cluster per thread
         if (n_empty > 0) {
             // relocate empty clusters to the points farthest from their centre
             // (_k_means_common.pyx:177-211): farthest first, ties to the lower index.
@@ -461,7 +477,7 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
             for (int j = tid; j < n; j += gsz) {
                 const uint32_t c = x[j];
                 const double d = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c), (double)rhccq_key_b(c),
-                                             C.center + 3 * (int)label[j]);
+                                             cen + 3 * (int)label[j]);
                 if (d > mx) mx = d;
             }
             mx = g.max_d(mx);
@@ -479,7 +495,7 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                         if (lj & Cfg::FLAG) continue;               // already taken
                         const uint32_t c = x[j];
                         const double d = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c),
-                                                     (double)rhccq_key_b(c), C.center + 3 * (int)lj);
+                                                     (double)rhccq_key_b(c), cen + 3 * (int)lj);
                         if (d > bm) { bm = d; bj = j; }             // ascending j: the first maximum stays
                     }
                     const double gm = g.max_d(bm);
@@ -497,6 +513,7 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                     ++e;
                 }
                 for (int j = tid; j < n; j += gsz) label[j] = (idx_t)(label[j] & ~Cfg::FLAG);
+                recount = true;                                     // the sums no longer follow the labels
                 g.sync();
             }
         }
@@ -512,18 +529,20 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                 c1 = __ddiv_rn((double)S1[1], (double)n);
                 c2 = __ddiv_rn((double)S1[2], (double)n);
             }
-            C.center_new[3 * q] = c0; C.center_new[3 * q + 1] = c1; C.center_new[3 * q + 2] = c2;
-            const double a0 = __dsub_rn(c0, C.center[3 * q]), a1 = __dsub_rn(c1, C.center[3 * q + 1]),
-                         a2 = __dsub_rn(c2, C.center[3 * q + 2]);
+            cen_new[3 * q] = c0; cen_new[3 * q + 1] = c1; cen_new[3 * q + 2] = c2;
+            const double a0 = __dsub_rn(c0, cen[3 * q]), a1 = __dsub_rn(c1, cen[3 * q + 1]), a2 = __dsub_rn(c2, cen[3 * q + 2]);
             C.term[q] = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
-            if (!C.hist) { C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0; }
+            if (recount) { C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0; }
         }
         g.sync();
         double shift = 0.0;
-        if (tid == 0) for (int q = 0; q < k; ++q) shift = __dadd_rn(shift, C.term[q]);     // fixed order
-        shift = g.bcast_d(shift);
-        for (int q = tid; q < 3 * k; q += gsz) C.center[q] = C.center_new[q];
-        g.sync();
+        if (k <= 64) {
+            for (int q = 0; q < k; ++q) shift = __dadd_rn(shift, C.term[q]);             // fixed order, every thread
+        } else {
+            if (tid == 0) for (int q = 0; q < k; ++q) shift = __dadd_rn(shift, C.term[q]);
+            shift = g.bcast_d(shift);
+        }
+        { double* t = cen; cen = cen_new; cen_new = t; }
         if (!changed) { strict = true; break; }
         if (shift <= tol) break;
     }
@@ -533,7 +552,7 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
             int bb[RHCCQ_EB];
 #pragma unroll
             for (int u = 0; u < RHCCQ_EB; ++u) { const int j = j0 + u * gsz; cb[u] = x[j < n ? j : j0]; }
-            rhccq_nearest_centers(cb, C.center, k, bb);
+            rhccq_nearest_centers(cb, cen, k, bb);
 #pragma unroll
             for (int u = 0; u < RHCCQ_EB; ++u) { const int j = j0 + u * gsz; if (j < n) label[j] = (idx_t)bb[u]; }
         }
@@ -542,6 +561,7 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
     g.sync();
     for (int j = tid; j < n; j += gsz) atomicAdd(&C.cnt[(int)label[j]], 1);
     g.sync();
+    if (g.size() > RHCCQ_WARP_SIZE) RHCCQ_PROF(2);
 }
 
 // Ascending sort of a[0..n) for any n: the bitonic network in its "flip" form, in which every
@@ -718,6 +738,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     __shared__ int s_scan[RHCCQ_MAX_WARPS + 2];
     __shared__ int s_tail, s_err, s_base, s_claim, s_wl;
     __shared__ int wlc[RHCCQ_MAX_WARPS];
+    RHCCQ_PROF_T0();
     const int n = B.pal_cnt[p];
     const uint32_t* keys = B.pal_keys + B.pal_off[p];
     const int* lab = labels + B.pal_off[p];
@@ -837,6 +858,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     RHCCQ_PAR_FOR(j, n_members) W.A.x[j] = keys[(int)(W.perm[j] & (idx_t)~Cfg::FLAG)];
     __syncthreads();
 
+    RHCCQ_PROF(0);                                                 // prologue
     // ---- level-synchronous splitting
     rhccq_grp_cta gc; gc.sll = s_ll;
     rhccq_grp_warp gw;
@@ -874,6 +896,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
             }
         }
         __syncthreads();
+        RHCCQ_PROF(3);                                             // CTA-level splits (K-Means + partition)
         if (s_err) break;
         // ranges for single warps, concurrently; warps claim the next range when they are done with one
         if (threadIdx.x == 0) s_claim = head;
@@ -901,6 +924,8 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
             rhccq_split_range<rhccq_grp_warp, Cfg>(gw, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
         }
         head = tail;
+        __syncthreads();
+        RHCCQ_PROF(4);                                             // warp-level splits of this level
     }
     __syncthreads();
     if (s_err) {
@@ -927,6 +952,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     }
     __syncthreads();
     if (threadIdx.x == 0) n_leaves[p] = s_base + n_split_leaves;
+    RHCCQ_PROF(5);                                                 // leaf numbering
 }
 
 template <class Cfg, bool ROWS_SMEM, int THREADS>
@@ -1009,3 +1035,11 @@ int rhccq_launch_palette_split(const rhccq_palette_batch& B, const int* labels, 
     return rhccq_launch_split_cfg<rhccq_cfg_large>(B, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves,
                                                    max_rows, ws, stream);
 }
+
+#if defined(RHCCQ_SPLIT_PROFILE) && !defined(RHCCQ_HOST_EMU)
+// tools/split_phases.py: copy out (reset != 0: clear) the phase counters
+extern "C" int rhccq_split_prof_read(unsigned long long* host_out, int reset) {
+    if (reset) { unsigned long long z[8] = {0}; return (int)cudaMemcpyToSymbol(rhccq_split_prof, z, sizeof z); }
+    return (int)cudaMemcpyFromSymbol(host_out, rhccq_split_prof, 8 * sizeof(unsigned long long));
+}
+#endif
