@@ -45,7 +45,8 @@ def subregion_quantization(image_rgb, subregions, quality=10, subregion_type=Non
     a_off, a_cnt, a_present = (A[k].cpu().numpy() for k in ("off", "cnt", "present"))
     a_color = A["color"].cpu().numpy()
     a_map = A["map"].cpu().numpy()
-    plane = st["plane"][0, 0].cpu().numpy().view(np.uint16).astype(np.int64)
+    plane = st["plane"][0, 0].cpu().numpy()
+    plane = (plane.view(np.uint16) if st["idx_bytes"] == 2 else plane.view(np.uint32)).astype(np.int64)
     label = lab[0, 0]
     nl1, ent_off = st["nl1"], st["ent_off_h"]
     pal_cnt_h = st["pal_cnt"].cpu().numpy()

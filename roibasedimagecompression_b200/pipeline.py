@@ -179,10 +179,11 @@ def stage1(be: Backend, images, labels, table: SegmentTable) -> dict:
     if pal_off_h[-1] >= 2 ** 31:
         raise RhccqError("batch too large for int32 palette offsets; split the batch")
     max_valid = int(table.n_valid.max())
+    idxb = 2 if max_valid + 1 <= 65535 else 4                      # a segment's palette has at most n_valid + 1 rows
     crops = table.dev(be, "crops", lambda: _dev(be, crops_h))
     pal_off = table.dev(be, "pal_off", lambda: _dev(be, pal_off_h[:-1]))
     pal_keys, pal_cnt, plane = ops.unique_index(be, images, labels, crops, pal_off, int(pal_off_h[-1]),
-                                                idx_bytes=2, repaint_black=True, max_valid=max_valid,
+                                                idx_bytes=idxb, repaint_black=True, max_valid=max_valid,
                                                 n_classes=K)
     s1 = ops.cluster_palettes(be, pal_keys, pal_off, pal_cnt, None, max_rows=max_valid + 1,
                               params=table.dev(be, "q1", lambda: ops.quality_params(be, q1[cls_h], max_valid + 1)))
@@ -193,7 +194,7 @@ def stage1(be: Backend, images, labels, table: SegmentTable) -> dict:
     E = int(ent_off_h[-1])
     ent_off0 = _dev(be, ent_off_h)
     ent_color0, ent_fpos0 = ops.remap_first(be, labels, plane, crops, pal_off, s1["leaf"], s1["n_leaves"],
-                                            s1["new_keys"], ent_off0, E, idx_bytes=2,
+                                            s1["new_keys"], ent_off0, E, idx_bytes=idxb,
                                             max_leaves=int(nl1_h.max()))
     # merge level A: segments -> region (subregions.py:639-650)
     reg_first = np.searchsorted(table.seg_region, np.arange(R + 1)).astype(np.int32)   # segments of region r
@@ -204,7 +205,7 @@ def stage1(be: Backend, images, labels, table: SegmentTable) -> dict:
                         max_comps=int(max(np.diff(reg_first).max(), 1)))
     return {"pal_keys": pal_keys, "pal_off": pal_off, "pal_cnt": pal_cnt, "plane": plane, "s1": s1, "nl1": nl1_h,
             "ent_off_h": ent_off_h, "ent_off0": ent_off0, "ent_color0": ent_color0, "ent_fpos0": ent_fpos0,
-            "A": A, "crops": crops, "reg_first": reg_first, "ent_per_region": ent_per_region, "E": E}
+            "A": A, "crops": crops, "reg_first": reg_first, "ent_per_region": ent_per_region, "E": E, "idx_bytes": idxb}
 
 
 def encode_batch(be: Backend, images, labels, table: SegmentTable, *, keep_stages: bool = False) -> EncodeResult:
@@ -250,7 +251,7 @@ def encode_batch(be: Backend, images, labels, table: SegmentTable, *, keep_stage
                                   s2["new_keys"], Cm, s3["leaf"], E)
     out = be.zeros((B, H, W), torch.int16)
     for k in range(K - 1, -1, -1):
-        ops.paint(be, labels, crops, ent_off0, ent_final, plane, out, cls=k, idx_bytes=2)
+        ops.paint(be, labels, crops, ent_off0, ent_final, plane, out, cls=k, idx_bytes=st["idx_bytes"])
     res = EncodeResult(indices=out, palette_keys=s3["new_keys"], palette_off=Cm["off"], palette_cnt=s3["n_leaves"])
     if keep_stages:
         res.stage = dict(st, B=Bm, s2=s2, fpos2=fpos2, C=Cm, s3=s3, ent_final=ent_final, grp_first=grp_first)

@@ -332,3 +332,17 @@ def test_minibatch_branch_equals_restated_oracle(backend, n, q, black):
     got = C.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m, as_arrays=True)
     assert np.array_equal(got["palette"], want["palette"])
     assert np.array_equal(got["indices"], want["indices"])
+
+
+def test_pipeline_with_large_segments_minibatch_in_stage1(backend):
+    """Segments of more than 10 000 colours (natural 128 px tiles hit this): stage 1 itself takes the
+    MiniBatchKMeans branch, and the index plane needs no more than 16 bits."""
+    H, W, tile = 128, 256, 128
+    img = synth(H, W, 99, sigma=6.0)
+    roi, non = tile_regions(H, W, tile)
+    n_colours = len(np.unique(img[:, :128].reshape(-1, 3), axis=0))
+    assert n_colours >= 10000
+    want = O.encode_image(img, roi, non)
+    pal, idx = _encode_device(backend, img, roi, non)
+    assert np.array_equal(pal, want["palette"])
+    assert np.array_equal(idx, want["indices"])
