@@ -46,6 +46,12 @@ WORKLOADS = {
     # BASELINE.json configs[3]: one 7680x4320 image, strips of rows + halo per GPU, NCCL all-gather of boundary edges
     "c4": (1, 4320, 7680, 0, "DBSCAN of the 33.2 M pixel features of one 7680x4320 synthetic image, strip-sharded"),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of the same command
+# (summaries under profiles/): (workload, entry point) -> (bytes, source)
+NCU_TRAFFIC = {
+    ("c2", "rhccq_palette_split"): (835103744 + 381782528, "profiles/r01_split_c2_v4.txt (the stage-1 launch)"),
+    ("c5l", "rhccq_dbscan_lattice_count"): (337112576 + 127552000, "profiles/r01_lattice_v1.txt"),
+}
 DBSCAN_BYTES_PER_POINT = 24       # 20 B read + 4 B written, both for the count kernel and the whole
 
 
@@ -246,7 +252,8 @@ def run_dbscan(args, be, rank, world, local, H, W, desc):
            "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": "points/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": n * 20 * world, "d2h_bytes_per_step": n * 4 * world},
            "roofline": {"kernel": count_name + (" (rhccq_k_lt_sweep<0,0>)" if lattice else " (rhccq_k_pt_sweep<0>)"), "bound": "hbm", "achieved": ach, "peak": peak,
-                        "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                        "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC.get((args.workload, count_name), (None, None))[0],
+                        "traffic_source": NCU_TRAFFIC.get((args.workload, count_name), (None, None))[1], "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": DBSCAN_BYTES_PER_POINT * n, "avg_launch_ms": cnt_ms / cnt_n,
                         "share_of_step": (cnt_ms / args.steps) / ms},
            "kernels": {k: {"ms_per_step": t / args.steps, "share": (t / args.steps) / ms} for k, (c, t) in kt.items()}}
@@ -267,6 +274,40 @@ def run_dbscan(args, be, rank, world, local, H, W, desc):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def dbscan_probe(be, args):
+    """8.4 M pixel-feature points (2048 x 4096 image, 168 MB of float32 points: larger than L2) through the
+    lattice kernels; per-phase CUDA-event times and the count kernel's roofline (24 B/point)."""
+    import torch
+    from roibasedimagecompression_b200 import dbscan as D
+    from roibasedimagecompression_b200.synth import synth, pixel_features
+    H, W = 2048, 4096
+    img = np.concatenate([synth(2048, 2048, 4321), synth(2048, 2048, 4322)], axis=1)
+    pts = torch.from_numpy(pixel_features(img)).cuda()
+    plan = D.LatticeDbscan(be, H, W, args.eps, args.min_pts)
+    for _ in range(3):
+        plan.run(pts)
+    torch.cuda.synchronize()
+    be.kernel_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        labels, core = plan.run(pts)
+    e1.record(); torch.cuda.synchronize()
+    kt = be.kernel_times_ms(); be.kernel_timing(False)
+    ms = e0.elapsed_time(e1) / 5
+    n = H * W
+    cn, cms = kt["rhccq_dbscan_lattice_count"]
+    peak, src = _peaks()
+    ach = DBSCAN_BYTES_PER_POINT * n / 1e9 / ((cms / cn) / 1e3)
+    return {"workload": f"DBSCAN(eps={args.eps}, min_samples={args.min_pts}) of the {n} pixel features of a {W}x{H} synthetic image "
+                        "(float32 [n,5], lattice kernels); see --workload c5l / c5 / c4 for the full runs",
+            "points_per_s": n / (ms / 1e3), "ms": ms, "clusters": int(labels.max().item()) + 1,
+            "phases_ms": {k: t / c for k, (c, t) in kt.items()},
+            "roofline": {"kernel": "rhccq_dbscan_lattice_count (rhccq_k_lt_sweep<0,0>)", "bound": "hbm", "achieved": ach,
+                         "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": src,
+                         "algorithmic_bytes_per_launch": DBSCAN_BYTES_PER_POINT * n, "avg_launch_ms": cms / cn}}
 
 
 # --------------------------------------------------------------------------- strip-sharded DBSCAN (C4)
@@ -331,6 +372,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--no-dbscan", action="store_true", help="skip the short DBSCAN probe of the default line")
     ap.add_argument("--eps", type=float, default=3.0, help="c5 workloads: DBSCAN radius")
     ap.add_argument("--min-pts", type=int, default=8, help="c5 workloads: DBSCAN min_samples")
     args = ap.parse_args()
@@ -412,8 +454,12 @@ def main():
     peak, peak_src = _peaks()
     # every launch of the per-segment / per-pixel kernels covers all pixels of the rank's batch
     achieved = ALGO_BYTES_PER_PIXEL * px_rank / 1e9 / ((top_ms / top_n) / 1e3)
-    roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    roofline = {"kernel": top, "bound": "hbm", "note": "the dominant kernel of the encode is FP64-issue/latency bound (recursive "
+                "K-Means on palettes in shared memory, DESIGN.md section 4); its HBM fraction is small by construction. "
+                "The HBM-shaped kernel of the path is the neighbour count: see the dbscan object of this line.",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, top), (None, None))[0],
+                "traffic_source": NCU_TRAFFIC.get((args.workload, top), (None, None))[1], "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL * px_rank,
                 "avg_launch_ms": top_ms / top_n, "share_of_step": (top_ms / args.steps) / ms_step,
                 "step_gbs": ALGO_BYTES_PER_PIXEL * px_rank / 1e9 / (ms_step / 1e3)}
@@ -444,6 +490,10 @@ def main():
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "kernels": kernels,
         "last_step_launches_ms": last_step,
     }
+
+    # ---- the DBSCAN operator itself on pixel features (BASELINE configs 3-5), short run: neighbour-count roofline
+    if rank == 0 and world == 1 and not args.no_dbscan:
+        out["dbscan"] = dbscan_probe(be, args)
 
     # ---- CPU baseline + parity of one frame (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu:

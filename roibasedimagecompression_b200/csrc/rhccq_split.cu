@@ -769,7 +769,6 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     // small shared tables: per-warp centre sets, per-warp M-step histograms, candidate slots
     rhccq_carver sv(small_base);
     const size_t nw = (size_t)RHCCQ_NWARPS;                        // the tables are sized for the launch's warps
-    int* hist = sv.take<int>(nw * 4 * RHCCQ_KPRIV);
     int* cand = sv.take<int>((nw + 1) * RHCCQ_KM_MAXT);
     double* wcent = sv.take<double>(nw * 7 * RHCCQ_KW);
     int* wint = sv.take<int>(nw * 5 * RHCCQ_KW);
@@ -883,7 +882,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
             }
             if (in_smem) {
                 rhccq_km_centers C = CS;
-                C.hist = k <= RHCCQ_KPRIV ? hist : nullptr;
+                C.hist = nullptr;
                 C.poff = poff;
                 C.wl = &s_wl;
                 rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
@@ -981,7 +980,7 @@ static size_t rhccq_split_small_bytes(int threads) {
 #else
     const size_t nw = (size_t)threads / 32;
 #endif
-    return rhccq_carve_bytes(nw * 4 * RHCCQ_KPRIV, 4) + rhccq_carve_bytes((nw + 1) * RHCCQ_KM_MAXT, 4)
+    return rhccq_carve_bytes((nw + 1) * RHCCQ_KM_MAXT, 4)
            + rhccq_carve_bytes(nw * 7 * RHCCQ_KW, 8) + rhccq_carve_bytes(nw * 5 * RHCCQ_KW, 4)
            + rhccq_carve_bytes(nw * RHCCQ_KC, 4);
 }
@@ -999,7 +998,8 @@ static int rhccq_launch_split_cfg(const rhccq_palette_batch& B, const int* label
     const size_t cent_s = rhccq_split_center_bytes(kc_s);
     const size_t slice = rhccq_palette_split_ws_bytes(max_rows);
     const size_t slices = ws.ws ? ws.ws_bytes / slice : 0;
-    const int rows_in_smem = small + row_bytes + cent_s <= RHCCQ_SMEM_BUDGET;
+    // everything the kernel needs next to its ~3.3 KB of static shared memory, within the 227 KB of an SM
+    const int rows_in_smem = small + row_bytes + cent_s + 4096 <= 227 * 1024;
     if (!rows_in_smem && slices == 0) {
         rhccq_set_error("rhccq_palette_split: the per-row working set (%zu bytes) exceeds shared memory and the "
                         "workspace (%zu bytes) holds no slice of %zu bytes", row_bytes, ws.ws_bytes, slice);
