@@ -323,16 +323,14 @@ def run_strips(args, be, rank, world, local, H, W, desc):
     for tr in range(l0 // th, (l1 - 1) // th + 1):
         band = np.concatenate([synth(th, tw, 1234 + tr * (W // tw) + tc) for tc in range(W // tw)], axis=1)
         rows.append(band[max(l0 - tr * th, 0):min(l1 - tr * th, th)])
-    img = np.concatenate(rows, axis=0)
-    yy, xx = np.mgrid[l0:l1, 0:W]
-    pts_np = np.concatenate([xx[..., None], yy[..., None], img], axis=2).reshape(-1, 5).astype(np.float32)
-    h_pts = torch.from_numpy(pts_np).pin_memory()
-    d_pts = h_pts.cuda()
-    own = ((r0 - l0) * W, (r1 - l0) * W)
-    zone_idx = [((a - l0) * W, (b - l0) * W) for a, b in zone]
+    img = np.ascontiguousarray(np.concatenate(rows, axis=0))
+    d_rows = torch.from_numpy(img).pin_memory().cuda()             # uint8 rows [l0, l1) of the image
+    eng = D.LatticeDbscan(be, l1 - l0, W, eps, min_pts)
+    st = D.StripDbscan(be, eng, (l1 - l0) * W, l0 * W, ((r0 - l0) * W, (r1 - l0) * W),
+                       [((a - l0) * W, (b - l0) * W) for a, b in zone])
     info = {}
     for _ in range(args.warmup):
-        labels, core = D.dbscan_strips(be, d_pts, l0 * W, own, zone_idx, eps, min_pts, timings=info)
+        labels, core = st.run(d_rows, info)
     torch.cuda.synchronize()
     sampler = ClockSampler(local); sampler.start()
     if world > 1: dist.barrier()
@@ -341,7 +339,7 @@ def run_strips(args, be, rank, world, local, H, W, desc):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        labels, core = D.dbscan_strips(be, d_pts, l0 * W, own, zone_idx, eps, min_pts, timings=info)
+        labels, core = st.run(d_rows, info)
     e1.record(); torch.cuda.synchronize()
     if world > 1: dist.barrier()
     clocks = sampler.stop()
@@ -353,7 +351,7 @@ def run_strips(args, be, rank, world, local, H, W, desc):
            "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "c4: " + desc, "eps": eps, "min_pts": min_pts, "rows_per_rank": r1 - r0,
-                      "halo_rows": r0 - l0, "boundary_edges_total": info.get("edges_total"),
+                      "halo_rows": r0 - l0, "engine": "lattice kernels on uint8 rows", "boundary_edges_total": info.get("edges_total"),
                       "clusters": info.get("roots_total"), "l2": "points larger than L2"},
            "clocks": clocks, "gpu_launches": be.launches - l0_launch,
            "e2e": None, "roofline": None}

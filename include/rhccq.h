@@ -238,6 +238,12 @@ int rhccq_dbscan_lattice_union(int H, int W, double eps, int min_pts, void* ws, 
 int rhccq_dbscan_lattice_border(int H, int W, double eps, int min_pts, const uint8_t* core, void* ws, size_t ws_bytes,
                                 void* stream);
 int rhccq_dbscan_lattice_relabel(int H, int W, void* ws, size_t ws_bytes, int32_t* labels, void* stream);
+/* border = flatten (roots of core pixels into the root array) + attach (non-core pixels take the lowest adjacent root) */
+int rhccq_dbscan_lattice_flatten(int H, int W, const uint8_t* core, void* ws, size_t ws_bytes, void* stream);
+int rhccq_dbscan_lattice_attach(int H, int W, double eps, int min_pts, void* ws, size_t ws_bytes, void* stream);
+/* byte offset inside the workspace of: 0 the root array, 1 root flags, 2 union-find parents, 3 packed colours (all
+ * 4 bytes x H*W), 4 scan scratch */
+size_t rhccq_dbscan_lattice_ws_offset(int H, int W, int which);
 
 /* ------------------------------------------------------------------ strips of one point set across GPUs
  * (SURVEY.md 8e).  Every rank runs plan..flatten on its strip plus a halo of 2 eps; local indices are
@@ -256,6 +262,10 @@ int rhccq_uf_lookup_roots(int32_t* rootlab, int n, int g0, const int32_t* table_
                           int table_cap, void* stream);
 int rhccq_dbscan_own_roots(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, int own_lo, int own_hi, int g0,
                            int32_t* out_ids, int32_t* out_count, void* stream);
+/* own_roots on a bare root array (global roots after rhccq_uf_lookup_roots); scratch: int32 [own_roots_scratch_ints(n)] */
+size_t rhccq_uf_own_roots_scratch_ints(int n);
+int rhccq_uf_own_roots(const int32_t* rootlab, int n, int own_lo, int own_hi, int g0, int32_t* scratch, int32_t* out_ids,
+                       int32_t* out_count, void* stream);
 int rhccq_uf_rank_labels(const int32_t* sorted_roots, int n_roots, const int32_t* rootlab, int lo, int hi, int32_t* labels,
                          void* stream);
 /* labels int32 [n], original order */

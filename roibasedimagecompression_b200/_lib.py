@@ -66,6 +66,11 @@ SIGNATURES = {
     "rhccq_dbscan_lattice_union": (_I, [_I, _I, _D, _I, _P, _Z, _P]),
     "rhccq_dbscan_lattice_border": (_I, [_I, _I, _D, _I, _P, _P, _Z, _P]),
     "rhccq_dbscan_lattice_relabel": (_I, [_I, _I, _P, _Z, _P, _P]),
+    "rhccq_dbscan_lattice_flatten": (_I, [_I, _I, _P, _P, _Z, _P]),
+    "rhccq_dbscan_lattice_attach": (_I, [_I, _I, _D, _I, _P, _Z, _P]),
+    "rhccq_dbscan_lattice_ws_offset": (_Z, [_I, _I, _I]),
+    "rhccq_uf_own_roots_scratch_ints": (_Z, [_I]),
+    "rhccq_uf_own_roots": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "rhccq_uf_emit_edges": (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
     "rhccq_uf_merge_edges": (_I, [_P, _I, _P, _P, _I, _P]),
     "rhccq_uf_lookup_roots": (_I, [_P, _I, _I, _P, _P, _I, _P]),

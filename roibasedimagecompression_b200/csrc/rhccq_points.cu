@@ -697,6 +697,24 @@ int rhccq_uf_lookup_roots(int32_t* rootlab, int n, int g0, const int32_t* table_
     return 0;
 }
 
+size_t rhccq_uf_own_roots_scratch_ints(int n) { return (size_t)(n > 0 ? n : 1) + rhccq_scan_scratch_ints(n) + 16; }
+
+int rhccq_uf_own_roots(const int32_t* rootlab, int n, int own_lo, int own_hi, int g0, int32_t* scratch, int32_t* out_ids,
+                       int32_t* out_count, void* stream) {
+    if (!rootlab || !scratch || !out_ids || !out_count || n <= 0 || own_lo < 0 || own_hi > n || own_hi < own_lo) {
+        rhccq_set_error("rhccq_uf_own_roots: bad arguments"); return -1;
+    }
+    int* flags = scratch;
+    int* scan = scratch + n;
+    RHCCQ_LAUNCH(rhccq_k_uf_root_flags, rhccq_pt_blocks(n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, rootlab, n, own_lo, own_hi, g0, flags);
+    if (n <= RHCCQ_SCAN_TILE) {
+        RHCCQ_LAUNCH(rhccq_k_scan_small, 1, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, flags, n, (int*)nullptr);
+    } else if (rhccq_scan_i32(flags, n, flags, scan, stream) != 0) return -1;
+    RHCCQ_LAUNCH(rhccq_k_uf_root_scatter, rhccq_pt_blocks(own_hi - own_lo), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, rootlab,
+                 flags, own_lo, own_hi, g0, out_ids, out_count, n);
+    return 0;
+}
+
 int rhccq_dbscan_own_roots(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes, int own_lo, int own_hi, int g0,
                            int32_t* out_ids, int32_t* out_count, void* stream) {
     RHCCQ_PT_ARGS("rhccq_dbscan_own_roots")
@@ -992,9 +1010,29 @@ int rhccq_dbscan_lattice_union(int H, int W, double eps, int min_pts, void* ws, 
     return 0;
 }
 
-int rhccq_dbscan_lattice_border(int H, int W, double eps, int min_pts, const uint8_t* core, void* ws, size_t ws_bytes, void* stream) {
-    RHCCQ_LT_PROLOGUE("rhccq_dbscan_lattice_border")
+int rhccq_dbscan_lattice_attach(int H, int W, double eps, int min_pts, void* ws, size_t ws_bytes, void* stream);
+
+int rhccq_dbscan_lattice_flatten(int H, int W, const uint8_t* core, void* ws, size_t ws_bytes, void* stream) {
+    if (!ws || ws_bytes < rhccq_dbscan_lattice_workspace_bytes(H, W) || !core) { rhccq_set_error("rhccq_dbscan_lattice_flatten: bad arguments"); return -1; }
+    rhccq_lt_ws L; rhccq_lt_carve(H, W, ws, &L);
     RHCCQ_LAUNCH(rhccq_k_pt_flatten, rhccq_pt_blocks((long long)H * W), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, H * W, L.parent, core, L.rootlab, L.is_root);
+    return 0;
+}
+
+size_t rhccq_dbscan_lattice_ws_offset(int H, int W, int which) {
+    rhccq_lt_ws L; rhccq_lt_carve(H, W, (void*)256, &L);
+    const unsigned char* p = which == 0 ? (unsigned char*)L.rootlab : which == 1 ? (unsigned char*)L.is_root
+                           : which == 2 ? (unsigned char*)L.parent : which == 3 ? (unsigned char*)L.packed : (unsigned char*)L.scan;
+    return (size_t)(p - (unsigned char*)256);
+}
+
+int rhccq_dbscan_lattice_border(int H, int W, double eps, int min_pts, const uint8_t* core, void* ws, size_t ws_bytes, void* stream) {
+    if (rhccq_dbscan_lattice_flatten(H, W, core, ws, ws_bytes, stream) != 0) return -1;
+    return rhccq_dbscan_lattice_attach(H, W, eps, min_pts, ws, ws_bytes, stream);
+}
+
+int rhccq_dbscan_lattice_attach(int H, int W, double eps, int min_pts, void* ws, size_t ws_bytes, void* stream) {
+    RHCCQ_LT_PROLOGUE("rhccq_dbscan_lattice_attach")
     if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<2, 2, RHCCQ_LT_H>, smem) != 0) return -1;
     RHCCQ_LAUNCH((rhccq_k_lt_sweep<2, 2, RHCCQ_LT_H>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, (const void*)L.packed, A, (int*)nullptr, L.packed,
                  (uint8_t*)nullptr, L.parent, L.rootlab, (int*)nullptr);

@@ -162,6 +162,89 @@ def strip_rows(H: int, world: int, rank: int, eps: float, w_xy: float = 1.0):
     return r0, r1, l0, l1, zone
 
 
+class StripDbscan:
+    """One rank's share of a DBSCAN over a point set split into strips: the local engine
+    (`PointDbscan` for generic points, `LatticeDbscan` for image rows) plus the buffers of the exchange.
+    Reusable across calls on same-shaped inputs."""
+
+    def __init__(self, be: Backend, engine, n_loc: int, g0: int, own, zone, group=None):
+        self.be, self.engine, self.n_loc, self.g0 = be, engine, int(n_loc), int(g0)
+        self.own, self.zone, self.group = (int(own[0]), int(own[1])), [(int(a), int(b)) for a, b in zone], group
+        self.lattice = isinstance(engine, LatticeDbscan)
+        if self.lattice:
+            off = int(be.cdll.rhccq_dbscan_lattice_ws_offset(engine.H, engine.W, 0))
+        else:
+            off = int(be.cdll.rhccq_dbscan_ws_offset(engine._p(), 0))
+        self.rootlab = engine.ws[off:off + 4 * self.n_loc].view(torch.int32)
+        self.cap = max(sum(b - a for a, b in self.zone), 1)
+        self.edges = be.empty((self.cap, 2), torch.int32)
+        self.counter = be.zeros((1,), torch.int32)
+        n_own = self.own[1] - self.own[0]
+        self.ids = be.empty((max(n_own, 1),), torch.int32)
+        self.cnt = be.zeros((1,), torch.int32)
+        self.scratch = be.empty((int(be.cdll.rhccq_uf_own_roots_scratch_ints(self.n_loc)),), torch.int32)
+        self.labels = be.empty((max(n_own, 1),), torch.int32)
+
+    def _gather(self, mine, n_mine: int, width):
+        """all_gather of variable-length int32 rows: sizes first, then buffers padded to the largest."""
+        import torch.distributed as dist
+        be = self.be
+        world = dist.get_world_size(self.group)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=be.device) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([n_mine], dtype=torch.int64, device=be.device), group=self.group)
+        sizes = [int(s.item()) for s in sizes]
+        m = max(max(sizes), 1)
+        shape = (m,) + tuple(width)
+        pad = be.zeros(shape, torch.int32)
+        pad[:n_mine] = mine[:n_mine]
+        bufs = [be.empty(shape, torch.int32) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=self.group)
+        return torch.cat([b[:s] for b, s in zip(bufs, sizes)]).contiguous()
+
+    def run(self, src, timings: dict | None = None):
+        import torch.distributed as dist
+        be, eng = self.be, self.engine
+        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        # ---- local phases up to the roots of the local components
+        if self.lattice:
+            eng.count(src); eng.union()
+            be.call("rhccq_dbscan_lattice_flatten", eng.H, eng.W, be.ptr(eng.core), be.ptr(eng.ws), eng.ws_bytes, be.stream())
+        else:
+            eng.bin(src); eng.count(); eng.union()
+            be.call("rhccq_dbscan_flatten", eng._p(), be.ptr(eng.ws), eng.ws_bytes, be.ptr(eng.core), be.stream())
+        # ---- boundary edges of this rank, then the one exchange step
+        self.counter.zero_()
+        for a, b in self.zone:
+            be.call("rhccq_uf_emit_edges", be.ptr(self.rootlab), a, b, self.g0, be.ptr(self.edges), be.ptr(self.counter),
+                    self.cap, be.stream())
+        n_e = int(self.counter.item())                              # <= cap by construction (one edge per zone point)
+        all_edges = self._gather(self.edges, n_e, (2,)) if world > 1 else self.edges[:n_e].contiguous()
+        E = int(all_edges.shape[0])
+        if E > 0:
+            tcap = 1 << max(4, int(np.ceil(np.log2(4 * E))))
+            tk, tp = be.empty((tcap,), torch.int32), be.empty((tcap,), torch.int32)
+            be.call("rhccq_uf_merge_edges", be.ptr(all_edges), E, be.ptr(tk), be.ptr(tp), tcap, be.stream(), launches=3)
+            be.call("rhccq_uf_lookup_roots", be.ptr(self.rootlab), self.n_loc, self.g0, be.ptr(tk), be.ptr(tp), tcap, be.stream())
+        else:
+            be.call("rhccq_uf_lookup_roots", be.ptr(self.rootlab), self.n_loc, self.g0, 0, 0, 0, be.stream())
+        # ---- border points against global roots, then the global numbering of roots
+        if self.lattice:
+            be.call("rhccq_dbscan_lattice_attach", eng.H, eng.W, eng.eps, eng.min_pts, be.ptr(eng.ws), eng.ws_bytes, be.stream())
+        else:
+            be.call("rhccq_dbscan_attach", eng._p(), be.ptr(eng.ws), eng.ws_bytes, be.ptr(eng.core), be.stream())
+        self.cnt.zero_()
+        be.call("rhccq_uf_own_roots", be.ptr(self.rootlab), self.n_loc, self.own[0], self.own[1], self.g0, be.ptr(self.scratch),
+                be.ptr(self.ids), be.ptr(self.cnt), be.stream(), launches=3)
+        n_r = int(self.cnt.item())
+        roots = self._gather(self.ids, n_r, ()) if world > 1 else self.ids[:n_r].contiguous()   # ascending: strips are ordered
+        be.call("rhccq_uf_rank_labels", be.ptr(roots), int(roots.numel()), be.ptr(self.rootlab), self.own[0], self.own[1],
+                be.ptr(self.labels), be.stream())
+        if timings is not None:
+            timings.update(edges_local=n_e, edges_total=E, roots_total=int(roots.numel()))
+        n_own = self.own[1] - self.own[0]
+        return self.labels[:n_own], eng.core[self.own[0]:self.own[1]]
+
+
 def dbscan_strips(be: Backend, pts_local, g0: int, own, zone, eps: float, min_pts: int, group=None, grid_dims: int = 2,
                   timings: dict | None = None):
     """DBSCAN of one point set split into strips, one per rank of `group` (torch.distributed).
@@ -173,71 +256,21 @@ def dbscan_strips(be: Backend, pts_local, g0: int, own, zone, eps: float, min_pt
                 2 eps of an internal boundary)
     Returns labels int32 [own points] identical to the labels an unsplit run gives those points.
     """
-    import torch.distributed as dist
-    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     n_loc, dims = pts_local.shape
     lo, hi = point_bounds(be, pts_local, grid_dims)
-    plan = PointDbscan(be, n_loc, dims, eps, min_pts, lo, hi, grid_dims)
-    p, ws, wsb = plan._p(), plan.ws, plan.ws_bytes
-    plan.bin(pts_local); plan.count(); plan.union()
-    be.call("rhccq_dbscan_flatten", p, be.ptr(ws), wsb, be.ptr(plan.core), be.stream())
-    off = int(be.cdll.rhccq_dbscan_ws_offset(p, 0))
-    rootlab = ws[off:off + 4 * n_loc].view(torch.int32)
-    # ---- boundary edges of this rank
-    cap = max(sum(b - a for a, b in zone), 1)
-    edges = be.empty((cap, 2), torch.int32)
-    counter = be.zeros((1,), torch.int32)
-    for a, b in zone:
-        be.call("rhccq_uf_emit_edges", be.ptr(rootlab), int(a), int(b), int(g0), be.ptr(edges), be.ptr(counter), cap,
-                be.stream())
-    n_e = int(counter.item())                                       # <= cap by construction (one edge per zone point)
-    # ---- the one exchange step: all ranks gather all edges
-    if world > 1:
-        sizes = [torch.zeros(1, dtype=torch.int64, device=be.device) for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([n_e], dtype=torch.int64, device=be.device), group=group)
-        sizes = [int(s.item()) for s in sizes]
-        m = max(max(sizes), 1)
-        mine = be.zeros((m, 2), torch.int32)
-        mine[:n_e] = edges[:n_e]
-        bufs = [be.empty((m, 2), torch.int32) for _ in range(world)]
-        dist.all_gather(bufs, mine, group=group)
-        all_edges = torch.cat([b[:s] for b, s in zip(bufs, sizes)]).contiguous()
-    else:
-        all_edges = edges[:n_e].contiguous()
-    E = int(all_edges.shape[0])
-    if E > 0:
-        tcap = 1 << max(4, int(np.ceil(np.log2(4 * E))))
-        tk, tp = be.empty((tcap,), torch.int32), be.empty((tcap,), torch.int32)
-        be.call("rhccq_uf_merge_edges", be.ptr(all_edges), E, be.ptr(tk), be.ptr(tp), tcap, be.stream(), launches=3)
-        be.call("rhccq_uf_lookup_roots", be.ptr(rootlab), n_loc, int(g0), be.ptr(tk), be.ptr(tp), tcap, be.stream())
-    else:
-        be.call("rhccq_uf_lookup_roots", be.ptr(rootlab), n_loc, int(g0), 0, 0, 0, be.stream())
-    # ---- border points against global roots, then the global numbering of roots
-    be.call("rhccq_dbscan_attach", p, be.ptr(ws), wsb, be.ptr(plan.core), be.stream())
-    n_own = own[1] - own[0]
-    ids = be.empty((max(n_own, 1),), torch.int32)
-    cnt = be.zeros((1,), torch.int32)
-    be.call("rhccq_dbscan_own_roots", p, be.ptr(ws), wsb, int(own[0]), int(own[1]), int(g0), be.ptr(ids), be.ptr(cnt),
-            be.stream(), launches=3)
-    n_r = int(cnt.item())
-    if world > 1:
-        sizes = [torch.zeros(1, dtype=torch.int64, device=be.device) for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([n_r], dtype=torch.int64, device=be.device), group=group)
-        sizes = [int(s.item()) for s in sizes]
-        m = max(max(sizes), 1)
-        mine = be.zeros((m,), torch.int32)
-        mine[:n_r] = ids[:n_r]
-        bufs = [be.empty((m,), torch.int32) for _ in range(world)]
-        dist.all_gather(bufs, mine, group=group)
-        roots = torch.cat([b[:s] for b, s in zip(bufs, sizes)]).contiguous()     # ascending: strips are ordered
-    else:
-        roots = ids[:n_r].contiguous()
-    labels = be.empty((max(n_own, 1),), torch.int32)
-    be.call("rhccq_uf_rank_labels", be.ptr(roots), int(roots.numel()), be.ptr(rootlab), int(own[0]), int(own[1]),
-            be.ptr(labels), be.stream())
-    if timings is not None:
-        timings.update(edges_local=n_e, edges_total=E, roots_total=int(roots.numel()))
-    return labels[:n_own], plan.core[own[0]:own[1]]
+    eng = PointDbscan(be, n_loc, dims, eps, min_pts, lo, hi, grid_dims)
+    return StripDbscan(be, eng, n_loc, g0, own, zone, group).run(pts_local, timings)
+
+
+def dbscan_image_strips(be: Backend, rows_local, W: int, row0: int, own_rows, zone_rows, eps: float, min_pts: int,
+                        group=None, timings: dict | None = None):
+    """The same for image rows through the lattice kernels.  rows_local: uint8 [h_loc, W, 3] (or float32
+    points [h_loc * W, 5]) = image rows [row0, row0 + h_loc); own_rows / zone_rows in local row indices."""
+    h_loc = rows_local.shape[0] if rows_local.dtype == torch.uint8 else rows_local.shape[0] // W
+    eng = LatticeDbscan(be, h_loc, W, eps, min_pts)
+    st = StripDbscan(be, eng, h_loc * W, row0 * W, (own_rows[0] * W, own_rows[1] * W),
+                     [(a * W, b * W) for a, b in zone_rows], group)
+    return st.run(rows_local, timings)
 
 
 # --------------------------------------------------------------------------- image lattice fast path
