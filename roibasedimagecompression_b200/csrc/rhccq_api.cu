@@ -172,7 +172,7 @@ size_t rhccq_palette_minibatch_workspace_bytes(int max_rows, int n_problems) {
     if (max_rows < 1 || n_problems < 1) return 0;
     const size_t kmax = (size_t)max_rows / 10 + 2;
     int slices = n_problems < rhccq_sm_count() ? n_problems : rhccq_sm_count();
-    return rhccq_carve_bytes((size_t)n_problems + 4, 4) + rhccq_carve_bytes((size_t)n_problems * 3 * kmax, 8)
+    return rhccq_carve_bytes((size_t)n_problems + 4 + 256, 4) + rhccq_carve_bytes((size_t)n_problems * 3 * kmax, 8)
            + (size_t)slices * rhccq_palette_minibatch_ws_bytes(max_rows);
 }
 

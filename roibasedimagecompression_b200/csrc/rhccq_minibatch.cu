@@ -16,6 +16,7 @@
 #define RHCCQ_MB_THREADS 512
 #define RHCCQ_MB_BATCH 1000
 #define RHCCQ_MB_MAXT 12
+#define RHCCQ_MB_CLUSTER 8           // CTAs (SMs) that walk one palette together
 
 // ---------------------------------------------------------------- MT19937 as numpy.random.RandomState(42)
 struct rhccq_mt { uint32_t* s; int* pos; };
@@ -151,7 +152,8 @@ __host__ __device__ static inline size_t rhccq_mb_bytes(size_t n, size_t kmax, s
     while (k2 < kmax) k2 <<= 1;
     return rhccq_carve_bytes(n, 4) + rhccq_carve_bytes(n, 8) + rhccq_carve_bytes(init_max, 4) * 2 + rhccq_carve_bytes(init_max, 8)
            + rhccq_carve_bytes(3 * kmax, 8) * 2 + rhccq_carve_bytes(kmax, 8) + rhccq_carve_bytes(k2, 8)
-           + rhccq_carve_bytes(kmax + 1, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 4) + rhccq_carve_bytes(init_max, 4);
+           + rhccq_carve_bytes(kmax + 1, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 4) + rhccq_carve_bytes(init_max, 4)
+           + rhccq_carve_bytes(16, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 8);
 }
 size_t rhccq_palette_minibatch_ws_bytes(int max_rows) {
     // k <= n / 10 (q <= 100); init subset <= max(3000, 3k)
@@ -160,10 +162,34 @@ size_t rhccq_palette_minibatch_ws_bytes(int max_rows) {
     return rhccq_mb_bytes(n, kmax, init < n ? init : n);
 }
 
-template <bool SMEMC>
+// Barrier over the CTAs of a thread-block cluster (release / acquire at cluster scope: global-memory writes
+// before it are visible to every CTA of the cluster after it).  One CTA per "cluster" in the emulation build.
+__device__ __forceinline__ void rhccq_cluster_sync() {
+#ifdef RHCCQ_HOST_EMU
+    __syncthreads();
+#else
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void rhccq_cluster_rank(int* rank, int* size, int* id) {
+#ifdef RHCCQ_HOST_EMU
+    *rank = 0; *size = 1; *id = (int)blockIdx.x;
+#else
+    unsigned r, n, c;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(n));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(c));
+    *rank = (int)r; *size = (int)n; *id = (int)c;
+#endif
+}
+
+// One palette, walked by the CTAs of one cluster.  The seeding and everything that consumes the random stream
+// or is sequential by definition (batch selection, inertia, reassignment, convergence) runs on the CTA of rank
+// 0; the two phases proportional to batch x k — the labels of the batch and the centre update — are spread
+// over all CTAs, exchanging through the global workspace between cluster barriers.
 __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, const double* __restrict__ quality,
                                         int* __restrict__ n_clusters, int max_rows, unsigned char* wsbase,
-                                        double* __restrict__ centers_out, double* smem_centers) {
+                                        double* __restrict__ centers_out, int rank, int csize) {
     __shared__ uint32_t s_mt[624];
     __shared__ int s_mtpos;
     __shared__ int s_i[RHCCQ_MAX_WARPS + 2 + 16];
@@ -171,16 +197,16 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
     __shared__ double s_d[RHCCQ_MAX_WARPS + 2];
     __shared__ int s_lab[RHCCQ_MB_BATCH];
     __shared__ double s_own[RHCCQ_MB_BATCH];
+    __shared__ uint32_t s_col[RHCCQ_MB_BATCH];
     __shared__ int s_cand[RHCCQ_MB_MAXT];
-    __shared__ int s_flag, s_nre;
     __shared__ double s_val;
     const int n_all = B.pal_cnt[p];
     const uint32_t* keys = B.pal_keys + B.pal_off[p];
-    if (n_all > max_rows) { if (threadIdx.x == 0) n_clusters[p] = -1; return; }
     const size_t kmax = (size_t)max_rows / 10 + 2;
     size_t init_max = 3 * kmax > 3 * RHCCQ_MB_BATCH ? 3 * kmax : 3 * RHCCQ_MB_BATCH;
     if (init_max > (size_t)max_rows) init_max = (size_t)max_rows;
     rhccq_mb_ws W;
+    int* hdr; int* lab_g; double* own_g;
     {
         rhccq_carver cv(wsbase);
         size_t k2 = 1;
@@ -197,20 +223,26 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         W.flag = cv.take<int>(kmax + 1);
         W.perm = cv.take<int>(RHCCQ_MB_BATCH);
         W.perm_xs = cv.take<uint32_t>(init_max);
-        if (SMEMC) { W.center = smem_centers; W.center_new = smem_centers + 3 * kmax; }     // compile-time: LDS in the E step
+        hdr = cv.take<int>(16);
+        lab_g = cv.take<int>(RHCCQ_MB_BATCH);
+        own_g = cv.take<double>(RHCCQ_MB_BATCH);
     }
+    const rhccq_mt mt = {s_mt, &s_mtpos};
+    int status = 0, n = 0, k = 0, batch = 0;
+    if (rank == 0) {
+        do {
+            if (n_all > max_rows) { status = -1; break; }
     // non-black rows in row order (clustering.py:185-192)
     int* mark = reinterpret_cast<int*>(W.cdf);                      // n ints fit into n doubles
     RHCCQ_PAR_FOR(i, n_all) mark[i] = keys[i] != 0u ? 1 : 0;
     __syncthreads();
-    const int n = rhccq_block_excl_scan_array<int>(mark, n_all, s_i);
+    n = rhccq_block_excl_scan_array<int>(mark, n_all, s_i);
     RHCCQ_PAR_FOR(i, n_all) if (keys[i] != 0u) W.nb[mark[i]] = i;
     __syncthreads();
-    const int k = rhccq_mb_k(n, quality[p]);
-    if (k < 1 || k > n || (size_t)k > kmax - 1) { if (threadIdx.x == 0) n_clusters[p] = -1; return; }
-    const int batch = n < RHCCQ_MB_BATCH ? n : RHCCQ_MB_BATCH;
+    k = rhccq_mb_k(n, quality[p]);
+    if (k < 1 || k > n || (size_t)k > kmax - 1) { status = -1; break; }
+    batch = n < RHCCQ_MB_BATCH ? n : RHCCQ_MB_BATCH;
     const int init_size = rhccq_mb_init_size(n, k);
-    const rhccq_mt mt = {s_mt, &s_mtpos};
     // ---- RandomState(42); validation indices are drawn and dropped (n_init == 1); init subset
     if (threadIdx.x == 0) {
         rhccq_mt_seed(mt, 42u);
@@ -292,179 +324,214 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         pot = best_pot;
     }
     __syncthreads();
-    // ---- mini-batch steps (_kmeans.py:2160-2215)
-    RHCCQ_PAR_FOR(q, k) W.counts[q] = 0.0;
-    if (threadIdx.x == 0) {                                         // cdf of choice(n, batch, p=ones/n)
-        const double pi = __ddiv_rn(1.0, (double)n);
-        double run = 0.0;
-        for (int i = 0; i < n; ++i) { run = __dadd_rn(run, pi); W.cdf[i] = run; }
+            RHCCQ_PAR_FOR(q, k) W.counts[q] = 0.0;
+            if (threadIdx.x == 0) {                                 // cdf of choice(n, batch, p=ones/n)
+                const double pi = __ddiv_rn(1.0, (double)n);
+                double run = 0.0;
+                for (int i = 0; i < n; ++i) { run = __dadd_rn(run, pi); W.cdf[i] = run; }
+            }
+        } while (0);
+        __syncthreads();
+        if (threadIdx.x == 0) { hdr[0] = status; hdr[1] = n; hdr[2] = k; hdr[3] = batch; hdr[4] = 0; }
     }
-    __syncthreads();
+    rhccq_cluster_sync();
+    status = hdr[0]; n = hdr[1]; k = hdr[2]; batch = hdr[3];
+    if (status < 0) {                                               // cluster-uniform
+        if (rank == 0 && threadIdx.x == 0) n_clusters[p] = status;
+        return;
+    }
+    // ---- mini-batch steps (_kmeans.py:2160-2215)
     const double cdf_last = W.cdf[n - 1];
     const long long n_steps = (100LL * n) / batch;
-    int n_since = 0, no_improvement = 0;
+    int n_since = 0, no_improvement = 0;                            // rank 0's bookkeeping
     bool have_ewa = false, have_min = false;
     double ewa = 0.0, ewa_min = 0.0;
     int* bidx = W.sub;                                              // the batch's rows (nb order); the subset is dead
+    double* cen = W.center;
+    double* cen_new = W.center_new;
+    const int pts_per_cta = (batch + csize - 1) / csize;
+    const int k_per_cta = (k + csize - 1) / csize;
     for (long long step = 0; step < n_steps; ++step) {
-        // uniform_samples = random_sample(batch): two raw outputs per double, converted in place
-        rhccq_mt_fill_raw(mt, reinterpret_cast<uint32_t*>(s_own), 2 * batch);
-        RHCCQ_PAR_FOR(i, batch) {
-            const uint32_t a = reinterpret_cast<uint32_t*>(s_own)[2 * i] >> 5, b = reinterpret_cast<uint32_t*>(s_own)[2 * i + 1] >> 6;
-            s_own[i] = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
-        }
-        __syncthreads();
-        RHCCQ_PAR_FOR(i, batch) {
-            const double u = s_own[i];
-            int lo = 0, hi = n;                                    // searchsorted(cdf / last, u, side='right')
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ddiv_rn(W.cdf[mid], cdf_last) <= u) lo = mid + 1; else hi = mid; }
-            bidx[i] = lo < n ? lo : n - 1;
-        }
-        // _random_reassign (:2039-2054)
-        n_since += batch;
-        int zero = 0;
-        RHCCQ_PAR_FOR(q, k) if (W.counts[q] == 0.0) zero = 1;
-        zero = rhccq_block_or(zero, s_i);
-        const bool reassign = zero || n_since >= 10 * k;
-        if (reassign) n_since = 0;
-        __syncthreads();
-        // labels and distances of the batch: two points per thread against every centre
-        for (int i0 = (int)threadIdx.x; i0 < batch; i0 += 2 * (int)blockDim.x) {
-            const int i1 = i0 + (int)blockDim.x;
-            const uint32_t ca = keys[W.nb[bidx[i0]]], cb = keys[W.nb[bidx[i1 < batch ? i1 : i0]]];
-            const double a0 = (double)rhccq_key_r(ca), a1 = (double)rhccq_key_g(ca), a2 = (double)rhccq_key_b(ca);
-            const double b0 = (double)rhccq_key_r(cb), b1 = (double)rhccq_key_g(cb), b2 = (double)rhccq_key_b(cb);
-            double da = rhccq_mb_dist(a0, a1, a2, W.center), db = rhccq_mb_dist(b0, b1, b2, W.center);
-            int la = 0, lb = 0;
-            for (int q = 1; q < k; ++q) {
-                const double c0 = W.center[3 * q], c1 = W.center[3 * q + 1], c2 = W.center[3 * q + 2];
-                const double u0 = __dsub_rn(a0, c0), u1 = __dsub_rn(a1, c1), u2 = __dsub_rn(a2, c2);
-                const double v0 = __dsub_rn(b0, c0), v1 = __dsub_rn(b1, c1), v2 = __dsub_rn(b2, c2);
-                const double ea = __dadd_rn(__dadd_rn(__dmul_rn(u0, u0), __dmul_rn(u1, u1)), __dmul_rn(u2, u2));
-                const double eb = __dadd_rn(__dadd_rn(__dmul_rn(v0, v0), __dmul_rn(v1, v1)), __dmul_rn(v2, v2));
-                if (ea < da) { da = ea; la = q; }
-                if (eb < db) { db = eb; lb = q; }
-            }
-            s_lab[i0] = la; s_own[i0] = da;
-            if (i1 < batch) { s_lab[i1] = lb; s_own[i1] = db; }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {                                     // inertia in batch order
-            double in = 0.0;
-            for (int i = 0; i < batch; ++i) in = __dadd_rn(in, s_own[i]);
-            s_val = in;
-        }
-        // centre update, members in batch order (_k_means_minibatch.pyx:68-118)
-        RHCCQ_PAR_FOR(q, k) {
-            int members = 0;
-            for (int i = 0; i < batch; ++i) members += s_lab[i] == q;
-            if (members > 0) {
-                const double w = W.counts[q];
-                double c0 = __dmul_rn(W.center[3 * q], w), c1 = __dmul_rn(W.center[3 * q + 1], w), c2 = __dmul_rn(W.center[3 * q + 2], w);
-                for (int i = 0; i < batch; ++i) if (s_lab[i] == q) {
-                    const uint32_t c = keys[W.nb[bidx[i]]];
-                    c0 = __dadd_rn(c0, (double)rhccq_key_r(c)); c1 = __dadd_rn(c1, (double)rhccq_key_g(c)); c2 = __dadd_rn(c2, (double)rhccq_key_b(c));
-                }
-                const double wn = __dadd_rn(w, (double)members);
-                const double alpha = __ddiv_rn(1.0, wn);
-                W.counts[q] = wn;
-                W.center_new[3 * q] = __dmul_rn(c0, alpha); W.center_new[3 * q + 1] = __dmul_rn(c1, alpha); W.center_new[3 * q + 2] = __dmul_rn(c2, alpha);
-            } else {
-                W.center_new[3 * q] = W.center[3 * q]; W.center_new[3 * q + 1] = W.center[3 * q + 1]; W.center_new[3 * q + 2] = W.center[3 * q + 2];
-            }
-        }
-        __syncthreads();
-        const double inertia = s_val;
-        if (reassign) {                                             // :1652-1682
-            double mx = 0.0;
-            RHCCQ_PAR_FOR(q, k) if (W.counts[q] > mx) mx = W.counts[q];
-            mx = rhccq_block_max<double>(mx, s_d);
-            const double lim = __dmul_rn(0.01, mx);
-            int cnt = 0;
-            RHCCQ_PAR_FOR(q, k) { const int f = W.counts[q] < lim ? 1 : 0; W.flag[q] = f; cnt += f; }
-            cnt = rhccq_block_sum<int>(cnt, s_i);
-            if ((double)cnt > 0.5 * (double)batch) {
-                // keep all but the int(0.5 * batch) smallest counts (stable order: ties by index)
-                int k2 = 1;
-                while (k2 < k) k2 <<= 1;
-                for (int q = threadIdx.x; q < k2; q += blockDim.x)
-                    W.skey[q] = q < k ? (((unsigned long long)(long long)W.counts[q] << 24) | (unsigned)q) : ~0ull;
-                __syncthreads();
-                rhccq_block_bitonic_sort<unsigned long long>(W.skey, k2);
-                const int first_kept = (int)(0.5 * (double)batch);
-                RHCCQ_PAR_FOR(r, k) if (r >= first_kept) W.flag[(int)(W.skey[r] & 0xffffffu)] = 0;
-                __syncthreads();
-                cnt = 0;
-                RHCCQ_PAR_FOR(q, k) cnt += W.flag[q];
-                cnt = rhccq_block_sum<int>(cnt, s_i);
+        bool reassign = false;
+        if (rank == 0) {
+            // uniform_samples = random_sample(batch): two raw outputs per double, converted in place
+            rhccq_mt_fill_raw(mt, reinterpret_cast<uint32_t*>(s_own), 2 * batch);
+            RHCCQ_PAR_FOR(i, batch) {
+                const uint32_t a = reinterpret_cast<uint32_t*>(s_own)[2 * i] >> 5, b = reinterpret_cast<uint32_t*>(s_own)[2 * i + 1] >> 6;
+                s_own[i] = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
             }
             __syncthreads();
-            if (cnt > 0) {
-                if (threadIdx.x == 0) {                             // choice(batch, replace=False, size=cnt) == permutation(batch)[:cnt]
-                    for (int i = 0; i < batch; ++i) W.perm[i] = i;
-                    for (int i = batch - 1; i >= 1; --i) {
-                        const int j = (int)rhccq_mt_below(mt, (uint32_t)i);
-                        const int t = W.perm[i]; W.perm[i] = W.perm[j]; W.perm[j] = t;
+            RHCCQ_PAR_FOR(i, batch) {
+                const double u = s_own[i];
+                int lo = 0, hi = n;                                // searchsorted(cdf / last, u, side='right')
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ddiv_rn(W.cdf[mid], cdf_last) <= u) lo = mid + 1; else hi = mid; }
+                bidx[i] = lo < n ? lo : n - 1;
+            }
+            // _random_reassign (:2039-2054)
+            n_since += batch;
+            int zero = 0;
+            RHCCQ_PAR_FOR(q, k) if (W.counts[q] == 0.0) zero = 1;
+            zero = rhccq_block_or(zero, s_i);
+            reassign = zero || n_since >= 10 * k;
+            if (reassign) n_since = 0;
+        }
+        rhccq_cluster_sync();
+        // labels and distances of this CTA's share of the batch: four threads per point, each a quarter of the
+        // centres (interleaved); the first minimum is kept by comparing (distance, index)
+        {
+            const int p_lo = rank * pts_per_cta, p_hi = p_lo + pts_per_cta < batch ? p_lo + pts_per_cta : batch;
+            const int tpp = RHCCQ_WARP_SIZE >= 4 ? 4 : 1;           // threads per point
+            for (int i0 = p_lo; i0 < p_hi; i0 += (int)blockDim.x / tpp) {
+                const int i = i0 + (int)threadIdx.x / tpp, part = (int)threadIdx.x % tpp;
+                const bool have = i < p_hi;
+                const uint32_t c = keys[W.nb[bidx[have ? i : p_lo]]];
+                const double x0 = (double)rhccq_key_r(c), x1 = (double)rhccq_key_g(c), x2 = (double)rhccq_key_b(c);
+                double bd = 1.0e300;
+                int bq = 0x7fffffff;
+                for (int q = part; q < k; q += tpp) {
+                    const double d = rhccq_mb_dist(x0, x1, x2, cen + 3 * q);
+                    if (d < bd) { bd = d; bq = q; }
+                }
+                __syncwarp();                                       // the four parts ran different trip counts
+                for (int m = 1; m < tpp; m <<= 1) {
+                    const double od = rhccq_shfl_xor(bd, m);
+                    const int oq = rhccq_shfl_xor(bq, m);
+                    if (od < bd || (od == bd && oq < bq)) { bd = od; bq = oq; }
+                }
+                if (have && part == 0) { lab_g[i] = bq; own_g[i] = bd; }
+            }
+        }
+        rhccq_cluster_sync();
+        // centre update of this CTA's share of the clusters, members in batch order (_k_means_minibatch.pyx:68-118)
+        RHCCQ_PAR_FOR(i, batch) { s_lab[i] = lab_g[i]; s_col[i] = keys[W.nb[bidx[i]]]; }
+        __syncthreads();
+        {
+            const int q_lo = rank * k_per_cta, q_hi = q_lo + k_per_cta < k ? q_lo + k_per_cta : k;
+            for (int q = q_lo + (int)threadIdx.x; q < q_hi; q += (int)blockDim.x) {
+                int members = 0;
+                for (int i = 0; i < batch; ++i) members += s_lab[i] == q;
+                if (members > 0) {
+                    const double w = W.counts[q];
+                    double c0 = __dmul_rn(cen[3 * q], w), c1 = __dmul_rn(cen[3 * q + 1], w), c2 = __dmul_rn(cen[3 * q + 2], w);
+                    for (int i = 0; i < batch; ++i) if (s_lab[i] == q) {
+                        const uint32_t c = s_col[i];
+                        c0 = __dadd_rn(c0, (double)rhccq_key_r(c)); c1 = __dadd_rn(c1, (double)rhccq_key_g(c)); c2 = __dadd_rn(c2, (double)rhccq_key_b(c));
+                    }
+                    const double wn = __dadd_rn(w, (double)members);
+                    const double alpha = __ddiv_rn(1.0, wn);
+                    W.counts[q] = wn;
+                    cen_new[3 * q] = __dmul_rn(c0, alpha); cen_new[3 * q + 1] = __dmul_rn(c1, alpha); cen_new[3 * q + 2] = __dmul_rn(c2, alpha);
+                } else {
+                    cen_new[3 * q] = cen[3 * q]; cen_new[3 * q + 1] = cen[3 * q + 1]; cen_new[3 * q + 2] = cen[3 * q + 2];
+                }
+            }
+        }
+        rhccq_cluster_sync();
+        if (rank == 0) {
+            if (threadIdx.x == 0) {                                 // inertia in batch order
+                double in = 0.0;
+                for (int i = 0; i < batch; ++i) in = __dadd_rn(in, own_g[i]);
+                s_val = in;
+            }
+            __syncthreads();
+            const double inertia = s_val;
+            if (reassign) {                                             // :1652-1682
+                double mx = 0.0;
+                RHCCQ_PAR_FOR(q, k) if (W.counts[q] > mx) mx = W.counts[q];
+                mx = rhccq_block_max<double>(mx, s_d);
+                const double lim = __dmul_rn(0.01, mx);
+                int cnt = 0;
+                RHCCQ_PAR_FOR(q, k) { const int f = W.counts[q] < lim ? 1 : 0; W.flag[q] = f; cnt += f; }
+                cnt = rhccq_block_sum<int>(cnt, s_i);
+                if ((double)cnt > 0.5 * (double)batch) {
+                    // keep all but the int(0.5 * batch) smallest counts (stable order: ties by index)
+                    int k2 = 1;
+                    while (k2 < k) k2 <<= 1;
+                    for (int q = threadIdx.x; q < k2; q += blockDim.x)
+                        W.skey[q] = q < k ? (((unsigned long long)(long long)W.counts[q] << 24) | (unsigned)q) : ~0ull;
+                    __syncthreads();
+                    rhccq_block_bitonic_sort<unsigned long long>(W.skey, k2);
+                    const int first_kept = (int)(0.5 * (double)batch);
+                    RHCCQ_PAR_FOR(r, k) if (r >= first_kept) W.flag[(int)(W.skey[r] & 0xffffffu)] = 0;
+                    __syncthreads();
+                    cnt = 0;
+                    RHCCQ_PAR_FOR(q, k) cnt += W.flag[q];
+                    cnt = rhccq_block_sum<int>(cnt, s_i);
+                }
+                __syncthreads();
+                if (cnt > 0) {
+                    if (threadIdx.x == 0) {                             // choice(batch, replace=False, size=cnt) == permutation(batch)[:cnt]
+                        for (int i = 0; i < batch; ++i) W.perm[i] = i;
+                        for (int i = batch - 1; i >= 1; --i) {
+                            const int j = (int)rhccq_mt_below(mt, (uint32_t)i);
+                            const int t = W.perm[i]; W.perm[i] = W.perm[j]; W.perm[j] = t;
+                        }
+                    }
+                    // rank of every flagged centre among the flagged ones, ascending
+                    int* rank = reinterpret_cast<int*>(W.skey);
+                    RHCCQ_PAR_FOR(q, k) rank[q] = W.flag[q];
+                    __syncthreads();
+                    rhccq_block_excl_scan_array<int>(rank, k, s_i);
+                    RHCCQ_PAR_FOR(q, k) if (W.flag[q]) {
+                        const uint32_t c = keys[W.nb[bidx[W.perm[rank[q]]]]];
+                        cen_new[3 * q] = (double)rhccq_key_r(c); cen_new[3 * q + 1] = (double)rhccq_key_g(c); cen_new[3 * q + 2] = (double)rhccq_key_b(c);
                     }
                 }
-                // rank of every flagged centre among the flagged ones, ascending
-                int* rank = reinterpret_cast<int*>(W.skey);
-                RHCCQ_PAR_FOR(q, k) rank[q] = W.flag[q];
+                double mn = 1.0e300;
+                RHCCQ_PAR_FOR(q, k) if (!W.flag[q] && W.counts[q] < mn) mn = W.counts[q];
+                mn = rhccq_block_min<double>(mn, s_d);
+                if (mn < 1.0e300) RHCCQ_PAR_FOR(q, k) if (W.flag[q]) W.counts[q] = mn;
                 __syncthreads();
-                rhccq_block_excl_scan_array<int>(rank, k, s_i);
-                RHCCQ_PAR_FOR(q, k) if (W.flag[q]) {
-                    const uint32_t c = keys[W.nb[bidx[W.perm[rank[q]]]]];
-                    W.center_new[3 * q] = (double)rhccq_key_r(c); W.center_new[3 * q + 1] = (double)rhccq_key_g(c); W.center_new[3 * q + 2] = (double)rhccq_key_b(c);
-                }
             }
-            double mn = 1.0e300;
-            RHCCQ_PAR_FOR(q, k) if (!W.flag[q] && W.counts[q] < mn) mn = W.counts[q];
-            mn = rhccq_block_min<double>(mn, s_d);
-            if (mn < 1.0e300) RHCCQ_PAR_FOR(q, k) if (W.flag[q]) W.counts[q] = mn;
+            int done = 0;
+            do {
+                // _mini_batch_convergence (:1974-2037), tol == 0
+                const double bi = __ddiv_rn(inertia, (double)batch);
+                if (step == 0) break;
+                if (!have_ewa) { ewa = bi; have_ewa = true; }
+                else {
+                    double alpha = __ddiv_rn(__dmul_rn((double)batch, 2.0), (double)(n + 1));
+                    if (alpha > 1.0) alpha = 1.0;
+                    ewa = __dadd_rn(__dmul_rn(ewa, __dsub_rn(1.0, alpha)), __dmul_rn(bi, alpha));
+                }
+                if (!have_min || ewa < ewa_min) { no_improvement = 0; ewa_min = ewa; have_min = true; }
+                else ++no_improvement;
+                if (no_improvement >= 10) done = 1;
+            } while (0);
             __syncthreads();
+            if (threadIdx.x == 0) hdr[4] = done;
         }
-        { double* t = W.center; W.center = W.center_new; W.center_new = t; }
-        __syncthreads();
-        // _mini_batch_convergence (:1974-2037), tol == 0
-        const double bi = __ddiv_rn(inertia, (double)batch);
-        if (step == 0) continue;
-        if (!have_ewa) { ewa = bi; have_ewa = true; }
-        else {
-            double alpha = __ddiv_rn(__dmul_rn((double)batch, 2.0), (double)(n + 1));
-            if (alpha > 1.0) alpha = 1.0;
-            ewa = __dadd_rn(__dmul_rn(ewa, __dsub_rn(1.0, alpha)), __dmul_rn(bi, alpha));
-        }
-        if (!have_min || ewa < ewa_min) { no_improvement = 0; ewa_min = ewa; have_min = true; }
-        else ++no_improvement;
-        if (no_improvement >= 10) break;
+        rhccq_cluster_sync();
+        { double* t = cen; cen = cen_new; cen_new = t; }
+        if (hdr[4]) break;                                          // cluster-uniform
     }
-    __syncthreads();
-    RHCCQ_PAR_FOR(q, 3 * k) centers_out[q] = W.center[q];
-    if (threadIdx.x == 0) n_clusters[p] = k;
+    if (rank == 0) {
+        RHCCQ_PAR_FOR(q, 3 * k) centers_out[q] = cen[q];
+        if (threadIdx.x == 0) n_clusters[p] = k;
+    }
 }
 
-// status -4 (set by rhccq_k_palette_dbscan) selects the palettes of this branch
-template <bool SMEMC>
+// status -4 (set by rhccq_k_palette_dbscan) selects the palettes of this branch; one cluster of CTAs per palette
 __global__ void __launch_bounds__(RHCCQ_MB_THREADS)
 rhccq_k_palette_minibatch(rhccq_palette_batch B, const double* __restrict__ quality, int* __restrict__ n_clusters,
                           int max_rows, unsigned char* gws, size_t gws_stride, double* __restrict__ centers,
-                          size_t centers_stride, int* __restrict__ todo) {
-    RHCCQ_DYN_SMEM(dyn);
-    __shared__ int s_p;
+                          size_t centers_stride, int* __restrict__ todo, int* __restrict__ claim) {
+    int rank, csize, cid;
+    rhccq_cluster_rank(&rank, &csize, &cid);
     while (true) {
-        if (threadIdx.x == 0) {
-            // next palette that needs the branch: a grid-wide cursor keeps one workspace slice per CTA enough
+        if (rank == 0 && threadIdx.x == 0) {
+            // next palette that needs the branch: a grid-wide cursor keeps one workspace slice per cluster enough
             int p;
             while ((p = atomicAdd(todo, 1)) < B.n_problems && n_clusters[p] != -4) {}
-            s_p = p;
+            claim[cid] = p;
         }
-        __syncthreads();
-        const int p = s_p;
-        __syncthreads();
+        rhccq_cluster_sync();
+        const int p = claim[cid];
+        rhccq_cluster_sync();
         if (p >= B.n_problems) return;
-        rhccq_minibatch_problem<SMEMC>(B, p, quality, n_clusters, max_rows, gws + (size_t)blockIdx.x * gws_stride,
-                                       centers + (size_t)p * centers_stride, reinterpret_cast<double*>(dyn));
-        __syncthreads();
+        rhccq_minibatch_problem(B, p, quality, n_clusters, max_rows, gws + (size_t)cid * gws_stride,
+                                centers + (size_t)p * centers_stride, rank, csize);
+        rhccq_cluster_sync();
     }
 }
 
@@ -499,37 +566,47 @@ int rhccq_launch_palette_minibatch(const rhccq_palette_batch& B, const double* q
     const size_t slice = rhccq_palette_minibatch_ws_bytes(max_rows);
     const size_t kmax = (size_t)max_rows / 10 + 2;
     const size_t cstride = 3 * kmax;
-    // workspace: [todo cursor + copy of the status vector][centres of every palette][one slice per CTA]
-    const size_t head = rhccq_carve_bytes((size_t)B.n_problems + 4, 4);
+    // workspace: [todo cursor, claim slots, copy of the status vector][centres of every palette][one slice per cluster]
+    const size_t head = rhccq_carve_bytes((size_t)B.n_problems + 4 + 256, 4);
     const size_t cbytes = rhccq_carve_bytes((size_t)B.n_problems * cstride, 8);
     if (!ws.ws || ws.ws_bytes < head + cbytes + slice) {
         rhccq_set_error("rhccq_palette_minibatch: workspace of %zu bytes is smaller than %zu", ws.ws_bytes, head + cbytes + slice);
         return -1;
     }
-    int grid = (int)((ws.ws_bytes - head - cbytes) / slice);
-    if (grid > B.n_problems) grid = B.n_problems;
-    const int cap = rhccq_sm_count();
-    if (grid > cap) grid = cap;
+    // one cluster of RHCCQ_MB_CLUSTER CTAs per palette in flight; every cluster owns one workspace slice
+    int workers = (int)((ws.ws_bytes - head - cbytes) / slice);
+    if (workers > B.n_problems) workers = B.n_problems;
+    const int cap = rhccq_sm_count() / RHCCQ_MB_CLUSTER;
+    if (workers > cap) workers = cap;
+    if (workers < 1) workers = 1;
     int* todo = (int*)ws.ws;
-    int* before = todo + 4;
+    int* claim = todo + 4;                                          // one slot per cluster, then the status copy
+    int* before = claim + workers;
     double* centers = (double*)(ws.ws + head);
     unsigned char* slices = ws.ws + head + cbytes;
 #ifdef RHCCQ_HOST_EMU
     memset(todo, 0, 16);
     memcpy(before, n_clusters, (size_t)B.n_problems * 4);
+    RHCCQ_LAUNCH(rhccq_k_palette_minibatch, workers, RHCCQ_MB_THREADS, 0, (cudaStream_t)stream, B, quality, n_clusters, max_rows,
+                 slices, slice, centers, cstride, todo, claim);
 #else
     cudaMemsetAsync(todo, 0, 16, (cudaStream_t)stream);
     cudaMemcpyAsync(before, n_clusters, (size_t)B.n_problems * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-#endif
-    const size_t csmem = 2 * 3 * kmax * sizeof(double);             // centre tables of the steps, in shared memory if they fit
-    if (csmem + 20 * 1024 <= RHCCQ_SMEM_BUDGET) {
-        if (rhccq_smem_optin((const void*)rhccq_k_palette_minibatch<true>, csmem) != 0) return -1;
-        RHCCQ_LAUNCH(rhccq_k_palette_minibatch<true>, grid, RHCCQ_MB_THREADS, csmem, (cudaStream_t)stream, B, quality, n_clusters,
-                     max_rows, slices, slice, centers, cstride, todo);
-    } else {
-        RHCCQ_LAUNCH(rhccq_k_palette_minibatch<false>, grid, RHCCQ_MB_THREADS, 0, (cudaStream_t)stream, B, quality, n_clusters,
-                     max_rows, slices, slice, centers, cstride, todo);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(workers * RHCCQ_MB_CLUSTER), 1, 1);
+        cfg.blockDim = dim3(RHCCQ_MB_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = RHCCQ_MB_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, rhccq_k_palette_minibatch, B, quality, n_clusters, max_rows, slices, slice,
+                                           centers, cstride, todo, claim);
+        if (e != cudaSuccess) { rhccq_set_error("rhccq_palette_minibatch: cluster launch failed: %s", cudaGetErrorString(e)); return -1; }
     }
+#endif
     const int chunks = 64;
     int g2 = B.n_problems * chunks;
     const int cap2 = rhccq_sm_count() * 8;

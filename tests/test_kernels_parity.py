@@ -346,3 +346,17 @@ def test_pipeline_with_large_segments_minibatch_in_stage1(backend):
     pal, idx = _encode_device(backend, img, roi, non)
     assert np.array_equal(pal, want["palette"])
     assert np.array_equal(idx, want["indices"])
+
+
+def test_pipeline_one_huge_segment_and_an_empty_class(backend):
+    """A 40 000-pixel segment (38 752 colours: unique runs from the global workspace, stage 1 takes the
+    MiniBatchKMeans branch, the split its wide-index form) next to a small one; the non-ROI class is empty."""
+    H, W = 200, 260
+    img = synth(H, W, 5, sigma=8.0)
+    seg = np.ones((H, W), np.int32)
+    seg[:, 200:] = 2
+    roi = [{"bbox": (0, 0, H, W), "bbox_mask": np.ones((H, W), bool), "segments": seg}]
+    want = O.encode_image(img, roi, [])
+    pal, idx = _encode_device(backend, img, roi, [])
+    assert np.array_equal(pal, want["palette"])
+    assert np.array_equal(idx, want["indices"])
