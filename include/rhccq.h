@@ -271,6 +271,15 @@ int rhccq_uf_rank_labels(const int32_t* sorted_roots, int n_roots, const int32_t
 /* labels int32 [n], original order */
 int rhccq_dbscan_relabel(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, int32_t* labels, void* stream);
 
+/* ------------------------------------------------------------------ decoder side
+ * out_rgb[i] = palette[indices[i]] (decoder/uncompression/uncompression.py:209); indices of 1, 2 or 4 bytes,
+ * palette uint8 [n_palette,3]; *bad = 1 when an index is outside the palette (zero it first).
+ * acc2 (int64 [2], zeroed by the caller) += (sum of squared differences, sum of absolute differences) of two
+ * uint8 arrays: MSE, PSNR and MAE of decoder/uncompression/comparison.py:43-44,64-79. */
+int rhccq_decode_gather(const void* indices, int idx_bytes, long long n, const uint8_t* palette, int n_palette,
+                        uint8_t* out_rgb, int32_t* bad, void* stream);
+int rhccq_sq_abs_err(const uint8_t* a, const uint8_t* b, long long n, long long* acc2, void* stream);
+
 /* out[i] = sum_{j<i} max(in[j],0), out[n] = total. */
 int rhccq_excl_scan(const int32_t* in, int n, int32_t* out, void* stream);
 

@@ -279,6 +279,19 @@ int rhccq_comp_pass(const int32_t* comps, int n_comps, const int32_t* indices, i
     return rhccq_after_launch("rhccq_comp_pass");
 }
 
+int rhccq_decode_gather(const void* indices, int idx_bytes, long long n, const uint8_t* palette, int n_palette,
+                        uint8_t* out_rgb, int32_t* bad, void* stream) {
+    RHCCQ_REQUIRE(indices && palette && out_rgb && bad && n >= 0 && n_palette >= 0, "rhccq_decode_gather");
+    if (rhccq_launch_decode_gather(indices, idx_bytes, n, palette, n_palette, out_rgb, bad, stream) != 0) return -1;
+    return rhccq_after_launch("rhccq_decode_gather");
+}
+
+int rhccq_sq_abs_err(const uint8_t* a, const uint8_t* b, long long n, long long* acc2, void* stream) {
+    RHCCQ_REQUIRE(a && b && acc2 && n >= 0, "rhccq_sq_abs_err");
+    if (rhccq_launch_sq_abs_err(a, b, n, acc2, stream) != 0) return -1;
+    return rhccq_after_launch("rhccq_sq_abs_err");
+}
+
 int rhccq_excl_scan(const int32_t* in, int n, int32_t* out, void* stream) {
     RHCCQ_REQUIRE(in && out && n >= 0, "rhccq_excl_scan");
     if (rhccq_launch_excl_scan(in, n, out, stream) != 0) return -1;

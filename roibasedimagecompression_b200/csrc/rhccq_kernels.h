@@ -90,6 +90,9 @@ int rhccq_launch_first_min(const int* off, const int* cnt, const int* n_leaves, 
 int rhccq_launch_compose_final(const rhccq_compose& C, void* stream);
 int rhccq_launch_comp_pass(const int32_t* comps, int n_comps, const int32_t* indices, int Hc, int Wc, int mode,
                            const int* map, uint32_t* fpos, int* prio, int32_t* canvas, void* stream);
+int rhccq_launch_decode_gather(const void* idx, int idx_bytes, long long n, const uint8_t* pal, int n_pal, uint8_t* out,
+                               int* bad, void* stream);
+int rhccq_launch_sq_abs_err(const uint8_t* a, const uint8_t* b, long long n, long long* acc, void* stream);
 int rhccq_launch_excl_scan(const int* in, int n, int* out, void* stream);
 
 // Shared-memory or global-workspace placement of a per-CTA working set of

@@ -274,3 +274,50 @@ int rhccq_launch_paint(const int32_t* seg, int B, int H, int W, const int32_t* c
     }
     return 0;
 }
+
+// ---------------------------------------------------------------- decoder gather and quality metrics
+// image = palette[indices] (/root/reference/decoder/uncompression/uncompression.py:209) and the sums behind
+// MSE / PSNR / MAE (decoder/uncompression/comparison.py:43-44,64-79): streaming, HBM-bound.
+template <class IdxT>
+__global__ void __launch_bounds__(RHCCQ_PIXEL_THREADS)
+rhccq_k_decode_gather(const IdxT* __restrict__ idx, long long n, const uint8_t* __restrict__ pal, int n_pal,
+                      uint8_t* __restrict__ out, int* __restrict__ bad) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned v = (unsigned)idx[i];
+        if (v >= (unsigned)n_pal) { *bad = 1; continue; }
+        out[3 * i] = pal[3 * v]; out[3 * i + 1] = pal[3 * v + 1]; out[3 * i + 2] = pal[3 * v + 2];
+    }
+}
+__global__ void __launch_bounds__(RHCCQ_PIXEL_THREADS)
+rhccq_k_sq_abs_err(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, long long n, long long* __restrict__ acc) {
+    __shared__ long long s_ll[RHCCQ_MAX_WARPS + 2];
+    long long sq = 0, ab = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)a[i] - (int)b[i];
+        sq += d * d; ab += d < 0 ? -d : d;
+    }
+    sq = rhccq_block_sum<long long>(sq, s_ll);
+    ab = rhccq_block_sum<long long>(ab, s_ll);
+    if (threadIdx.x == 0) { atomicAdd((unsigned long long*)&acc[0], (unsigned long long)sq); atomicAdd((unsigned long long*)&acc[1], (unsigned long long)ab); }
+}
+
+int rhccq_launch_decode_gather(const void* idx, int idx_bytes, long long n, const uint8_t* pal, int n_pal, uint8_t* out,
+                               int* bad, void* stream) {
+    if (n <= 0) return 0;
+    long long blocks = (n + RHCCQ_PIXEL_THREADS - 1) / RHCCQ_PIXEL_THREADS;
+    const long long cap = (long long)rhccq_sm_count() * 16;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    if (idx_bytes == 1) RHCCQ_LAUNCH(rhccq_k_decode_gather<uint8_t>, grid, RHCCQ_PIXEL_THREADS, 0, (cudaStream_t)stream, (const uint8_t*)idx, n, pal, n_pal, out, bad);
+    else if (idx_bytes == 2) RHCCQ_LAUNCH(rhccq_k_decode_gather<uint16_t>, grid, RHCCQ_PIXEL_THREADS, 0, (cudaStream_t)stream, (const uint16_t*)idx, n, pal, n_pal, out, bad);
+    else if (idx_bytes == 4) RHCCQ_LAUNCH(rhccq_k_decode_gather<uint32_t>, grid, RHCCQ_PIXEL_THREADS, 0, (cudaStream_t)stream, (const uint32_t*)idx, n, pal, n_pal, out, bad);
+    else { rhccq_set_error("rhccq_decode_gather: idx_bytes must be 1, 2 or 4"); return -1; }
+    return 0;
+}
+int rhccq_launch_sq_abs_err(const uint8_t* a, const uint8_t* b, long long n, long long* acc, void* stream) {
+    if (n <= 0) return 0;
+    long long blocks = (n + RHCCQ_PIXEL_THREADS * 8 - 1) / (RHCCQ_PIXEL_THREADS * 8);
+    const long long cap = (long long)rhccq_sm_count() * 8;
+    const int grid = (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+    RHCCQ_LAUNCH(rhccq_k_sq_abs_err, grid, RHCCQ_PIXEL_THREADS, 0, (cudaStream_t)stream, a, b, n, acc);
+    return 0;
+}

@@ -9,3 +9,6 @@ from .merging import merge_region_components_simple                             
 from .subregions import subregion_quantization                                             # noqa: F401
 from .regions import region_quantization                                                   # noqa: F401
 from .image import quantize_image                                                          # noqa: F401
+from .image import optimize_compressed_dtype                                               # noqa: F401
+from .compression import (compress_palette, compress_indices_simple_optimized, lossless_compress_optimized,   # noqa: F401
+                          save_compressed, save_compression, save_encoded)

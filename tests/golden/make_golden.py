@@ -345,8 +345,29 @@ def main_minibatch():
     save("minibatch_palette.npz", **d)
 
 
+def main_container():
+    """G8: the container writer (compression.py:119-220) on the final result of the small pipeline golden,
+    and one of the reference's own shipped outputs (images/rhccq_20_10/Lenna_compressed.rhccq) for the reader."""
+    import shutil
+    import tempfile
+    with quiet():
+        from encoder.compression import compression as ref_comp
+    g = np.load(os.path.join(OUT, "pipeline_small.npz"))
+    pal, idx, shape = g["palette"], g["indices"], tuple(int(v) for v in g["shape"])
+    with quiet():
+        pkg = ref_comp.lossless_compress_optimized([tuple(int(v) for v in c) for c in pal],
+                                                   idx.astype(np.int64).reshape(shape), shape)
+        fn = os.path.join(tempfile.mkdtemp(), "x.rhccq")
+        ref_comp.save_compressed(pkg, fn)
+    shutil.copy(fn, os.path.join(OUT, "container_small.rhccq"))
+    shutil.copy(os.path.join(REF, "images/rhccq_20_10/Lenna_compressed.rhccq"), os.path.join(OUT, "reference_Lenna_compressed.rhccq"))
+    print("wrote container_small.rhccq", os.path.getsize(os.path.join(OUT, "container_small.rhccq")), "bytes")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "minibatch":
+    if len(sys.argv) > 1 and sys.argv[1] == "container":
+        main_container()
+    elif len(sys.argv) > 1 and sys.argv[1] == "minibatch":
         main_minibatch()
     else:
         main()
