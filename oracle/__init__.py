@@ -15,9 +15,13 @@ Contents
 ``kmeans_restated`` the exact-arithmetic restatement of scikit-learn's
                    KMeans(k, random_state=42, n_init='auto') that the CUDA
                    k-means kernel must match bit for bit.
-``dbscan_ref.c``   plain-C grid/union-find restatement of scikit-learn DBSCAN
-                   (sklearn/cluster/_dbscan.py, _dbscan_inner.pyx) for point
-                   counts sklearn cannot hold in memory.
+``minibatch_restated`` the same for MiniBatchKMeans (the >= 10 000-colour branch).
+
+Large point sets: ``rhccq_oracle.dbscan_labels`` is a brute-force restatement of
+scikit-learn's DBSCAN for up to ~20 000 points; beyond that the tests compare with
+scikit-learn itself (262 144 and 1 048 576 points on the GPU box) and check
+size-independent properties (determinism, numbering by lowest core index, brute
+force inside sampled windows, strips == unsplit).
 
 Parity pinning: the restatement is checked in ``tests/`` against (1) golden
 vectors produced by importing the reference's own modules

@@ -84,7 +84,9 @@ struct rhccq_cfg_large {
 // The K-Means below is written once against a "group": the whole CTA or one
 // warp.  Every member of the group must call the collective functions.
 struct rhccq_grp_cta {
+    static const bool kCta = true;
     long long* sll;                    // RHCCQ_MAX_WARPS * RHCCQ_KM_MAXT + 2 elements of shared scratch
+    unsigned long long* csum;          // one slot per thread: chunk sums of the seeding
     __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
     __device__ __forceinline__ int size() const { return (int)blockDim.x; }
     __device__ __forceinline__ int sub() const { return RHCCQ_WARP; }          // warp of the caller inside the group
@@ -143,6 +145,8 @@ struct rhccq_grp_cta {
 };
 
 struct rhccq_grp_warp {
+    static const bool kCta = false;
+    unsigned long long* csum;          // unused
     __device__ __forceinline__ int tid() const { return RHCCQ_LANE; }
     __device__ __forceinline__ int size() const { return RHCCQ_WARP_SIZE; }
     __device__ __forceinline__ int sub() const { return 0; }
@@ -206,6 +210,18 @@ struct rhccq_grp_warp {
     __device__ __forceinline__ double bcast_d(double v) const { __syncwarp(); return __shfl_sync(0xffffffffu, v, 0); }
 #endif
 };
+
+__device__ __forceinline__ unsigned long long rhccq_warp_incl_scan_u64(unsigned long long v) {
+#ifndef RHCCQ_HOST_EMU
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+#endif
+    return v;
+}
 
 // ---------------------------------------------------------------- K-Means (exact arithmetic)
 __device__ __forceinline__ int rhccq_kmeans_local_trials(int k) {   // 2 + int(log(k)), sklearn/_kmeans.py:226
@@ -327,22 +343,63 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
     const long long S1[3] = {acc[1], acc[2], acc[3]}, S2[3] = {acc[4], acc[5], acc[6]};
     int ri = 1;
     for (int c = 1; c < k; ++c) {
-        // inclusive cumulative sum of closest (exact integers)
-        cum_t total;
-        cum_t run = g.template excl_scan<cum_t>(chunk_sum, &total);
-        for (int j = c_lo; j < c_hi; ++j) { run += closest[j]; cum[j] = run; }
-        g.sync();
-        // candidates: searchsorted(cum, r * pot, side='left'), clipped
-        for (int t = tid; t < T; t += gsz) {
-            const double rv = __dmul_rn(rng[ri + t], (double)pot);
-            int l = 0, h = n;                                       // first j with cum[j] >= rv
-            while (l < h) {
-                const int mid = (l + h) >> 1;
-                if ((double)cum[mid] < rv) l = mid + 1; else h = mid;
+        if (G::kCta) {
+            // Candidates without materialising the cumulative sum: every thread publishes the sum of its chunk;
+            // one warp per trial scans the chunk sums (shuffles), finds the chunk in which the inclusive sum
+            // first reaches r * pot, then the element inside it — the same element a search of the cumulative
+            // array gives (searchsorted(cum, r * pot, side='left'), clipped).  One barrier instead of five.
+            g.csum[tid] = (unsigned long long)chunk_sum;
+            g.sync();
+            const int E = (gsz + RHCCQ_WARP_SIZE - 1) / RHCCQ_WARP_SIZE;     // chunk sums per lane
+            for (int t = RHCCQ_WARP; t < T; t += RHCCQ_NWARPS) {
+                const double rv = __dmul_rn(rng[ri + t], (double)pot);
+                unsigned long long loc = 0;
+                for (int e = 0; e < E; ++e) { const int ix = RHCCQ_LANE * E + e; if (ix < gsz) loc += g.csum[ix]; }
+                const unsigned long long incl = rhccq_warp_incl_scan_u64(loc);
+                const unsigned m = rhccq_ballot((double)incl >= rv);
+                int found = n - 1;                                  // beyond the total: clipped
+                if (m != 0u) {
+                    const int L = __ffs((int)m) - 1;
+                    unsigned long long pre = rhccq_shfl(incl - loc, L);
+                    int cix = L * E;
+                    for (int e = 0; e < E; ++e) {                   // the chunk inside lane L's share (warp-uniform walk)
+                        const int ix = L * E + e;
+                        if (ix >= gsz) break;
+                        const unsigned long long nx = pre + g.csum[ix];
+                        cix = ix;
+                        if ((double)nx >= rv) break;
+                        pre = nx;
+                    }
+                    const int j0 = cix * per < n ? cix * per : n, j1 = j0 + per < n ? j0 + per : n;
+                    for (int base = j0; base < j1; base += RHCCQ_WARP_SIZE) {
+                        const int j = base + RHCCQ_LANE;
+                        const unsigned long long inc = rhccq_warp_incl_scan_u64(j < j1 ? (unsigned long long)closest[j] : 0ull);
+                        const unsigned mm = rhccq_ballot(j < j1 && (double)(pre + inc) >= rv);
+                        if (mm != 0u) { found = base + __ffs((int)mm) - 1; break; }
+                        pre += rhccq_shfl(inc, RHCCQ_WARP_SIZE - 1);
+                    }
+                }
+                if (RHCCQ_LANE == 0) C.cand[t] = found < n - 1 ? found : n - 1;
             }
-            C.cand[t] = l < n - 1 ? l : n - 1;
+            g.sync();
+        } else {
+            // inclusive cumulative sum of closest (exact integers)
+            cum_t total;
+            cum_t run = g.template excl_scan<cum_t>(chunk_sum, &total);
+            for (int j = c_lo; j < c_hi; ++j) { run += closest[j]; cum[j] = run; }
+            g.sync();
+            // candidates: searchsorted(cum, r * pot, side='left'), clipped
+            for (int t = tid; t < T; t += gsz) {
+                const double rv = __dmul_rn(rng[ri + t], (double)pot);
+                int l = 0, h = n;                                   // first j with cum[j] >= rv
+                while (l < h) {
+                    const int mid = (l + h) >> 1;
+                    if ((double)cum[mid] < rv) l = mid + 1; else h = mid;
+                }
+                C.cand[t] = l < n - 1 ? l : n - 1;
+            }
+            g.sync();
         }
-        g.sync();
         ri += T;
         uint32_t xc[RHCCQ_KM_MAXT];
 #pragma unroll
@@ -860,7 +917,8 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     RHCCQ_PROF(0);                                                 // prologue
     // ---- level-synchronous splitting
     rhccq_grp_cta gc; gc.sll = s_ll;
-    rhccq_grp_warp gw;
+    gc.csum = reinterpret_cast<unsigned long long*>(poff);         // the partition table is idle during a seeding (8 B x threads fit)
+    rhccq_grp_warp gw; gw.csum = nullptr;
     int head = 0;
     while (true) {
         __syncthreads();
