@@ -104,6 +104,7 @@ static inline unsigned rhccq_ballot(int pred) { return pred ? 1u : 0u; }
 static inline int rhccq_any(int pred) { return pred; }
 template <class T> static inline T rhccq_shfl(T v, int) { return v; }
 template <class T> static inline T rhccq_shfl_xor(T v, int) { return v; }
+static inline unsigned rhccq_lanemask_lt() { return 0u; }
 #else
 #define RHCCQ_LANE ((int)(threadIdx.x & 31))
 #define RHCCQ_WARP ((int)(threadIdx.x >> 5))
@@ -113,6 +114,7 @@ __device__ __forceinline__ unsigned rhccq_ballot(int pred) { return __ballot_syn
 __device__ __forceinline__ int rhccq_any(int pred) { return __any_sync(0xffffffffu, pred); }
 template <class T> __device__ __forceinline__ T rhccq_shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 template <class T> __device__ __forceinline__ T rhccq_shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ unsigned rhccq_lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
 #endif
 
 #define RHCCQ_PAR_FOR(i, n) for (int i = (int)threadIdx.x; i < (int)(n); i += (int)blockDim.x)

@@ -59,22 +59,47 @@ __device__ void rhccq_unique_problem(int p, const uint8_t* __restrict__ img, con
     int* rank = cv.take<int>(np2cap);
     if (threadIdx.x == 0) { s_nb = 0; s_valid = 0; s_black = 0; s_best = ~0ull; s_repl = 0u; }
     __syncthreads();
-    // pass A: collect the non-black colours of the segment
-    RHCCQ_PAR_FOR(q, npx) {
-        const int r = r0 + q / w, c = c0 + q % w;
-        const size_t pos = plane + (size_t)r * W + c;
-        if (seg != nullptr && sid != 0 && seg[pos] != sid) continue;
-        const uint8_t* px = img + 3 * (iplane + (size_t)r * W + c);
-        const uint32_t key = rhccq_pack_rgb(px[0], px[1], px[2]);
-        atomicAdd(&s_valid, 1);
-        if (key == 0u) { atomicAdd(&s_black, 1); continue; }
-        const int slot = atomicAdd(&s_nb, 1);
-        if (slot < cap) buf[slot] = key;
-        if (repaint_black) {
-            // "nearest" colour to black = smallest norm, first in raster order (subregions.py:406-416)
-            const unsigned long long cand = ((unsigned long long)rhccq_d2(key, 0u) << 32) | (unsigned)q;
-            atomicMin(&s_best, cand);
+    // pass A: collect the non-black colours of the segment.  The three counters are bumped once per warp
+    // (ballot + popcount) and the repaint candidate is reduced in registers first: per-pixel atomics on four
+    // shared addresses were the bulk of this kernel's time.
+    unsigned long long best_local = ~0ull;
+    for (int q = (int)threadIdx.x; q - RHCCQ_LANE < npx; q += (int)blockDim.x) {          // warp-uniform trip count
+        bool valid = q < npx;
+        uint32_t key = 0u;
+        if (valid) {
+            const int r = r0 + q / w, c = c0 + q % w;
+            const size_t pos = plane + (size_t)r * W + c;
+            if (seg != nullptr && sid != 0 && seg[pos] != sid) valid = false;
+            else {
+                const uint8_t* px = img + 3 * (iplane + (size_t)r * W + c);
+                key = rhccq_pack_rgb(px[0], px[1], px[2]);
+            }
         }
+        const bool nonblack = valid && key != 0u;
+        const unsigned mv = rhccq_ballot(valid), mnb = rhccq_ballot(nonblack);
+        int base = 0;
+        if (RHCCQ_LANE == 0) {
+            if (mnb) base = atomicAdd(&s_nb, __popc(mnb));
+            if (mv) atomicAdd(&s_valid, __popc(mv));
+            if (mv & ~mnb) atomicAdd(&s_black, __popc(mv & ~mnb));
+        }
+        base = rhccq_shfl(base, 0);
+        if (nonblack) {
+            const int slot = base + __popc(mnb & rhccq_lanemask_lt());
+            if (slot < cap) buf[slot] = key;
+            if (repaint_black) {
+                // "nearest" colour to black = smallest norm, first in raster order (subregions.py:406-416)
+                const unsigned long long cand = ((unsigned long long)rhccq_d2(key, 0u) << 32) | (unsigned)q;
+                best_local = cand < best_local ? cand : best_local;
+            }
+        }
+    }
+    if (repaint_black) {
+        for (int d = RHCCQ_WARP_SIZE >> 1; d > 0; d >>= 1) {
+            const unsigned long long o = rhccq_shfl_xor(best_local, d);
+            best_local = o < best_local ? o : best_local;
+        }
+        if (RHCCQ_LANE == 0 && best_local != ~0ull) atomicMin(&s_best, best_local);
     }
     __syncthreads();
     const int nb = s_nb, nvalid = s_valid, nblack = s_black;

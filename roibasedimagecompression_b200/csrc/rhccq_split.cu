@@ -38,6 +38,9 @@ __device__ unsigned long long rhccq_split_prof[8];
 #define RHCCQ_PROF(slot) do {} while (0)
 #endif
 
+#ifndef RHCCQ_PRUNE_MIN_WORK
+#define RHCCQ_PRUNE_MIN_WORK 20000     // n * k from which the pruned E step pays for its extra pass
+#endif
 #define RHCCQ_SPLIT_THREADS 256
 #define RHCCQ_KM_MAXT 12               // 2 + int(log(k)) for k < 22027
 #define RHCCQ_KC 128                   // centres of a CTA-level K-Means kept in shared memory
@@ -467,7 +470,7 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
         // evaluating every centre; the other points (about 40 %) are compacted into a worklist so that the
         // warps of the full loop stay full.  Worth its extra pass only for large problems.
         int changed = 0;
-        const bool prune = it > 0 && !recount && C.wl != nullptr && (long long)n * k >= 200000;
+        const bool prune = it > 0 && !recount && C.wl != nullptr && (long long)n * k >= RHCCQ_PRUNE_MIN_WORK;
         uint32_t* wl = reinterpret_cast<uint32_t*>(closest);       // dead after the seeding; positions of this range
         if (prune) {
             g.sync();                                               // slower threads may still be summing the last shift from term
@@ -485,11 +488,19 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
             }
             if (tid == 0) *C.wl = 0;
             g.sync();
-            for (int j = tid; j < n; j += gsz) {
-                const uint32_t c = x[j];
-                const int a = (int)label[j];
-                const double u = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c), (double)rhccq_key_b(c), cen + 3 * a);
-                if (!(u < C.term[a])) wl[atomicAdd(C.wl, 1)] = (uint32_t)j;
+            for (int j = tid; j - RHCCQ_LANE < n; j += gsz) {          // warp-uniform trip count
+                bool push = false;
+                if (j < n) {
+                    const uint32_t c = x[j];
+                    const int a = (int)label[j];
+                    const double u = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c), (double)rhccq_key_b(c), cen + 3 * a);
+                    push = !(u < C.term[a]);
+                }
+                const unsigned m = rhccq_ballot(push);                 // one counter bump per warp
+                int base = 0;
+                if (RHCCQ_LANE == 0 && m) base = atomicAdd(C.wl, __popc(m));
+                base = rhccq_shfl(base, 0);
+                if (push) wl[base + __popc(m & rhccq_lanemask_lt())] = (uint32_t)j;
             }
             g.sync();
         }
