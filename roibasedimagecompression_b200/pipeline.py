@@ -282,7 +282,11 @@ class HostEncoder:
         self.h_idx = [torch.empty((B, H, W), dtype=torch.int16, pin_memory=self.cuda) for _ in range(2)]
         self.h2d_bytes = self.d_img[0].numel() + 4 * self.d_lab[0].numel()
         self.d2h_bytes = 2 * self.h_idx[0].numel()
+        self.h_off = [torch.empty((B + 1,), dtype=torch.int32, pin_memory=self.cuda) for _ in range(2)]
+        self.h_cnt = [torch.empty((B,), dtype=torch.int32, pin_memory=self.cuda) for _ in range(2)]
+        self.h_keys = [torch.empty((B * 4096,), dtype=torch.int32, pin_memory=self.cuda) for _ in range(2)]   # palettes are ~10^2 rows
         if self.cuda:
+            self.out_stream = torch.cuda.Stream(device=be.device)
             self.copy_stream = torch.cuda.Stream(device=be.device)
             self.ev_ready = [torch.cuda.Event() for _ in range(2)]
             self.ev_free = [torch.cuda.Event() for _ in range(2)]
@@ -298,23 +302,48 @@ class HostEncoder:
             self.d_lab[slot].copy_(labels_host, non_blocking=True)
             self.ev_ready[slot].record(self.copy_stream)
 
-    def _encode_slot(self, slot: int):
+    def _launch(self, slot: int):
+        """Queue the encode of the batch in `slot` and the device->host copies of its results (on the copy-out
+        stream, so that they overlap the next batch's kernels).  Returns the handle `_finish` needs."""
+        dev = self.be.device
         if self.cuda:
-            torch.cuda.current_stream(self.be.device).wait_event(self.ev_ready[slot])
+            torch.cuda.current_stream(dev).wait_event(self.ev_ready[slot])
         res = encode_batch(self.be, self.d_img[slot], self.d_lab[slot], self.table)
-        if self.cuda:
-            self.ev_free[slot].record(torch.cuda.current_stream(self.be.device))
-        self.h_idx[slot].copy_(res.indices, non_blocking=True)
-        off = res.palette_off.cpu().numpy()                       # synchronises the stream
-        cnt = res.palette_cnt.cpu().numpy()
-        ops.check_counts("final palette", torch.from_numpy(cnt))
+        B = self.table.B
+        if not self.cuda:
+            self.h_idx[slot].copy_(res.indices)
+            return slot, res, res.palette_off.clone(), res.palette_cnt.clone(), res.palette_keys, None
+        cur = torch.cuda.current_stream(dev)
+        self.ev_free[slot].record(cur)
+        done = torch.cuda.Event(); done.record(cur)
+        with torch.cuda.stream(self.out_stream):
+            self.out_stream.wait_event(done)
+            self.h_idx[slot].copy_(res.indices, non_blocking=True)
+            self.h_off[slot].copy_(res.palette_off[:B + 1], non_blocking=True)
+            self.h_cnt[slot].copy_(res.palette_cnt[:B], non_blocking=True)
+            n_cap = min(res.palette_keys.numel(), self.h_keys[slot].numel())
+            self.h_keys[slot][:n_cap].copy_(res.palette_keys[:n_cap], non_blocking=True)
+            out_ev = torch.cuda.Event(); out_ev.record(self.out_stream)
+        return slot, res, self.h_off[slot], self.h_cnt[slot], self.h_keys[slot], out_ev
+
+    def _finish(self, handle):
+        slot, res, off_t, cnt_t, keys_t, out_ev = handle
+        if out_ev is not None:
+            out_ev.synchronize()
+        off, cnt = off_t.cpu().numpy(), cnt_t.cpu().numpy()
+        ops.check_counts("final palette", torch.from_numpy(np.ascontiguousarray(cnt)))
         n_keys = int(off[len(cnt) - 1] + cnt[-1]) if len(cnt) else 0
-        keys = res.palette_keys[:n_keys].cpu().numpy().astype(np.uint32)
+        if n_keys > keys_t.numel():                                 # more palette rows than the staging buffer: fetch directly
+            keys_t = res.palette_keys[:n_keys].cpu()
+        keys = keys_t[:n_keys].cpu().numpy().astype(np.uint32)
         pals = []
         for b in range(len(cnt)):
             k = keys[off[b]:off[b] + cnt[b]]
             pals.append(np.stack([(k >> 16) & 255, (k >> 8) & 255, k & 255], axis=-1).astype(np.uint8))
         return pals, self.h_idx[slot].numpy().view(np.uint16)
+
+    def _encode_slot(self, slot: int):
+        return self._finish(self._launch(slot))
 
     def encode(self, images_host: torch.Tensor, labels_host: torch.Tensor):
         """images uint8 [B,H,W,3], labels int32 [K,B,H,W] (pinned host tensors for full copy speed).
@@ -324,17 +353,25 @@ class HostEncoder:
 
     def encode_many(self, batches):
         """Generator over (palettes, indices) for an iterable of (images_host, labels_host) batches of the
-        table's shape.  The result of a batch stays valid until two more batches have been produced."""
+        table's shape, in order.  Three things overlap: the host->device copy of batch i+1, the encode of batch
+        i, and the device->host copy of batch i-1's results; a result stays valid until two more batches have
+        been produced."""
         it = iter(batches)
         cur = next(it, None)
         if cur is None:
             return
         self._upload(0, cur[0], cur[1], first_use=True)
         i = 0
+        pending = None
         while cur is not None:
             nxt = next(it, None)
             if nxt is not None:
                 self._upload((i + 1) & 1, nxt[0], nxt[1], first_use=(i == 0))
-            yield self._encode_slot(i & 1)
+            handle = self._launch(i & 1)                            # blocks the host until this batch's stage 1 is sized
+            if pending is not None:
+                yield self._finish(pending)                         # batch i-1: its copies ran beside batch i's kernels
+            pending = handle
             cur = nxt
             i += 1
+        if pending is not None:
+            yield self._finish(pending)

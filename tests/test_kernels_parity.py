@@ -360,3 +360,25 @@ def test_pipeline_one_huge_segment_and_an_empty_class(backend):
     pal, idx = _encode_device(backend, img, roi, [])
     assert np.array_equal(pal, want["palette"])
     assert np.array_equal(idx, want["indices"])
+
+
+def test_host_encoder_streaming_equals_single_batches(backend):
+    """HostEncoder.encode_many (upload of batch i+1, encode of batch i and download of batch i-1 overlap)
+    returns, in order, exactly what encode returns batch by batch."""
+    be = backend
+    B, H, W = 2, 64, 96
+    tab, lab = pipeline.table_from_tiles(B, H, W, 32)
+    labs = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(lab, (2, B, H, W))))
+    batches = [torch.from_numpy(np.stack([synth(H, W, 10 * s + i) for i in range(B)])) for s in range(4)]
+    if be.device.type == "cuda":
+        labs, batches = labs.pin_memory(), [b.pin_memory() for b in batches]
+    enc = pipeline.HostEncoder(be, tab)
+    outs = [(p, i.copy()) for p, i in enc.encode_many([(b, labs) for b in batches])]
+    assert len(outs) == 4
+    for s, (p, i) in enumerate(outs):
+        p2, i2 = enc.encode(batches[s], labs)
+        assert all(np.array_equal(a, b) for a, b in zip(p, p2)) and np.array_equal(i, i2), s
+    roi, non = tile_regions(H, W, 32)
+    want = O.encode_image(batches[3][1].numpy(), roi, non)
+    assert np.array_equal(outs[3][0][1], want["palette"])
+    assert np.array_equal(outs[3][1][1].reshape(-1).astype(np.int64), want["indices"])
