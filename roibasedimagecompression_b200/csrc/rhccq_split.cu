@@ -1036,7 +1036,18 @@ rhccq_k_palette_split(rhccq_palette_batch B, const int* __restrict__ labels, con
     unsigned char* row_base = ROWS_SMEM ? dyn + small_bytes : slice;    // compile-time: keeps the address space known
     unsigned char* cent_s = dyn + small_bytes + (ROWS_SMEM ? row_bytes : 0);
     unsigned char* cent_g = slice ? slice + row_bytes : nullptr;
-    for (int p = blockIdx.x; p < B.n_problems; p += gridDim.x) {
+    // problems are handed out by a grid-wide cursor when there is one (palettes take unequal time); it lives in
+    // the row area of workspace slice 0, which is unused while the rows are in shared memory
+    int* cursor = (ROWS_SMEM && gws) ? reinterpret_cast<int*>(gws) : nullptr;
+    __shared__ int s_next;
+    for (int p = blockIdx.x; ; p += gridDim.x) {
+        if (cursor) {
+            if (threadIdx.x == 0) s_next = atomicAdd(cursor, 1);
+            __syncthreads();
+            p = s_next;
+            __syncthreads();
+        }
+        if (p >= B.n_problems) break;
         rhccq_palette_split_problem<Cfg>(B, p, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves, max_rows,
                                          row_base, dyn, cent_s, kc_s, cent_g, max_rows);
         __syncthreads();
@@ -1081,6 +1092,13 @@ static int rhccq_launch_split_cfg(const rhccq_palette_batch& B, const int* label
     if (!rows_in_smem) { const int cap = rhccq_sm_count() * 2; if (grid > cap) grid = cap; }
     const size_t smem = small + (rows_in_smem ? row_bytes : 0) + cent_s;
     unsigned char* gws = slices > 0 ? ws.ws : nullptr;
+    if (rows_in_smem && gws) {                                     // the problem cursor (see the kernel)
+#ifdef RHCCQ_HOST_EMU
+        memset(gws, 0, 4);
+#else
+        cudaMemsetAsync(gws, 0, 4, (cudaStream_t)stream);
+#endif
+    }
 #define RHCCQ_SPLIT_GO(ROWS, THREADS)                                                                                  \
     do {                                                                                                               \
         if (rhccq_smem_optin((const void*)rhccq_k_palette_split<Cfg, ROWS, THREADS>, smem) != 0) return -1;            \
