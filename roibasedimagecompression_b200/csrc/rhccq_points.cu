@@ -780,22 +780,50 @@ __device__ __forceinline__ int rhccq_lt_build_offsets(int2* offs, int R, int thr
     return n;
 }
 
+// one float32 point -> packed colour, checking that it is pixel (x, y) of an 8-bit image
+__device__ __forceinline__ uint32_t rhccq_lt_pack_point(float fx, float fy, float r, float g, float b, int x, int y, int* bad) {
+    const int ir = (int)r, ig = (int)g, ib = (int)b;
+    if (fx != (float)x || fy != (float)y || (float)ir != r || (float)ig != g || (float)ib != b ||
+        (unsigned)ir > 255u || (unsigned)ig > 255u || (unsigned)ib > 255u) *bad = 1;
+    return rhccq_pack_rgb((unsigned)ir & 255u, (unsigned)ig & 255u, (unsigned)ib & 255u);
+}
+
 // tile of packed colours (top byte: 0xFF outside the image, bit 24 = core) with a halo of R pixels
 template <int SRC>   // 0: float32 points [H*W,5], 1: uint8 image [H,W,3], 2: packed uint32 [H*W]
 __device__ __forceinline__ void rhccq_lt_load_tile(const void* src, const rhccq_lt_args& A, int ty0, int tx0, uint32_t* tile,
                                                    int tw, int th, int* bad) {
+#ifndef RHCCQ_HOST_EMU
+    // float points, interior of the tile: four pixels = 80 bytes = five 16-byte loads, contiguous across the lanes
+    const bool vec = SRC == 0 && (A.W & 3) == 0;
+    if (vec) {
+        const int own_h = th - 2 * A.R, quads = RHCCQ_LT_W / 4;
+        RHCCQ_PAR_FOR(t, own_h * quads) {
+            const int ly = t / quads, lx = (t % quads) * 4;
+            const int y = ty0 + ly, x = tx0 + lx;
+            if (y >= A.H || x >= A.W) continue;                        // W % 4 == 0: a quad is inside or outside as a whole
+            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + ((size_t)y * A.W + x) * 5);
+            const float4 a = p[0], b = p[1], c = p[2], d = p[3], e = p[4];
+            uint32_t* o = tile + (ly + A.R) * tw + lx + A.R;
+            o[0] = rhccq_lt_pack_point(a.x, a.y, a.z, a.w, b.x, x, y, bad);
+            o[1] = rhccq_lt_pack_point(b.y, b.z, b.w, c.x, c.y, x + 1, y, bad);
+            o[2] = rhccq_lt_pack_point(c.z, c.w, d.x, d.y, d.z, x + 2, y, bad);
+            o[3] = rhccq_lt_pack_point(d.w, e.x, e.y, e.z, e.w, x + 3, y, bad);
+        }
+    }
+#else
+    const bool vec = false;
+#endif
     RHCCQ_PAR_FOR(t, tw * th) {
-        const int y = ty0 - A.R + t / tw, x = tx0 - A.R + t % tw;
+        const int ty = t / tw, tx = t % tw;
+        const int y = ty0 - A.R + ty, x = tx0 - A.R + tx;
+        const bool inside = y >= 0 && y < A.H && x >= 0 && x < A.W;
+        if (vec && inside && ty >= A.R && ty < th - A.R && tx >= A.R && tx < A.R + RHCCQ_LT_W) continue;   // loaded above
         uint32_t v = RHCCQ_LT_INVALID;
-        if (y >= 0 && y < A.H && x >= 0 && x < A.W) {
+        if (inside) {
             const size_t i = (size_t)y * A.W + x;
             if (SRC == 0) {
                 const float* p = reinterpret_cast<const float*>(src) + i * 5;
-                const float fx = p[0], fy = p[1], r = p[2], g = p[3], b = p[4];
-                const int ir = (int)r, ig = (int)g, ib = (int)b;
-                if (fx != (float)x || fy != (float)y || (float)ir != r || (float)ig != g || (float)ib != b ||
-                    (unsigned)ir > 255u || (unsigned)ig > 255u || (unsigned)ib > 255u) *bad = 1;
-                v = rhccq_pack_rgb((unsigned)ir & 255u, (unsigned)ig & 255u, (unsigned)ib & 255u);
+                v = rhccq_lt_pack_point(p[0], p[1], p[2], p[3], p[4], x, y, bad);
             } else if (SRC == 1) {
                 const uint8_t* p = reinterpret_cast<const uint8_t*>(src) + i * 3;
                 v = rhccq_pack_rgb(p[0], p[1], p[2]);
@@ -918,6 +946,81 @@ rhccq_k_lt_sweep(const void* __restrict__ src, rhccq_lt_args A, int* __restrict_
     if (MODE == 0 && SRC == 0 && threadIdx.x == 0 && s_bad) *status = 1;
 }
 
+// Count pass for small radii (R <= 4, the usual eps 1..4.9): every thread owns 8 horizontally adjacent pixels.
+// For a stencil row dy it loads the 8 + 2R tile values under them once and slides the dx offsets over that
+// register window, so a candidate costs 4 instructions and a quarter of a shared-memory load.
+template <int SRC, int RT>
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_lt_count_rows(const void* __restrict__ src, rhccq_lt_args A, int* __restrict__ count, uint32_t* __restrict__ packed,
+                      uint8_t* __restrict__ core, int* __restrict__ status) {
+    RHCCQ_DYN_SMEM(dyn);
+    __shared__ int s_bad;
+    const int TH = 32, SW = 8;
+    const int tw = RHCCQ_LT_W + 2 * RT, th = TH + 2 * RT;
+    uint32_t* tile = reinterpret_cast<uint32_t*>(dyn);
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    const int tiles_x = (A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W, tiles_y = (A.H + TH - 1) / TH;
+    for (int tI = blockIdx.x; tI < tiles_x * tiles_y; tI += gridDim.x) {
+        const int ty0 = (tI / tiles_x) * TH, tx0 = (tI % tiles_x) * RHCCQ_LT_W;
+        rhccq_lt_load_tile<SRC>(src, A, ty0, tx0, tile, tw, th, &s_bad);
+        __syncthreads();
+        RHCCQ_PAR_FOR(t, (RHCCQ_LT_W / SW) * TH) {
+            const int ly = t / (RHCCQ_LT_W / SW), lx0 = (t % (RHCCQ_LT_W / SW)) * SW;
+            uint32_t c[SW];
+            int acc[SW];
+#pragma unroll
+            for (int u = 0; u < SW; ++u) { c[u] = tile[(ly + RT) * tw + lx0 + RT + u] & 0x00ffffffu; acc[u] = 0; }
+#pragma unroll
+            for (int dy = -RT; dy <= RT; ++dy) {
+                if (dy * dy > A.thr) continue;                         // (block-uniform)
+                uint32_t win[SW + 2 * RT];
+                const uint32_t* row = tile + (ly + RT + dy) * tw + lx0;
+#pragma unroll
+                for (int j = 0; j < SW + 2 * RT; ++j) win[j] = row[j];
+#pragma unroll
+                for (int dx = -RT; dx <= RT; ++dx) {
+                    const int budget = A.thr - dy * dy - dx * dx;
+                    if (budget < 0) continue;
+#pragma unroll
+                    for (int u = 0; u < SW; ++u)                        // 0xFF top byte (outside the image): never within
+                        acc[u] += (int)((unsigned)rhccq_d2(c[u], win[u + dx + RT]) <= (unsigned)budget);
+                }
+            }
+            const int y = ty0 + ly, x0 = tx0 + lx0;
+            if (y >= A.H || x0 >= A.W) continue;
+            uint32_t pk[SW];
+            unsigned long long cbits = 0ull;
+#pragma unroll
+            for (int u = 0; u < SW; ++u) {
+                const int is_core = acc[u] >= A.min_pts;
+                pk[u] = c[u] | (is_core ? RHCCQ_LT_CORE : 0u);
+                cbits |= (unsigned long long)is_core << (8 * u);
+            }
+            const size_t id0 = (size_t)y * A.W + x0;
+#ifndef RHCCQ_HOST_EMU
+            if ((A.W & 7) == 0 && x0 + SW <= A.W) {                    // 8 adjacent pixels: 32-byte aligned vector stores
+                reinterpret_cast<int4*>(count + id0)[0] = make_int4(acc[0], acc[1], acc[2], acc[3]);
+                reinterpret_cast<int4*>(count + id0)[1] = make_int4(acc[4], acc[5], acc[6], acc[7]);
+                reinterpret_cast<uint4*>(packed + id0)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                reinterpret_cast<uint4*>(packed + id0)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                *reinterpret_cast<unsigned long long*>(core + id0) = cbits;
+                continue;
+            }
+#endif
+#pragma unroll
+            for (int u = 0; u < SW; ++u) {
+                if (x0 + u >= A.W) break;
+                count[id0 + u] = acc[u];
+                core[id0 + u] = (uint8_t)((cbits >> (8 * u)) & 1ull);
+                packed[id0 + u] = pk[u];
+            }
+        }
+        __syncthreads();
+    }
+    if (SRC == 0 && threadIdx.x == 0 && s_bad) *status = 1;
+}
+
 #define RHCCQ_LT_H 16         // tile height of the count and attachment passes
 #define RHCCQ_LT_UH 32        // tile height of the union passes: fewer edges cross tile borders
 
@@ -985,6 +1088,18 @@ int rhccq_dbscan_lattice_count(const void* src, int src_kind, int H, int W, doub
 #endif
     const size_t csmem = rhccq_lt_smem(A, RHCCQ_LT_UH);
     const int cgrid = rhccq_lt_grid(A, RHCCQ_LT_UH);
+#define RHCCQ_LT_ROWS(SRCK, RT)                                                                                      \
+    RHCCQ_LAUNCH((rhccq_k_lt_count_rows<SRCK, RT>), cgrid, RHCCQ_PT_THREADS, csmem, (cudaStream_t)stream, src, A, count,   \
+                 L.packed, core, status)
+    if (A.R >= 1 && A.R <= 4) {                                    // sliding-window form
+        if (src_kind == 0) {
+            if (A.R == 1) RHCCQ_LT_ROWS(0, 1); else if (A.R == 2) RHCCQ_LT_ROWS(0, 2); else if (A.R == 3) RHCCQ_LT_ROWS(0, 3); else RHCCQ_LT_ROWS(0, 4);
+        } else {
+            if (A.R == 1) RHCCQ_LT_ROWS(1, 1); else if (A.R == 2) RHCCQ_LT_ROWS(1, 2); else if (A.R == 3) RHCCQ_LT_ROWS(1, 3); else RHCCQ_LT_ROWS(1, 4);
+        }
+        return 0;
+    }
+#undef RHCCQ_LT_ROWS
     if (src_kind == 0) {
         if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<0, 0, RHCCQ_LT_UH>, csmem) != 0) return -1;
         RHCCQ_LAUNCH((rhccq_k_lt_sweep<0, 0, RHCCQ_LT_UH>), cgrid, RHCCQ_PT_THREADS, csmem, (cudaStream_t)stream, src, A, count, L.packed, core, L.parent, L.rootlab, status);
