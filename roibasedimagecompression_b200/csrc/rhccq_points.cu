@@ -903,7 +903,7 @@ rhccq_k_lt_sweep(const void* __restrict__ src, rhccq_lt_args A, int* __restrict_
                 const int id = y * A.W + x;
                 const bool me_core = (me & RHCCQ_LT_CORE) != 0u;
                 if ((MODE == 2) == me_core) continue;                   // unions: core pixels; attachment: the others
-                int best = 0x7fffffff, my_root = id;
+                int best = 0x7fffffff, my_root = MODE == 1 ? t : id;
                 for (int o = 0; o < n_off; ++o) {
                     const int2 e = offs[o];
                     const int dy = (e.x >> 8) - 64, dx = (e.x & 255) - 64;
@@ -914,7 +914,13 @@ rhccq_k_lt_sweep(const void* __restrict__ src, rhccq_lt_args A, int* __restrict_
                     if ((nb >> 24) != 1u) continue;                     // outside the image, or not core
                     if ((unsigned)rhccq_d2(c, nb & 0x00ffffffu) > (unsigned)e.y) continue;
                     if (MODE == 1) {
-                        rhccq_pt_union(lpar, t + dy * RHCCQ_LT_W + dx, t);
+                        // one hop tells when the neighbour already hangs under my root (the usual case once a
+                        // dense patch is linked); only otherwise walk both trees and link
+                        const int nl = t + dy * RHCCQ_LT_W + dx;
+                        if (((volatile int*)lpar)[nl] != my_root) {
+                            rhccq_pt_union(lpar, nl, t);
+                            my_root = rhccq_pt_find(lpar, t);
+                        }
                     } else if (MODE == 3) {
                         const int nid = id + dy * A.W + dx;
                         if (((volatile int*)parent)[nid] != my_root) {
