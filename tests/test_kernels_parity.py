@@ -382,3 +382,30 @@ def test_host_encoder_streaming_equals_single_batches(backend):
     want = O.encode_image(batches[3][1].numpy(), roi, non)
     assert np.array_equal(outs[3][0][1], want["palette"])
     assert np.array_equal(outs[3][1][1].reshape(-1).astype(np.int64), want["indices"])
+
+
+def _oracle_frame(args):
+    img, tile = args
+    roi, non = tile_regions(img.shape[0], img.shape[1], tile)
+    r = O.encode_image(img, roi, non)
+    return r["palette"], r["indices"]
+
+
+@pytest.mark.gpu
+def test_full_hd_batch_equals_oracle_frame_by_frame():
+    """BASELINE.json configs[1] at reduced batch: four 1920x1080 frames in one device batch, every frame
+    compared with the oracle (run in parallel processes), palettes and index planes bit for bit."""
+    import multiprocessing as mp
+    from roibasedimagecompression_b200._lib import lib
+    be = lib()
+    B, H, W, tile = 4, 1080, 1920, 64
+    imgs = np.stack([synth(H, W, 777 + i) for i in range(B)])
+    tab, lab = pipeline.table_from_tiles(B, H, W, tile)
+    labels = np.ascontiguousarray(np.broadcast_to(lab, (2, B, H, W)))
+    res = pipeline.encode_batch(be, torch.from_numpy(imgs).cuda(), torch.from_numpy(labels).cuda(), tab)
+    pipeline.finish_checks(res)
+    with mp.get_context("fork").Pool(B) as pool:
+        want = pool.map(_oracle_frame, [(imgs[b], tile) for b in range(B)])
+    for b in range(B):
+        assert np.array_equal(res.palette(b), want[b][0]), b
+        assert np.array_equal(res.index_image(b).reshape(-1).astype(np.int64), want[b][1]), b
