@@ -846,23 +846,44 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     // ---- entries that need no K-Means.  csize / crank live in the (still unused) seeding arrays.
     int* csize = reinterpret_cast<int*>(W.A.x);
     int* crank = reinterpret_cast<int*>(W.A.closest);
-    // black rows first, one entry each, in row order (clustering.py:253-255)
-    RHCCQ_PAR_FOR(i, n) { crank[i] = (keys[i] == 0u) ? 1 : 0; csize[i] = 0; }
+    // One look at the rows: is there a black row, a noise row, and how far do the cluster labels reach.  The
+    // usual palette has neither black nor noise and a single cluster (the eps radii of the reference chain
+    // whole palettes), so the scans below shrink to nothing.
+    int f_black = 0, f_noise = 0, l_max = -1;
+    RHCCQ_PAR_FOR(i, n) {
+        const int l = lab[i];
+        if (keys[i] == 0u) f_black = 1; else if (l == -1) f_noise = 1;
+        l_max = l > l_max ? l : l_max;
+    }
+    f_black = rhccq_block_or(f_black, s_scan);
+    f_noise = rhccq_block_or(f_noise, s_scan);
+    const int n_lab = rhccq_block_max<int>(l_max, s_scan) + 1;      // labels are 0 .. n_lab - 1 (n_lab <= n)
+    RHCCQ_PAR_FOR(l, n_lab) csize[l] = 0;
     __syncthreads();
-    const int n_black = rhccq_block_excl_scan_array<int>(crank, n, s_scan);
-    RHCCQ_PAR_FOR(i, n) if (keys[i] == 0u) lf[i] = crank[i];
+    // black rows first, one entry each, in row order (clustering.py:253-255)
+    int n_black = 0;
+    if (f_black) {
+        RHCCQ_PAR_FOR(i, n) crank[i] = (keys[i] == 0u) ? 1 : 0;
+        __syncthreads();
+        n_black = rhccq_block_excl_scan_array<int>(crank, n, s_scan);
+        RHCCQ_PAR_FOR(i, n) if (keys[i] == 0u) lf[i] = crank[i];
+        __syncthreads();
+    }
     // cluster sizes; labels are dense non-negative (a noise row would carry -1: one entry each, :258-264)
     RHCCQ_PAR_FOR(i, n) if (lab[i] >= 0) atomicAdd(&csize[lab[i]], 1);
     __syncthreads();
-    RHCCQ_PAR_FOR(i, n) crank[i] = (keys[i] != 0u && lab[i] == -1) ? 1 : 0;
-    __syncthreads();
-    const int n_noise = rhccq_block_excl_scan_array<int>(crank, n, s_scan);
-    RHCCQ_PAR_FOR(i, n) if (keys[i] != 0u && lab[i] == -1) lf[i] = n_black + crank[i];
-    __syncthreads();
+    int n_noise = 0;
+    if (f_noise) {
+        RHCCQ_PAR_FOR(i, n) crank[i] = (keys[i] != 0u && lab[i] == -1) ? 1 : 0;
+        __syncthreads();
+        n_noise = rhccq_block_excl_scan_array<int>(crank, n, s_scan);
+        RHCCQ_PAR_FOR(i, n) if (keys[i] != 0u && lab[i] == -1) lf[i] = n_black + crank[i];
+        __syncthreads();
+    }
     // small clusters in ascending label order (:273-310)
-    RHCCQ_PAR_FOR(l, n) crank[l] = (csize[l] > 0 && csize[l] <= mcpc) ? 1 : 0;
+    RHCCQ_PAR_FOR(l, n_lab) crank[l] = (csize[l] > 0 && csize[l] <= mcpc) ? 1 : 0;
     __syncthreads();
-    const int n_small = rhccq_block_excl_scan_array<int>(crank, n, s_scan);
+    const int n_small = rhccq_block_excl_scan_array<int>(crank, n_lab, s_scan);
     RHCCQ_PAR_FOR(i, n) {
         const int l = lab[i];
         if (l >= 0 && csize[l] <= mcpc) lf[i] = n_black + n_noise + crank[l];
@@ -870,13 +891,13 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     __syncthreads();
     // large clusters in ascending label order (:315-355): their members, in ascending row order, fill
     // consecutive ranges of the permutation; crank[l] <- first position of cluster l
-    RHCCQ_PAR_FOR(l, n) crank[l] = csize[l] > mcpc ? csize[l] : 0;
+    RHCCQ_PAR_FOR(l, n_lab) crank[l] = csize[l] > mcpc ? csize[l] : 0;
     __syncthreads();
-    const int n_members = rhccq_block_excl_scan_array<int>(crank, n, s_scan);
+    const int n_members = rhccq_block_excl_scan_array<int>(crank, n_lab, s_scan);
     if (threadIdx.x == 0) { s_tail = 0; s_err = 0; s_base = n_black + n_noise + n_small; }
     __syncthreads();
     // roots: a cluster of more than two colours is split (:745), a larger-than-allowed pair stays one entry
-    RHCCQ_PAR_FOR(l, n) {
+    RHCCQ_PAR_FOR(l, n_lab) {
         const int c = csize[l];
         if (c > mcpc) {
             const int slot = atomicAdd(&s_tail, 1);
@@ -893,7 +914,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
             int L = -1;
             // the cluster whose range starts at r_lo
             __shared__ int s_L;
-            RHCCQ_PAR_FOR(l, n) if (csize[l] > mcpc && crank[l] == r_lo) s_L = l;
+            RHCCQ_PAR_FOR(l, n_lab) if (csize[l] > mcpc && crank[l] == r_lo) s_L = l;
             __syncthreads();
             L = s_L;
             int* flag = reinterpret_cast<int*>(W.A.cum);             // n ints fit: cum_t is at least 4 bytes
