@@ -49,8 +49,8 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of the same command
 # (summaries under profiles/): (workload, entry point) -> (bytes, source)
 NCU_TRAFFIC = {
-    ("c2", "rhccq_palette_split"): (835103744 + 381782528, "profiles/r01_split_c2_v4.txt (the stage-1 launch)"),
-    ("c5l", "rhccq_dbscan_lattice_count"): (337112576 + 127552000, "profiles/r01_lattice_v1.txt"),
+    ("c2", "rhccq_palette_split"): (832561152 + 379788544, "profiles/r01_split_c2_v6.txt (the stage-1 launch)"),
+    ("c5l", "rhccq_dbscan_lattice_count"): (336087808 + 122899200, "profiles/r01_lattice_count_v2.txt"),
 }
 DBSCAN_BYTES_PER_POINT = 24       # 20 B read + 4 B written, both for the count kernel and the whole
 
