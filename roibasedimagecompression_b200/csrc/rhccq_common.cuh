@@ -20,6 +20,7 @@
 #include <math.h>
 struct rhccq_emu_dim3 { unsigned x, y, z; };
 struct int2 { int x, y; };
+struct uint4 { unsigned x, y, z, w; };
 extern rhccq_emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 extern unsigned char* rhccq_emu_dyn_smem;
 void rhccq_emu_prepare_smem(size_t bytes);

@@ -791,7 +791,8 @@ __device__ __forceinline__ uint32_t rhccq_lt_pack_point(float fx, float fy, floa
 // tile of packed colours (top byte: 0xFF outside the image, bit 24 = core) with a halo of R pixels
 template <int SRC>   // 0: float32 points [H*W,5], 1: uint8 image [H,W,3], 2: packed uint32 [H*W]
 __device__ __forceinline__ void rhccq_lt_load_tile(const void* src, const rhccq_lt_args& A, int ty0, int tx0, uint32_t* tile,
-                                                   int tw, int th, int* bad) {
+                                                   int tw, int th, int* bad, int pad = -1) {
+    if (pad < 0) pad = A.R;                                        // columns of halo on each side (rows: always A.R)
 #ifndef RHCCQ_HOST_EMU
     // float points, interior of the tile: four pixels = 80 bytes = five 16-byte loads, contiguous across the lanes
     const bool vec = SRC == 0 && (A.W & 3) == 0;
@@ -803,7 +804,7 @@ __device__ __forceinline__ void rhccq_lt_load_tile(const void* src, const rhccq_
             if (y >= A.H || x >= A.W) continue;                        // W % 4 == 0: a quad is inside or outside as a whole
             const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + ((size_t)y * A.W + x) * 5);
             const float4 a = p[0], b = p[1], c = p[2], d = p[3], e = p[4];
-            uint32_t* o = tile + (ly + A.R) * tw + lx + A.R;
+            uint32_t* o = tile + (ly + A.R) * tw + lx + pad;
             o[0] = rhccq_lt_pack_point(a.x, a.y, a.z, a.w, b.x, x, y, bad);
             o[1] = rhccq_lt_pack_point(b.y, b.z, b.w, c.x, c.y, x + 1, y, bad);
             o[2] = rhccq_lt_pack_point(c.z, c.w, d.x, d.y, d.z, x + 2, y, bad);
@@ -815,9 +816,9 @@ __device__ __forceinline__ void rhccq_lt_load_tile(const void* src, const rhccq_
 #endif
     RHCCQ_PAR_FOR(t, tw * th) {
         const int ty = t / tw, tx = t % tw;
-        const int y = ty0 - A.R + ty, x = tx0 - A.R + tx;
+        const int y = ty0 - A.R + ty, x = tx0 - pad + tx;
         const bool inside = y >= 0 && y < A.H && x >= 0 && x < A.W;
-        if (vec && inside && ty >= A.R && ty < th - A.R && tx >= A.R && tx < A.R + RHCCQ_LT_W) continue;   // loaded above
+        if (vec && inside && ty >= A.R && ty < th - A.R && tx >= pad && tx < pad + RHCCQ_LT_W) continue;   // loaded above
         uint32_t v = RHCCQ_LT_INVALID;
         if (inside) {
             const size_t i = (size_t)y * A.W + x;
@@ -953,79 +954,201 @@ rhccq_k_lt_sweep(const void* __restrict__ src, rhccq_lt_args A, int* __restrict_
 }
 
 // Count pass for small radii (R <= 4, the usual eps 1..4.9): every thread owns 8 horizontally adjacent pixels.
-// For a stencil row dy it loads the 8 + 2R tile values under them once and slides the dx offsets over that
-// register window, so a candidate costs 4 instructions and a quarter of a shared-memory load.
+// The tile has RHCCQ_LTT_PAD halo columns on each side whatever the radius, so that a thread's window of a
+// stencil row (its 8 pixels + 4 either side) is four aligned 16-byte shared-memory loads; the dx offsets slide
+// over that register window. A candidate costs three instructions: byte-wise |difference|, a dot product that
+// starts from -(budget + 1), and the sign bit of the result added to the count.
+#define RHCCQ_LTT_PAD 4
+#define RHCCQ_LTT_TW (RHCCQ_LT_W + 2 * RHCCQ_LTT_PAD)
+#define RHCCQ_LTT_TH 32
+
+template <int RT, int THR = -1>       // THR >= 0: the threshold is a compile-time constant (no per-offset branches)
+__device__ __forceinline__ void rhccq_lt_stencil8(const uint32_t* tile, int ly, int lx0, int thr_rt, uint32_t (&c)[8], int (&acc)[8]) {
+    const int TW = RHCCQ_LTT_TW;
+    const int thr = THR >= 0 ? THR : thr_rt;
+    {
+        const uint4* ctr = reinterpret_cast<const uint4*>(tile + (ly + RT) * TW + lx0 + RHCCQ_LTT_PAD);
+        const uint4 a = ctr[0], b = ctr[1];
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 1;                            // the pixel itself
+#pragma unroll
+    for (int dy = -RT; dy <= RT; ++dy) {
+        if (dy * dy > thr) continue;                                   // (block-uniform)
+        uint32_t win[16];
+        const uint4* row = reinterpret_cast<const uint4*>(tile + (ly + RT + dy) * TW + lx0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const uint4 v = row[j]; win[4 * j] = v.x; win[4 * j + 1] = v.y; win[4 * j + 2] = v.z; win[4 * j + 3] = v.w; }
+#pragma unroll
+        for (int dx = -RT; dx <= RT; ++dx) {
+            if (dy == 0 && dx == 0) continue;
+            const int budget = thr - dy * dy - dx * dx;
+            if (budget < 0) continue;
+            const unsigned start = (unsigned)(-(budget + 1));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {                              // 0xFF top byte (outside the image): never within
+                const unsigned d = __vabsdiffu4(c[u], win[u + dx + RHCCQ_LTT_PAD]);
+                acc[u] += (int)(__dp4a(d, d, start) >> 31);            // d2 - budget - 1 < 0  <=>  d2 <= budget
+            }
+        }
+    }
+}
+
+// results of 8 adjacent pixels: counts, packed colours with the core bit, core flags
+__device__ __forceinline__ void rhccq_lt_store8(const rhccq_lt_args& A, int y, int x0, const uint32_t (&c)[8], const int (&acc)[8],
+                                                int* __restrict__ count, uint32_t* __restrict__ packed, uint8_t* __restrict__ core) {
+    if (y >= A.H || x0 >= A.W) return;
+    uint32_t pk[8];
+    unsigned long long cbits = 0ull;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int is_core = acc[u] >= A.min_pts;
+        pk[u] = c[u] | (is_core ? RHCCQ_LT_CORE : 0u);
+        cbits |= (unsigned long long)is_core << (8 * u);
+    }
+    const size_t id0 = (size_t)y * A.W + x0;
+#ifndef RHCCQ_HOST_EMU
+    if ((A.W & 7) == 0 && x0 + 8 <= A.W) {                             // 8 adjacent pixels: 32-byte aligned vector stores
+        reinterpret_cast<int4*>(count + id0)[0] = make_int4(acc[0], acc[1], acc[2], acc[3]);
+        reinterpret_cast<int4*>(count + id0)[1] = make_int4(acc[4], acc[5], acc[6], acc[7]);
+        reinterpret_cast<uint4*>(packed + id0)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        reinterpret_cast<uint4*>(packed + id0)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        *reinterpret_cast<unsigned long long*>(core + id0) = cbits;
+        return;
+    }
+#endif
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        if (x0 + u >= A.W) break;
+        count[id0 + u] = acc[u];
+        core[id0 + u] = (uint8_t)((cbits >> (8 * u)) & 1ull);
+        packed[id0 + u] = pk[u];
+    }
+}
+
 template <int SRC, int RT>
 __global__ void __launch_bounds__(RHCCQ_PT_THREADS)
 rhccq_k_lt_count_rows(const void* __restrict__ src, rhccq_lt_args A, int* __restrict__ count, uint32_t* __restrict__ packed,
                       uint8_t* __restrict__ core, int* __restrict__ status) {
     RHCCQ_DYN_SMEM(dyn);
     __shared__ int s_bad;
-    const int TH = 32, SW = 8;
-    const int tw = RHCCQ_LT_W + 2 * RT, th = TH + 2 * RT;
+    const int TH = RHCCQ_LTT_TH, SW = 8;
+    const int tw = RHCCQ_LTT_TW, th = TH + 2 * RT;
     uint32_t* tile = reinterpret_cast<uint32_t*>(dyn);
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
     const int tiles_x = (A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W, tiles_y = (A.H + TH - 1) / TH;
     for (int tI = blockIdx.x; tI < tiles_x * tiles_y; tI += gridDim.x) {
         const int ty0 = (tI / tiles_x) * TH, tx0 = (tI % tiles_x) * RHCCQ_LT_W;
-        rhccq_lt_load_tile<SRC>(src, A, ty0, tx0, tile, tw, th, &s_bad);
+        rhccq_lt_load_tile<SRC>(src, A, ty0, tx0, tile, tw, th, &s_bad, RHCCQ_LTT_PAD);
         __syncthreads();
         RHCCQ_PAR_FOR(t, (RHCCQ_LT_W / SW) * TH) {
             const int ly = t / (RHCCQ_LT_W / SW), lx0 = (t % (RHCCQ_LT_W / SW)) * SW;
             uint32_t c[SW];
             int acc[SW];
-#pragma unroll
-            for (int u = 0; u < SW; ++u) { c[u] = tile[(ly + RT) * tw + lx0 + RT + u] & 0x00ffffffu; acc[u] = 0; }
-#pragma unroll
-            for (int dy = -RT; dy <= RT; ++dy) {
-                if (dy * dy > A.thr) continue;                         // (block-uniform)
-                uint32_t win[SW + 2 * RT];
-                const uint32_t* row = tile + (ly + RT + dy) * tw + lx0;
-#pragma unroll
-                for (int j = 0; j < SW + 2 * RT; ++j) win[j] = row[j];
-#pragma unroll
-                for (int dx = -RT; dx <= RT; ++dx) {
-                    const int budget = A.thr - dy * dy - dx * dx;
-                    if (budget < 0) continue;
-#pragma unroll
-                    for (int u = 0; u < SW; ++u)                        // 0xFF top byte (outside the image): never within
-                        acc[u] += (int)((unsigned)rhccq_d2(c[u], win[u + dx + RT]) <= (unsigned)budget);
-                }
-            }
-            const int y = ty0 + ly, x0 = tx0 + lx0;
-            if (y >= A.H || x0 >= A.W) continue;
-            uint32_t pk[SW];
-            unsigned long long cbits = 0ull;
-#pragma unroll
-            for (int u = 0; u < SW; ++u) {
-                const int is_core = acc[u] >= A.min_pts;
-                pk[u] = c[u] | (is_core ? RHCCQ_LT_CORE : 0u);
-                cbits |= (unsigned long long)is_core << (8 * u);
-            }
-            const size_t id0 = (size_t)y * A.W + x0;
-#ifndef RHCCQ_HOST_EMU
-            if ((A.W & 7) == 0 && x0 + SW <= A.W) {                    // 8 adjacent pixels: 32-byte aligned vector stores
-                reinterpret_cast<int4*>(count + id0)[0] = make_int4(acc[0], acc[1], acc[2], acc[3]);
-                reinterpret_cast<int4*>(count + id0)[1] = make_int4(acc[4], acc[5], acc[6], acc[7]);
-                reinterpret_cast<uint4*>(packed + id0)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                reinterpret_cast<uint4*>(packed + id0)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                *reinterpret_cast<unsigned long long*>(core + id0) = cbits;
-                continue;
-            }
-#endif
-#pragma unroll
-            for (int u = 0; u < SW; ++u) {
-                if (x0 + u >= A.W) break;
-                count[id0 + u] = acc[u];
-                core[id0 + u] = (uint8_t)((cbits >> (8 * u)) & 1ull);
-                packed[id0 + u] = pk[u];
-            }
+            rhccq_lt_stencil8<RT>(tile, ly, lx0, A.thr, c, acc);
+            rhccq_lt_store8(A, ty0 + ly, tx0 + lx0, c, acc, count, packed, core);
         }
         __syncthreads();
     }
     if (SRC == 0 && threadIdx.x == 0 && s_bad) *status = 1;
 }
+
+#ifndef RHCCQ_HOST_EMU
+// One colour channel of a float32 point -> 0..255 without the conversion unit: v + 2^23 holds round(v) in its low
+// mantissa bits. `eor` collects the bits of every "must be exactly zero" difference, `uor` every channel value.
+__device__ __forceinline__ uint32_t rhccq_lt_chan(float v, uint32_t& eor, uint32_t& uor) {
+    const float s = v + 8388608.0f;
+    const uint32_t sb = __float_as_uint(s);
+    eor |= __float_as_uint(s - 8388608.0f) ^ __float_as_uint(v);      // v is an integer (bit pattern of its rounding)
+    uor |= sb ^ 0x4B000000u;                                           // ... of 0..255 (nothing above the low byte)
+    return sb & 255u;
+}
+__device__ __forceinline__ uint32_t rhccq_lt_pack_fast(float fx, float fy, float r, float g, float b, float xf, float yf,
+                                                       uint32_t& eor, uint32_t& uor) {
+    eor |= (__float_as_uint(fx) ^ __float_as_uint(xf)) | (__float_as_uint(fy) ^ __float_as_uint(yf));
+    const uint32_t ur = rhccq_lt_chan(r, eor, uor), ug = rhccq_lt_chan(g, eor, uor), ub = rhccq_lt_chan(b, eor, uor);
+    return (ur << 16) + (ug << 8) + ub;
+}
+
+// The same count pass for float32 points, as a persistent kernel fed by TMA: the rows of a tile (halo included)
+// are contiguous runs of 20-byte points in global memory, so one cp.async.bulk per row brings the raw floats into
+// a staging buffer; the copies of the next tile are in flight while the stencil of the current one runs.
+template <int RT, int THR>
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS, 3)
+rhccq_k_lt_count_tma(const float* __restrict__ pts, rhccq_lt_args A, int* __restrict__ count, uint32_t* __restrict__ packed,
+                     uint8_t* __restrict__ core, int* __restrict__ status) {
+    RHCCQ_DYN_SMEM(dyn);
+    __shared__ uint64_t s_bar;
+    __shared__ int s_bad;
+    constexpr int TH = RHCCQ_LTT_TH, TW = RHCCQ_LTT_TW, THH = TH + 2 * RT, QUADS = TW / 4;
+    float* stage = reinterpret_cast<float*>(dyn);                                   // [THH][TW] points of 5 floats
+    uint32_t* tile = reinterpret_cast<uint32_t*>(dyn + (size_t)THH * TW * 20);      // [THH][TW] packed colours
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_x = (A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W, tiles_y = (A.H + TH - 1) / TH, ntiles = tiles_x * tiles_y;
+    if (tid == 0) {
+        s_bad = 0;
+        rhccq_mbar_init(&s_bar);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int tI) {                                                      // warp 0: one bulk copy per tile row
+        const int ty0 = (tI / tiles_x) * TH, tx0 = (tI % tiles_x) * RHCCQ_LT_W;
+        const int y_lo = max(ty0 - RT, 0), y_hi = min(ty0 + TH + RT, A.H);
+        const int x_lo = max(tx0 - RHCCQ_LTT_PAD, 0), x_hi = min(tx0 + RHCCQ_LT_W + RHCCQ_LTT_PAD, A.W);
+        const uint32_t row_bytes = (uint32_t)(x_hi - x_lo) * 20u;                   // W % 4 == 0: a multiple of 16
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rhccq_smem_addr(&s_bar)), "r"(row_bytes * (uint32_t)(y_hi - y_lo)) : "memory");
+        __syncwarp();
+        for (int y = y_lo + lane; y < y_hi; y += 32) {
+            float* dst = stage + ((size_t)(y - (ty0 - RT)) * TW + (x_lo - (tx0 - RHCCQ_LTT_PAD))) * 5;
+            const float* srcp = pts + ((size_t)y * A.W + x_lo) * 5;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(rhccq_smem_addr(dst)), "l"(srcp), "r"(row_bytes), "r"(rhccq_smem_addr(&s_bar)) : "memory");
+        }
+    };
+    uint32_t phase = 0, eor = 0, uor = 0;
+    if (warp == 0 && (int)blockIdx.x < ntiles) issue((int)blockIdx.x);
+    for (int tI = (int)blockIdx.x; tI < ntiles; tI += (int)gridDim.x) {
+        const int ty0 = (tI / tiles_x) * TH, tx0 = (tI % tiles_x) * RHCCQ_LT_W;
+        rhccq_mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+        for (int t = tid; t < THH * QUADS; t += RHCCQ_PT_THREADS) {                 // raw floats -> packed colours
+            const int ty = t / QUADS, q = t % QUADS;
+            const int y = ty0 - RT + ty, x = tx0 - RHCCQ_LTT_PAD + 4 * q;
+            uint4 o = make_uint4(RHCCQ_LT_INVALID, RHCCQ_LT_INVALID, RHCCQ_LT_INVALID, RHCCQ_LT_INVALID);
+            if ((unsigned)y < (unsigned)A.H && (unsigned)x < (unsigned)A.W) {
+                const float4* p = reinterpret_cast<const float4*>(stage + ((size_t)ty * TW + 4 * q) * 5);
+                const float4 a = p[0], b = p[1], c4 = p[2], d = p[3], e = p[4];
+                const float xf = (float)x, yf = (float)y;
+                o.x = rhccq_lt_pack_fast(a.x, a.y, a.z, a.w, b.x, xf, yf, eor, uor);
+                o.y = rhccq_lt_pack_fast(b.y, b.z, b.w, c4.x, c4.y, xf + 1.0f, yf, eor, uor);
+                o.z = rhccq_lt_pack_fast(c4.z, c4.w, d.x, d.y, d.z, xf + 2.0f, yf, eor, uor);
+                o.w = rhccq_lt_pack_fast(d.w, e.x, e.y, e.z, e.w, xf + 3.0f, yf, eor, uor);
+            }
+            *reinterpret_cast<uint4*>(tile + ty * TW + 4 * q) = o;
+        }
+        __syncthreads();                                                            // tile complete, staging buffer free
+        const int next = tI + (int)gridDim.x;
+        if (warp == 0 && next < ntiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(next);
+        }
+        {
+            const int ly = tid / (RHCCQ_LT_W / 8), lx0 = (tid % (RHCCQ_LT_W / 8)) * 8;   // 256 threads = 32 rows x 8 octets
+            uint32_t c[8];
+            int acc[8];
+            rhccq_lt_stencil8<RT, THR>(tile, ly, lx0, A.thr, c, acc);
+            rhccq_lt_store8(A, ty0 + ly, tx0 + lx0, c, acc, count, packed, core);
+        }
+        __syncthreads();                                                            // before the next conversion overwrites the tile
+    }
+    if ((eor | (uor >> 8)) != 0u) s_bad = 1;            // (a -0.0 is flagged too: the caller then takes the generic path, which is always right)
+    __syncthreads();
+    if (tid == 0 && s_bad) *status = 1;
+}
+#endif
 
 #define RHCCQ_LT_H 16         // tile height of the count and attachment passes
 #define RHCCQ_LT_UH 32        // tile height of the union passes: fewer edges cross tile borders
@@ -1094,10 +1217,30 @@ int rhccq_dbscan_lattice_count(const void* src, int src_kind, int H, int W, doub
 #endif
     const size_t csmem = rhccq_lt_smem(A, RHCCQ_LT_UH);
     const int cgrid = rhccq_lt_grid(A, RHCCQ_LT_UH);
-#define RHCCQ_LT_ROWS(SRCK, RT)                                                                                      \
-    RHCCQ_LAUNCH((rhccq_k_lt_count_rows<SRCK, RT>), cgrid, RHCCQ_PT_THREADS, csmem, (cudaStream_t)stream, src, A, count,   \
-                 L.packed, core, status)
     if (A.R >= 1 && A.R <= 4) {                                    // sliding-window form
+        const size_t rsmem = (size_t)RHCCQ_LTT_TW * (RHCCQ_LTT_TH + 2 * A.R) * 4;
+#ifndef RHCCQ_HOST_EMU
+        if (src_kind == 0 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {     // persistent, TMA-fed
+            const size_t tsmem = rsmem * 6;                        // staging (20 B / pixel) + tile (4 B / pixel)
+            const long long tiles = (long long)((W + RHCCQ_LT_W - 1) / RHCCQ_LT_W) * ((H + RHCCQ_LTT_TH - 1) / RHCCQ_LTT_TH);
+            const long long cap = (long long)rhccq_sm_count() * 3;
+            const int tgrid = (int)(tiles < cap ? tiles : cap);
+#define RHCCQ_LT_TMA(RT, THR)                                                                                        \
+    do { if (rhccq_smem_optin((const void*)rhccq_k_lt_count_tma<RT, THR>, tsmem) != 0) return -1;                    \
+         RHCCQ_LAUNCH((rhccq_k_lt_count_tma<RT, THR>), tgrid, RHCCQ_PT_THREADS, tsmem, (cudaStream_t)stream,         \
+                      (const float*)src, A, count, L.packed, core, status); } while (0)
+            // integer radii (thr = R^2) get a kernel with the stencil resolved at compile time
+            if (A.R == 1) { if (A.thr == 1) RHCCQ_LT_TMA(1, 1); else RHCCQ_LT_TMA(1, -1); }
+            else if (A.R == 2) { if (A.thr == 4) RHCCQ_LT_TMA(2, 4); else RHCCQ_LT_TMA(2, -1); }
+            else if (A.R == 3) { if (A.thr == 9) RHCCQ_LT_TMA(3, 9); else RHCCQ_LT_TMA(3, -1); }
+            else { if (A.thr == 16) RHCCQ_LT_TMA(4, 16); else RHCCQ_LT_TMA(4, -1); }
+#undef RHCCQ_LT_TMA
+            return 0;
+        }
+#endif
+#define RHCCQ_LT_ROWS(SRCK, RT)                                                                                      \
+    RHCCQ_LAUNCH((rhccq_k_lt_count_rows<SRCK, RT>), cgrid, RHCCQ_PT_THREADS, rsmem, (cudaStream_t)stream, src, A, count,   \
+                 L.packed, core, status)
         if (src_kind == 0) {
             if (A.R == 1) RHCCQ_LT_ROWS(0, 1); else if (A.R == 2) RHCCQ_LT_ROWS(0, 2); else if (A.R == 3) RHCCQ_LT_ROWS(0, 3); else RHCCQ_LT_ROWS(0, 4);
         } else {
