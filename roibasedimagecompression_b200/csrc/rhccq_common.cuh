@@ -53,6 +53,7 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
 static inline unsigned __vabsdiffu4(unsigned a, unsigned b) {
     unsigned r = 0;
     for (int s = 0; s < 32; s += 8) {

@@ -953,6 +953,84 @@ rhccq_k_lt_sweep(const void* __restrict__ src, rhccq_lt_args A, int* __restrict_
     if (MODE == 0 && SRC == 0 && threadIdx.x == 0 && s_bad) *status = 1;
 }
 
+// Union inside a tile (what MODE 1 above did, restructured so that the shared-memory forest stays shallow):
+//  1. horizontal runs — core pixels linked to their left neighbour — are found with warp votes and start as
+//     stars under the run's first pixel, with no union at all;
+//  2. the remaining forward offsets are taken one at a time, all pixels in step. Every tree is a star when a
+//     pass starts, so "already linked" is one comparison of two shared-memory loads, and only pairs that really
+//     bridge two sets walk and link trees; the trees are flattened to stars again after each pass.
+// The result goes to `parent` as stars in global indices (a set's root is its lowest index, as before).
+template <int TH>
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_lt_union_tile(const uint32_t* __restrict__ packed, rhccq_lt_args A, int* __restrict__ parent) {
+    RHCCQ_DYN_SMEM(dyn);
+    __shared__ int s_noff, s_bad;
+    const int tw = RHCCQ_LT_W + 2 * A.R, th = TH + 2 * A.R;
+    uint32_t* tile = reinterpret_cast<uint32_t*>(dyn);
+    int2* offs = reinterpret_cast<int2*>(tile + (((size_t)tw * th + 1) & ~(size_t)1));
+    int* lpar = reinterpret_cast<int*>(offs + (2 * A.R + 1) * (2 * A.R + 1));
+    if (threadIdx.x == 0) { s_noff = rhccq_lt_build_offsets(offs, A.R, A.thr, true); s_bad = 0; }
+    __syncthreads();
+    const int n_off = s_noff;
+    const int run_budget = A.thr - 1;                                   // offset (0, 1)
+    const int tiles_x = (A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W, tiles_y = (A.H + TH - 1) / TH;
+    for (int tI = blockIdx.x; tI < tiles_x * tiles_y; tI += gridDim.x) {
+        const int ty0 = (tI / tiles_x) * TH, tx0 = (tI % tiles_x) * RHCCQ_LT_W;
+        rhccq_lt_load_tile<2>(packed, A, ty0, tx0, tile, tw, th, &s_bad);
+        __syncthreads();
+        // 1. horizontal runs
+        for (int row = RHCCQ_WARP; row < TH; row += RHCCQ_NWARPS) {
+            const uint32_t* trow = tile + (row + A.R) * tw + A.R;
+            unsigned long long linked = 0ull;                           // bit x: pixel x continues the run of x - 1
+            for (int h = 0; h < RHCCQ_LT_W / RHCCQ_WARP_SIZE; ++h) {
+                const int lx = h * RHCCQ_WARP_SIZE + RHCCQ_LANE;
+                bool conn = false;
+                if (lx > 0) {
+                    const uint32_t me = trow[lx], lf = trow[lx - 1];
+                    conn = (me >> 24) == 1u && (lf >> 24) == 1u && rhccq_d2(me & 0x00ffffffu, lf & 0x00ffffffu) <= run_budget;
+                }
+                linked |= (unsigned long long)rhccq_ballot(conn) << (h * RHCCQ_WARP_SIZE);
+            }
+            for (int h = 0; h < RHCCQ_LT_W / RHCCQ_WARP_SIZE; ++h) {
+                const int lx = h * RHCCQ_WARP_SIZE + RHCCQ_LANE;
+                const unsigned long long starts = ~linked & ((2ull << lx) - 1ull);      // bit 0 is always a start
+                lpar[row * RHCCQ_LT_W + lx] = row * RHCCQ_LT_W + 63 - __clzll((long long)starts);
+            }
+        }
+        __syncthreads();
+        // 2. one forward offset at a time, every tree a star when the pass starts
+        for (int o = 0; o < n_off; ++o) {
+            const int2 e = offs[o];
+            const int dy = (e.x >> 8) - 64, dx = (e.x & 255) - 64;
+            if (dy == 0 && dx == 1) continue;                           // the runs
+            RHCCQ_PAR_FOR(t, RHCCQ_LT_W * TH) {
+                const int ly = t / RHCCQ_LT_W, lx = t % RHCCQ_LT_W;
+                if (!((unsigned)(ly + dy) < (unsigned)TH && (unsigned)(lx + dx) < (unsigned)RHCCQ_LT_W)) continue;   // cross-border pass
+                const int ci = (ly + A.R) * tw + lx + A.R;
+                const uint32_t me = tile[ci], nb = tile[ci + dy * tw + dx];
+                if ((me >> 24) != 1u || (nb >> 24) != 1u) continue;     // core pixels of the image only
+                if ((unsigned)rhccq_d2(me & 0x00ffffffu, nb & 0x00ffffffu) > (unsigned)e.y) continue;
+                const int ra = ((volatile int*)lpar)[t], rb = ((volatile int*)lpar)[t + dy * RHCCQ_LT_W + dx];
+                if (ra != rb) rhccq_pt_union(lpar, ra, rb);
+            }
+            __syncthreads();
+            RHCCQ_PAR_FOR(t, RHCCQ_LT_W * TH) {
+                const int r = rhccq_pt_find_ro(lpar, t);
+                lpar[t] = r;                                            // racing readers see the old parent or the root: both ancestors
+            }
+            __syncthreads();
+        }
+        RHCCQ_PAR_FOR(t, RHCCQ_LT_W * TH) {
+            const int ly = t / RHCCQ_LT_W, lx = t % RHCCQ_LT_W;
+            const int y = ty0 + ly, x = tx0 + lx;
+            if (y >= A.H || x >= A.W) continue;
+            const int r = lpar[t];
+            parent[y * A.W + x] = (ty0 + r / RHCCQ_LT_W) * A.W + tx0 + r % RHCCQ_LT_W;
+        }
+        __syncthreads();
+    }
+}
+
 // Count pass for small radii (R <= 4, the usual eps 1..4.9): every thread owns 8 horizontally adjacent pixels.
 // The tile has RHCCQ_LTT_PAD halo columns on each side whatever the radius, so that a thread's window of a
 // stencil row (its 8 pixels + 4 either side) is four aligned 16-byte shared-memory loads; the dx offsets slide
@@ -1261,13 +1339,11 @@ int rhccq_dbscan_lattice_count(const void* src, int src_kind, int H, int W, doub
 
 int rhccq_dbscan_lattice_union(int H, int W, double eps, int min_pts, void* ws, size_t ws_bytes, void* stream) {
     RHCCQ_LT_PROLOGUE("rhccq_dbscan_lattice_union")
-    RHCCQ_LAUNCH(rhccq_k_pt_init_parent, rhccq_pt_blocks((long long)H * W), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, H * W, L.parent);
-    // (the init above is overwritten for every pixel by the tile-local pass; it keeps the array defined)
+    // (the tile-local pass writes the parent of every pixel)
     const size_t usmem = rhccq_lt_smem(A, RHCCQ_LT_UH);
     const int ugrid = rhccq_lt_grid(A, RHCCQ_LT_UH);
-    if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<1, 2, RHCCQ_LT_UH>, usmem) != 0) return -1;
-    RHCCQ_LAUNCH((rhccq_k_lt_sweep<1, 2, RHCCQ_LT_UH>), ugrid, RHCCQ_PT_THREADS, usmem, (cudaStream_t)stream, (const void*)L.packed, A,
-                 (int*)nullptr, L.packed, (uint8_t*)nullptr, L.parent, L.rootlab, (int*)nullptr);
+    if (rhccq_smem_optin((const void*)rhccq_k_lt_union_tile<RHCCQ_LT_UH>, usmem) != 0) return -1;
+    RHCCQ_LAUNCH((rhccq_k_lt_union_tile<RHCCQ_LT_UH>), ugrid, RHCCQ_PT_THREADS, usmem, (cudaStream_t)stream, L.packed, A, L.parent);
     if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<3, 2, RHCCQ_LT_UH>, usmem) != 0) return -1;
     RHCCQ_LAUNCH((rhccq_k_lt_sweep<3, 2, RHCCQ_LT_UH>), ugrid, RHCCQ_PT_THREADS, usmem, (cudaStream_t)stream, (const void*)L.packed, A,
                  (int*)nullptr, L.packed, (uint8_t*)nullptr, L.parent, L.rootlab, (int*)nullptr);
