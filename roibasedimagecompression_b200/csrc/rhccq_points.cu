@@ -838,28 +838,41 @@ __device__ __forceinline__ void rhccq_lt_load_tile(const void* src, const rhccq_
 
 #define RHCCQ_LT_PPT 8        // pixels per thread of the count pass: rows ly, ly + TH/8, ...
 
+// small shared-memory set of (set a, set b) pairs: true the first time a pair is offered (or when the
+// neighbourhood of its slot is full: a repeated union is harmless)
+#define RHCCQ_LT_PAIRS 1024
+__device__ __forceinline__ bool rhccq_lt_pair_is_new(unsigned long long* pairs, int a, int b) {
+    const unsigned long long key = ((unsigned long long)(unsigned)a << 32) | (unsigned)b;
+    unsigned slot = ((unsigned)a * 2654435761u ^ (unsigned)b * 2246822519u) >> 22;       // 10 bits
+    for (int probe = 0; probe < 16; ++probe) {
+        const unsigned long long old = atomicCAS(&pairs[slot], ~0ull, key);
+        if (old == ~0ull) return true;
+        if (old == key) return false;
+        slot = (slot + 1u) & (RHCCQ_LT_PAIRS - 1u);
+    }
+    return true;
+}
+
 // MODE 0: count (+ packed colours with the core bit)
-//      1: union inside the tile (shared-memory union-find), result as a star forest in `parent`
-//      3: union across tile borders (global union-find), after every tile has finished mode 1
+//      3: union across tile borders (global union-find), after rhccq_k_lt_union_tile has finished every tile
 //      2: border attachment
 template <int MODE, int SRC, int TH>
 __global__ void __launch_bounds__(RHCCQ_PT_THREADS)
 rhccq_k_lt_sweep(const void* __restrict__ src, rhccq_lt_args A, int* __restrict__ count, uint32_t* __restrict__ packed,
                  uint8_t* __restrict__ core, int* __restrict__ parent, int* __restrict__ rootlab, int* __restrict__ status) {
     RHCCQ_DYN_SMEM(dyn);
-    __shared__ int s_noff, s_bad;
+    __shared__ int s_noff, s_bad, s_cnt;
     const int tw = RHCCQ_LT_W + 2 * A.R, th = TH + 2 * A.R;
     uint32_t* tile = reinterpret_cast<uint32_t*>(dyn);
     int2* offs = reinterpret_cast<int2*>(tile + (((size_t)tw * th + 1) & ~(size_t)1));
-    int* lpar = reinterpret_cast<int*>(offs + (2 * A.R + 1) * (2 * A.R + 1));      // MODE 1: local parents
-    if (threadIdx.x == 0) { s_noff = rhccq_lt_build_offsets(offs, A.R, A.thr, MODE == 1 || MODE == 3); s_bad = 0; }
+    int* lpar = reinterpret_cast<int*>(offs + (2 * A.R + 1) * (2 * A.R + 1));      // RHCCQ_LT_W * TH ints: work list
+    if (threadIdx.x == 0) { s_noff = rhccq_lt_build_offsets(offs, A.R, A.thr, MODE == 3); s_bad = 0; }
     __syncthreads();
     const int n_off = s_noff;
     const int tiles_x = (A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W, tiles_y = (A.H + TH - 1) / TH;
     for (int tI = blockIdx.x; tI < tiles_x * tiles_y; tI += gridDim.x) {
         const int ty0 = (tI / tiles_x) * TH, tx0 = (tI % tiles_x) * RHCCQ_LT_W;
         rhccq_lt_load_tile<SRC>(src, A, ty0, tx0, tile, tw, th, &s_bad);
-        if (MODE == 1) RHCCQ_PAR_FOR(t, RHCCQ_LT_W * TH) lpar[t] = t;
         __syncthreads();
         if (MODE == 0) {
             // every thread owns RHCCQ_LT_PPT pixels of one column: a stencil entry is decoded once for all of them
@@ -894,58 +907,55 @@ rhccq_k_lt_sweep(const void* __restrict__ src, rhccq_lt_args A, int* __restrict_
                 }
             }
         } else {
-            RHCCQ_PAR_FOR(t, RHCCQ_LT_W * TH) {
+            // the pixels with work to do, compacted so that every lane of the pass below is busy:
+            // attachment (2): the non-core pixels; cross-border links (3): core pixels within R of the tile's
+            // left, right or bottom edge (forward offsets never leave through the top)
+            int* list = lpar;
+            unsigned long long* pairs = reinterpret_cast<unsigned long long*>(lpar + RHCCQ_LT_W * TH);
+            if (threadIdx.x == 0) s_cnt = 0;
+            if (MODE == 3) RHCCQ_PAR_FOR(k, RHCCQ_LT_PAIRS) pairs[k] = ~0ull;
+            __syncthreads();
+            RHCCQ_PAR_FOR(t, RHCCQ_LT_W * TH) {                         // (trip count uniform: votes are safe)
                 const int ly = t / RHCCQ_LT_W, lx = t % RHCCQ_LT_W;
-                const int y = ty0 + ly, x = tx0 + lx;
-                if (y >= A.H || x >= A.W) continue;
+                bool want = ty0 + ly < A.H && tx0 + lx < A.W;
+                if (want) {
+                    const bool is_core = (tile[(ly + A.R) * tw + lx + A.R] >> 24) == 1u;
+                    want = MODE == 2 ? !is_core : (is_core && (lx < A.R || lx >= RHCCQ_LT_W - A.R || ly >= TH - A.R));
+                }
+                const unsigned m = rhccq_ballot(want);
+                int base = 0;
+                if (RHCCQ_LANE == 0 && m) base = atomicAdd(&s_cnt, __popc(m));
+                base = rhccq_shfl(base, 0);
+                if (want) list[base + __popc(m & rhccq_lanemask_lt())] = t;
+            }
+            __syncthreads();
+            const int n_list = s_cnt;
+            RHCCQ_PAR_FOR(li, n_list) {
+                const int t = list[li];
+                const int ly = t / RHCCQ_LT_W, lx = t % RHCCQ_LT_W;
                 const int ci = (ly + A.R) * tw + lx + A.R;
-                const uint32_t me = tile[ci];
-                const uint32_t c = me & 0x00ffffffu;
-                const int id = y * A.W + x;
-                const bool me_core = (me & RHCCQ_LT_CORE) != 0u;
-                if ((MODE == 2) == me_core) continue;                   // unions: core pixels; attachment: the others
-                int best = 0x7fffffff, my_root = MODE == 1 ? t : id;
+                const uint32_t c = tile[ci] & 0x00ffffffu;
+                const int id = (ty0 + ly) * A.W + tx0 + lx;
+                int best = 0x7fffffff;
+                const int my_root = MODE == 3 ? ((volatile int*)parent)[id] : id;     // (3) a star from the tile pass: its set
                 for (int o = 0; o < n_off; ++o) {
                     const int2 e = offs[o];
                     const int dy = (e.x >> 8) - 64, dx = (e.x & 255) - 64;
-                    const bool inside = (unsigned)(ly + dy) < (unsigned)TH && (unsigned)(lx + dx) < (unsigned)RHCCQ_LT_W;
-                    if (MODE == 1 && !inside) continue;                 // the cross-border pass links those
-                    if (MODE == 3 && inside) continue;
+                    if (MODE == 3 && (unsigned)(ly + dy) < (unsigned)TH && (unsigned)(lx + dx) < (unsigned)RHCCQ_LT_W) continue;   // linked inside the tile
                     const uint32_t nb = tile[ci + dy * tw + dx];
                     if ((nb >> 24) != 1u) continue;                     // outside the image, or not core
                     if ((unsigned)rhccq_d2(c, nb & 0x00ffffffu) > (unsigned)e.y) continue;
-                    if (MODE == 1) {
-                        // one hop tells when the neighbour already hangs under my root (the usual case once a
-                        // dense patch is linked); only otherwise walk both trees and link
-                        const int nl = t + dy * RHCCQ_LT_W + dx;
-                        if (((volatile int*)lpar)[nl] != my_root) {
-                            rhccq_pt_union(lpar, nl, t);
-                            my_root = rhccq_pt_find(lpar, t);
-                        }
-                    } else if (MODE == 3) {
-                        const int nid = id + dy * A.W + dx;
-                        if (((volatile int*)parent)[nid] != my_root) {
-                            rhccq_pt_union(parent, nid, id);
-                            my_root = rhccq_pt_find(parent, id);
-                        }
+                    if (MODE == 3) {
+                        // many pixel pairs bridge the same two tile-local sets: only the first of a
+                        // (my set, neighbour's set) pair seen by this block goes to the global forest
+                        const int rb = ((volatile int*)parent)[id + dy * A.W + dx];
+                        if (rb != my_root && rhccq_lt_pair_is_new(pairs, my_root, rb)) rhccq_pt_union(parent, my_root, rb);
                     } else {
                         const int r = rootlab[id + dy * A.W + dx];
                         best = r < best ? r : best;
                     }
                 }
                 if (MODE == 2) rootlab[id] = best == 0x7fffffff ? -1 : best;
-            }
-            if (MODE == 1) {
-                // local sets -> stars in the global forest: local raster order is global index order inside a tile,
-                // so a set's local root is its lowest global index
-                __syncthreads();
-                RHCCQ_PAR_FOR(t, RHCCQ_LT_W * TH) {
-                    const int ly = t / RHCCQ_LT_W, lx = t % RHCCQ_LT_W;
-                    const int y = ty0 + ly, x = tx0 + lx;
-                    if (y >= A.H || x >= A.W) continue;
-                    const int r = rhccq_pt_find_ro(lpar, t);
-                    parent[y * A.W + x] = (ty0 + r / RHCCQ_LT_W) * A.W + tx0 + r % RHCCQ_LT_W;
-                }
             }
         }
         __syncthreads();
@@ -1248,7 +1258,7 @@ static int rhccq_lt_args_make(int H, int W, double eps, int min_pts, rhccq_lt_ar
 }
 static size_t rhccq_lt_smem(const rhccq_lt_args& A, int TH) {
     const size_t side = 2 * (size_t)A.R + 1;
-    return ((size_t)(RHCCQ_LT_W + 2 * A.R) * (TH + 2 * A.R) + 2) * 4 + side * side * 8 + (size_t)RHCCQ_LT_W * TH * 4;
+    return ((size_t)(RHCCQ_LT_W + 2 * A.R) * (TH + 2 * A.R) + 2) * 4 + side * side * 8 + (size_t)RHCCQ_LT_W * TH * 4 + RHCCQ_LT_PAIRS * 8;
 }
 static int rhccq_lt_grid(const rhccq_lt_args& A, int TH) {
     const long long tiles = (long long)((A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W) * ((A.H + TH - 1) / TH);
