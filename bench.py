@@ -251,7 +251,7 @@ def run_dbscan(args, be, rank, world, local, H, W, desc):
            "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": world * n / (e2e_ms / 1e3), "unit": "points/s", "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": n * 20 * world, "d2h_bytes_per_step": n * 4 * world},
-           "roofline": {"kernel": count_name + (" (rhccq_k_lt_sweep<0,0>)" if lattice else " (rhccq_k_pt_sweep<0>)"), "bound": "hbm", "achieved": ach, "peak": peak,
+           "roofline": {"kernel": count_name + (" (rhccq_k_lt_count_tma)" if lattice else " (rhccq_k_pt_sweep<0>)"), "bound": "hbm", "achieved": ach, "peak": peak,
                         "unit": "GB/s", "frac": ach / peak, "traffic": NCU_TRAFFIC.get((args.workload, count_name), (None, None))[0],
                         "traffic_source": NCU_TRAFFIC.get((args.workload, count_name), (None, None))[1], "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": DBSCAN_BYTES_PER_POINT * n, "avg_launch_ms": cnt_ms / cnt_n,
@@ -305,7 +305,7 @@ def dbscan_probe(be, args):
                         "(float32 [n,5], lattice kernels); see --workload c5l / c5 / c4 for the full runs",
             "points_per_s": n / (ms / 1e3), "ms": ms, "clusters": int(labels.max().item()) + 1,
             "phases_ms": {k: t / c for k, (c, t) in kt.items()},
-            "roofline": {"kernel": "rhccq_dbscan_lattice_count (rhccq_k_lt_sweep<0,0>)", "bound": "hbm", "achieved": ach,
+            "roofline": {"kernel": "rhccq_dbscan_lattice_count (rhccq_k_lt_count_tma)", "bound": "hbm", "achieved": ach,
                          "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": src,
                          "algorithmic_bytes_per_launch": DBSCAN_BYTES_PER_POINT * n, "avg_launch_ms": cms / cn}}
 

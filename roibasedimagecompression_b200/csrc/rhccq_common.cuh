@@ -29,6 +29,7 @@ typedef void* cudaStream_t;
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__ static
 #define __restrict__
 #define __launch_bounds__(...)

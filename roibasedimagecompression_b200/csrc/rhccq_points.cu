@@ -1143,6 +1143,124 @@ rhccq_k_lt_count_rows(const void* __restrict__ src, rhccq_lt_args A, int* __rest
     if (SRC == 0 && threadIdx.x == 0 && s_bad) *status = 1;
 }
 
+// The same tile-local union for small radii (R <= 4): a thread owns 8 adjacent pixels and looks UP and LEFT
+// (the mirror image of the forward offsets: same edges). Tile words are re-encoded so that one byte-wise distance
+// covers the core tests as well: core pixels carry top byte 0x00, everything else 0xFF, and a non-core centre
+// 0x7F — any pair that is not core/core is at least 127^2 apart. One offset per pass, all pixels in step: the
+// pairs within the budget are collected in a bit mask, and only those compare (and, when different, link) roots.
+template <int RT>
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_lt_union_rows(const uint32_t* __restrict__ packed, rhccq_lt_args A, int* __restrict__ parent) {
+    RHCCQ_DYN_SMEM(dyn);
+    __shared__ int s_linked;
+    constexpr int TH = RHCCQ_LTT_TH, TW = RHCCQ_LTT_TW, PAD = RHCCQ_LTT_PAD, TR = TH + RT, NTASK = TH * (RHCCQ_LT_W / 8);
+    if (threadIdx.x == 0) s_linked = 0;
+    uint32_t* tile = reinterpret_cast<uint32_t*>(dyn);                  // [TR][TW], RT rows of nothing on top
+    int* lpar = reinterpret_cast<int*>(tile + TR * TW);                 // [TR][TW], parents as indices of this layout
+    const int thr = A.thr;
+    const int tiles_x = (A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W, tiles_y = (A.H + TH - 1) / TH;
+    for (int tI = blockIdx.x; tI < tiles_x * tiles_y; tI += gridDim.x) {
+        const int ty0 = (tI / tiles_x) * TH, tx0 = (tI % tiles_x) * RHCCQ_LT_W;
+        // tile: own pixels re-encoded, the frame invalid; parents: everything its own root
+        RHCCQ_PAR_FOR(t, TR * (TW / 4)) {
+            const int r = t / (TW / 4), q = t % (TW / 4);
+            const int y = ty0 + r - RT, x = tx0 + 4 * q - PAD;
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t v = RHCCQ_LT_INVALID;
+                if (r >= RT && q >= 1 && q <= RHCCQ_LT_W / 4 && y < A.H && x + j < A.W) {
+                    const uint32_t pk = packed[(size_t)y * A.W + x + j];
+                    v = (pk >> 24) == 1u ? (pk & 0x00ffffffu) : (RHCCQ_LT_INVALID | (pk & 0x00ffffffu));
+                }
+                w[j] = v;
+            }
+            const int i0 = r * TW + 4 * q;
+            *reinterpret_cast<uint4*>(tile + i0) = uint4{w[0], w[1], w[2], w[3]};
+            *reinterpret_cast<uint4*>(lpar + i0) = uint4{(unsigned)i0, (unsigned)i0 + 1u, (unsigned)i0 + 2u, (unsigned)i0 + 3u};
+        }
+        __syncthreads();
+        // 1. horizontal runs
+        for (int row = RHCCQ_WARP; row < TH; row += RHCCQ_NWARPS) {
+            const int rb = (row + RT) * TW + PAD;
+            unsigned long long linked = 0ull;                           // bit x: pixel x continues the run of x - 1
+            for (int h = 0; h < RHCCQ_LT_W / RHCCQ_WARP_SIZE; ++h) {
+                const int lx = h * RHCCQ_WARP_SIZE + RHCCQ_LANE;
+                const uint32_t me = tile[rb + lx], lf = tile[rb + lx - 1];              // (lx == 0: the frame, never linked)
+                const bool conn = (me >> 24) == 0u && (int)__dp4a(__vabsdiffu4(me, lf), __vabsdiffu4(me, lf), (unsigned)(-thr)) < 0;
+                linked |= (unsigned long long)rhccq_ballot(conn) << (h * RHCCQ_WARP_SIZE);
+            }
+            for (int h = 0; h < RHCCQ_LT_W / RHCCQ_WARP_SIZE; ++h) {
+                const int lx = h * RHCCQ_WARP_SIZE + RHCCQ_LANE;
+                const unsigned long long starts = ~linked & ((2ull << lx) - 1ull);      // bit 0 is always a start
+                lpar[rb + lx] = rb + 63 - __clzll((long long)starts);
+            }
+        }
+        __syncthreads();
+        // 2. one offset at a time, all pixels in step; the forest is flattened to stars after a pass that linked
+        for (int dy = 0; dy <= RT; ++dy)
+            for (int dx = -RT; dx <= RT; ++dx) {
+                if (dy == 0 && dx >= -1) continue;                      // same row: the left side only, and (0, -1) are the runs
+                const int budget = thr - dy * dy - dx * dx;
+                if (budget < 0) continue;                               // (block-uniform)
+                const unsigned start = (unsigned)(-(budget + 1));
+                RHCCQ_PAR_FOR(task, NTASK) {
+                    const int ly = task / (RHCCQ_LT_W / 8), lx0 = (task % (RHCCQ_LT_W / 8)) * 8;
+                    const int mi = (ly + RT) * TW + lx0 + PAD, ni = mi - dy * TW + dx;       // my pixels, their neighbours
+                    uint32_t c[8];
+                    {
+                        const uint4 a = *reinterpret_cast<const uint4*>(tile + mi), b = *reinterpret_cast<const uint4*>(tile + mi + 4);
+                        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+                    }
+                    unsigned linked = 0u;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t cu = (c[u] >> 24) ? (c[u] ^ 0x80000000u) : c[u];      // non-core centre: 0x7F, far from both
+                        const unsigned d = __vabsdiffu4(cu, tile[ni + u]);
+                        linked |= (__dp4a(d, d, start) >> 31) << u;
+                    }
+                    bool any = false;
+                    while (linked) {
+                        const int u = __ffs((int)linked) - 1;
+                        linked &= linked - 1u;
+                        const int ra = ((volatile int*)lpar)[mi + u], rb = ((volatile int*)lpar)[ni + u];
+                        if (ra != rb) { rhccq_pt_union(lpar, ra, rb); any = true; }
+                    }
+                    if (any) s_linked = 1;
+                }
+                __syncthreads();
+                const int flat = s_linked;
+                __syncthreads();
+                if (!flat) continue;
+                if (threadIdx.x == 0) s_linked = 0;
+                RHCCQ_PAR_FOR(task, NTASK) {
+                    const int ly = task / (RHCCQ_LT_W / 8), lx0 = (task % (RHCCQ_LT_W / 8)) * 8;
+                    int* mine = lpar + (ly + RT) * TW + lx0 + PAD;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int p0 = ((volatile int*)mine)[u];
+                        const int r = rhccq_pt_find_ro(lpar, p0);
+                        if (r != p0) mine[u] = r;                       // (non-roots only, with an ancestor)
+                    }
+                }
+                __syncthreads();
+            }
+        RHCCQ_PAR_FOR(task, NTASK) {
+            const int ly = task / (RHCCQ_LT_W / 8), lx0 = (task % (RHCCQ_LT_W / 8)) * 8;
+            const int y = ty0 + ly, x0 = tx0 + lx0;
+            if (y >= A.H) continue;
+            const int* mine = lpar + (ly + RT) * TW + lx0 + PAD;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (x0 + u >= A.W) break;
+                const int r = rhccq_pt_find_ro(lpar, mine[u]);
+                parent[(size_t)y * A.W + x0 + u] = (ty0 + r / TW - RT) * A.W + tx0 + r % TW - PAD;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 #ifndef RHCCQ_HOST_EMU
 // One colour channel of a float32 point -> 0..255 without the conversion unit: v + 2^23 holds round(v) in its low
 // mantissa bits. `eor` collects the bits of every "must be exactly zero" difference, `uor` every channel value.
@@ -1352,8 +1470,18 @@ int rhccq_dbscan_lattice_union(int H, int W, double eps, int min_pts, void* ws, 
     // (the tile-local pass writes the parent of every pixel)
     const size_t usmem = rhccq_lt_smem(A, RHCCQ_LT_UH);
     const int ugrid = rhccq_lt_grid(A, RHCCQ_LT_UH);
-    if (rhccq_smem_optin((const void*)rhccq_k_lt_union_tile<RHCCQ_LT_UH>, usmem) != 0) return -1;
-    RHCCQ_LAUNCH((rhccq_k_lt_union_tile<RHCCQ_LT_UH>), ugrid, RHCCQ_PT_THREADS, usmem, (cudaStream_t)stream, L.packed, A, L.parent);
+    if (A.R >= 1 && A.R <= 4) {
+        const size_t rsmem = (size_t)RHCCQ_LTT_TW * (RHCCQ_LTT_TH + A.R) * 8;
+        const long long tiles = (long long)((W + RHCCQ_LT_W - 1) / RHCCQ_LT_W) * ((H + RHCCQ_LTT_TH - 1) / RHCCQ_LTT_TH);
+        const long long cap = (long long)rhccq_sm_count() * 32;
+        const int rgrid = (int)(tiles < cap ? tiles : cap);
+#define RHCCQ_LT_UROWS(RT) RHCCQ_LAUNCH((rhccq_k_lt_union_rows<RT>), rgrid, RHCCQ_PT_THREADS, rsmem, (cudaStream_t)stream, L.packed, A, L.parent)
+        if (A.R == 1) RHCCQ_LT_UROWS(1); else if (A.R == 2) RHCCQ_LT_UROWS(2); else if (A.R == 3) RHCCQ_LT_UROWS(3); else RHCCQ_LT_UROWS(4);
+#undef RHCCQ_LT_UROWS
+    } else {
+        if (rhccq_smem_optin((const void*)rhccq_k_lt_union_tile<RHCCQ_LT_UH>, usmem) != 0) return -1;
+        RHCCQ_LAUNCH((rhccq_k_lt_union_tile<RHCCQ_LT_UH>), ugrid, RHCCQ_PT_THREADS, usmem, (cudaStream_t)stream, L.packed, A, L.parent);
+    }
     if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<3, 2, RHCCQ_LT_UH>, usmem) != 0) return -1;
     RHCCQ_LAUNCH((rhccq_k_lt_sweep<3, 2, RHCCQ_LT_UH>), ugrid, RHCCQ_PT_THREADS, usmem, (cudaStream_t)stream, (const void*)L.packed, A,
                  (int*)nullptr, L.packed, (uint8_t*)nullptr, L.parent, L.rootlab, (int*)nullptr);
