@@ -50,7 +50,7 @@ WORKLOADS = {
 # (summaries under profiles/): (workload, entry point) -> (bytes, source)
 NCU_TRAFFIC = {
     ("c2", "rhccq_palette_split"): (832561152 + 379788544, "profiles/r01_split_c2_v6.txt (the stage-1 launch)"),
-    ("c5l", "rhccq_dbscan_lattice_count"): (336087808 + 122899200, "profiles/r01_lattice_count_v2.txt"),
+    ("c5l", "rhccq_dbscan_lattice_count"): (352404736 + 126816000, "profiles/r01_lattice_count_v3.txt"),
 }
 DBSCAN_BYTES_PER_POINT = 24       # 20 B read + 4 B written, both for the count kernel and the whole
 
