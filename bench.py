@@ -344,17 +344,55 @@ def run_strips(args, be, rank, world, local, H, W, desc):
     if world > 1: dist.barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
+    l_launches = be.launches - l0_launch
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     n = H * W
+    # the count kernel of this rank's strip (per-kernel CUDA events, separate short pass) against the HBM roofline
+    be.kernel_timing(True)
+    for _ in range(2):
+        st.run(d_rows, info)
+    torch.cuda.synchronize()
+    kt = be.kernel_times_ms(); be.kernel_timing(False)
+    cn, cms = kt["rhccq_dbscan_lattice_count"]
+    peak, peak_src = _peaks()
+    n_loc = (l1 - l0) * W
+    bpp = 3 + 4                                                     # uint8 RGB rows read + int32 count written
+    ach = bpp * n_loc / 1e9 / ((cms / cn) / 1e3)
+    roofline = {"kernel": "rhccq_dbscan_lattice_count (rhccq_k_lt_count_rows<1,R>, uint8 rows)", "bound": "hbm", "achieved": ach,
+                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bpp * n_loc, "avg_launch_ms": cms / cn,
+                "note": "7 B/point here (3 B uint8 colour read + 4 B count written; the position is the pixel index), "
+                        "not the 24 B/point of float32 [n,5] input", "share_of_step": (cms / cn) / ms,
+                "phases_ms": {k: t / c for k, (c, t) in kt.items()}}
+    # end to end: this rank's rows from pinned host memory, labels of its own rows back to the host
+    h_rows = torch.from_numpy(img).pin_memory()
+    own0, own1 = (r0 - l0) * W, (r1 - l0) * W
+    h_out = torch.empty(own1 - own0, dtype=torch.int32).pin_memory()
+    def e2e_step():
+        d_rows.copy_(h_rows, non_blocking=True)
+        lab, _ = st.run(d_rows, info)
+        h_out.copy_(lab, non_blocking=True)                         # (labels of the rank's own rows)
+    e2e_step(); torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if world > 1:
+        t = torch.tensor([e_ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e_ms = float(t.item())
+    e2e = {"value": n / (e_ms / 1e3), "unit": "points/s", "ms_per_step": e_ms,
+           "h2d_bytes_per_step": int(h_rows.numel()), "d2h_bytes_per_step": int(h_out.numel() * 4)}
     out = {"metric": "DBSCAN points/sec, one image strip-sharded (halo + NCCL boundary-edge merge)", "value": n / (ms / 1e3),
            "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "c4: " + desc, "eps": eps, "min_pts": min_pts, "rows_per_rank": r1 - r0,
                       "halo_rows": r0 - l0, "engine": "lattice kernels on uint8 rows", "boundary_edges_total": info.get("edges_total"),
                       "clusters": info.get("roots_total"), "l2": "points larger than L2"},
-           "clocks": clocks, "gpu_launches": be.launches - l0_launch,
-           "e2e": None, "roofline": None}
+           "clocks": clocks, "gpu_launches": l_launches,
+           "e2e": e2e, "roofline": roofline}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
