@@ -177,34 +177,57 @@ class StripDbscan:
             off = int(be.cdll.rhccq_dbscan_ws_offset(engine._p(), 0))
         self.rootlab = engine.ws[off:off + 4 * self.n_loc].view(torch.int32)
         self.cap = max(sum(b - a for a, b in self.zone), 1)
-        self.edges = be.empty((self.cap, 2), torch.int32)
-        self.counter = be.zeros((1,), torch.int32)
         n_own = self.own[1] - self.own[0]
-        self.ids = be.empty((max(n_own, 1),), torch.int32)
+        # exchange buffers are sized for the largest rank, so that a gather never has to re-pad (one collective
+        # here, at construction, instead of one per call)
+        import torch.distributed as dist
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        caps = torch.tensor([self.cap, max(n_own, 1)], dtype=torch.int64, device=be.device)
+        if self.world > 1:
+            dist.all_reduce(caps, op=dist.ReduceOp.MAX, group=group)
+        self.cap_all, self.ids_all = (int(v) for v in caps.tolist())
+        self.edges = be.empty((self.cap_all, 2), torch.int32)
+        self.counter = be.zeros((1,), torch.int32)
+        self.ids = be.empty((self.ids_all,), torch.int32)
         self.cnt = be.zeros((1,), torch.int32)
+        self.sizes = be.zeros((self.world,), torch.int32)
+        self._stage = {}
         self.scratch = be.empty((int(be.cdll.rhccq_uf_own_roots_scratch_ints(self.n_loc)),), torch.int32)
         self.labels = be.empty((max(n_own, 1),), torch.int32)
 
-    def _gather(self, mine, n_mine: int, width):
-        """all_gather of variable-length int32 rows: sizes first, then buffers padded to the largest."""
+    def _gather(self, mine, counter, width):
+        """all_gather of variable-length int32 rows. `counter` is the device-side row count of this rank: the
+        counts travel first (one collective, one host synchronisation for all of them), then every rank's first
+        max(count) rows. Returns (rows of all ranks in rank order, this rank's count)."""
         import torch.distributed as dist
-        be = self.be
-        world = dist.get_world_size(self.group)
-        sizes = [torch.zeros(1, dtype=torch.int64, device=be.device) for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([n_mine], dtype=torch.int64, device=be.device), group=self.group)
-        sizes = [int(s.item()) for s in sizes]
+        be, world = self.be, self.world
+        if world == 1:
+            n = int(counter.item())
+            return mine[:n].contiguous(), n
+        if dist.get_backend(self.group) == "gloo":                   # CPU tests
+            parts = [torch.zeros_like(counter) for _ in range(world)]
+            dist.all_gather(parts, counter, group=self.group)
+            sizes = [int(t.item()) for t in parts]
+        else:
+            dist.all_gather_into_tensor(self.sizes, counter, group=self.group)
+            sizes = self.sizes.tolist()
         m = max(max(sizes), 1)
-        shape = (m,) + tuple(width)
-        pad = be.zeros(shape, torch.int32)
-        pad[:n_mine] = mine[:n_mine]
-        bufs = [be.empty(shape, torch.int32) for _ in range(world)]
-        dist.all_gather(bufs, pad, group=self.group)
-        return torch.cat([b[:s] for b, s in zip(bufs, sizes)]).contiguous()
+        flat = self._stage.get(tuple(width))                          # grown on demand, reused across calls
+        need = world * m * (2 if width else 1)
+        if flat is None or flat.numel() < need:
+            flat = self._stage[tuple(width)] = be.empty((need + need // 4,), torch.int32)
+        out = flat[:need].view((world, m) + tuple(width))
+        if dist.get_backend(self.group) == "gloo":
+            dist.all_gather([out[r] for r in range(world)], mine[:m].contiguous(), group=self.group)
+        else:
+            dist.all_gather_into_tensor(out, mine[:m], group=self.group)
+        return torch.cat([out[r, :sizes[r]] for r in range(world)]), sizes[self.rank]
 
     def run(self, src, timings: dict | None = None):
         import torch.distributed as dist
         be, eng = self.be, self.engine
-        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        world = self.world
         # ---- local phases up to the roots of the local components
         if self.lattice:
             eng.count(src); eng.union()
@@ -217,8 +240,7 @@ class StripDbscan:
         for a, b in self.zone:
             be.call("rhccq_uf_emit_edges", be.ptr(self.rootlab), a, b, self.g0, be.ptr(self.edges), be.ptr(self.counter),
                     self.cap, be.stream())
-        n_e = int(self.counter.item())                              # <= cap by construction (one edge per zone point)
-        all_edges = self._gather(self.edges, n_e, (2,)) if world > 1 else self.edges[:n_e].contiguous()
+        all_edges, n_e = self._gather(self.edges, self.counter, (2,))      # n_e <= cap by construction (one edge per zone point)
         E = int(all_edges.shape[0])
         if E > 0:
             tcap = 1 << max(4, int(np.ceil(np.log2(4 * E))))
@@ -235,8 +257,7 @@ class StripDbscan:
         self.cnt.zero_()
         be.call("rhccq_uf_own_roots", be.ptr(self.rootlab), self.n_loc, self.own[0], self.own[1], self.g0, be.ptr(self.scratch),
                 be.ptr(self.ids), be.ptr(self.cnt), be.stream(), launches=3)
-        n_r = int(self.cnt.item())
-        roots = self._gather(self.ids, n_r, ()) if world > 1 else self.ids[:n_r].contiguous()   # ascending: strips are ordered
+        roots, n_r = self._gather(self.ids, self.cnt, ())            # ascending: strips are ordered
         be.call("rhccq_uf_rank_labels", be.ptr(roots), int(roots.numel()), be.ptr(self.rootlab), self.own[0], self.own[1],
                 be.ptr(self.labels), be.stream())
         if timings is not None:
