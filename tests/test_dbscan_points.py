@@ -140,6 +140,30 @@ def test_lattice_rejects_non_lattice_points_and_ragged_sizes(backend):
         plan.run(torch.from_numpy(bad).to(be.device))
 
 
+def test_lattice_float_points_every_small_radius(backend):
+    """float32 [n,5] points of an image whose width is a multiple of 4 but not of the 64-pixel tile: on the GPU this
+    is the TMA-fed count kernel (compile-time stencil for integer eps, run-time otherwise) and the row-window union;
+    several tiles in both directions, partial tiles on the right and bottom edges."""
+    be = backend
+    img = synth(40, 72, 11)
+    img[:, 36:] = (img[:, 36:] // 3) * 3                                # flatter right half: larger clusters
+    pts = pixel_features(img)
+    d_pts = torch.from_numpy(pts).to(be.device)
+    for eps, mp in ((1.0, 1), (1.5, 2), (2.0, 4), (2.9, 3), (3.0, 8), (4.0, 12), (4.9, 20)):
+        plan = D.LatticeDbscan(be, 40, 72, eps, mp)
+        lab, core = plan.run(d_pts)
+        want = O.dbscan_labels(pts, eps, mp)
+        assert np.array_equal(lab.cpu().numpy().astype(np.int64), want), (eps, mp)
+    # anything that is not pixel (x, y) with 8-bit colours must be refused, wherever it sits in a tile
+    plan = D.LatticeDbscan(be, 40, 72, 2.0, 3)
+    for idx, col, val in ((0, 2, 0.5), (71, 3, 256.0), (72 * 20 + 67, 4, -1.0), (72 * 39 + 71, 0, 70.0),
+                          (72 * 33 + 5, 1, 32.5), (72 * 32 + 64, 2, float("nan"))):
+        bad = pts.copy()
+        bad[idx, col] = val
+        with pytest.raises(Exception):
+            plan.run(torch.from_numpy(bad).to(be.device))
+
+
 @pytest.mark.gpu
 def test_lattice_equals_generic_on_1080p():
     from roibasedimagecompression_b200._lib import lib
