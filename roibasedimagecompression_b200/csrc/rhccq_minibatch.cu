@@ -16,6 +16,7 @@
 #define RHCCQ_MB_THREADS 512
 #define RHCCQ_MB_BATCH 1000
 #define RHCCQ_MB_MAXT 12
+#define RHCCQ_MB_SEED_CAP 3072      // subset sizes up to this are seeded out of shared memory (3 * batch = 3 000 is the usual one)
 #define RHCCQ_MB_CLUSTER 8           // CTAs (SMs) that walk one palette together
 
 // ---------------------------------------------------------------- MT19937 as numpy.random.RandomState(42)
@@ -195,9 +196,17 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
     __shared__ int s_i[RHCCQ_MAX_WARPS + 2 + 16];
     __shared__ long long s_ll[RHCCQ_MAX_WARPS * RHCCQ_MB_MAXT + 2];
     __shared__ double s_d[RHCCQ_MAX_WARPS + 2];
-    __shared__ int s_lab[RHCCQ_MB_BATCH];
-    __shared__ double s_own[RHCCQ_MB_BATCH];
-    __shared__ uint32_t s_col[RHCCQ_MB_BATCH];
+    // one buffer, two tenants: the seeding keeps the colours and closest distances of the (usual) 3 000-point
+    // subset and the cumulative sums of the threads' chunks here; the mini-batch steps their labels / values / colours
+    __shared__ unsigned long long s_raw8[RHCCQ_MB_SEED_CAP + RHCCQ_MB_THREADS];
+    unsigned char* s_raw = reinterpret_cast<unsigned char*>(s_raw8);
+    double* s_own = reinterpret_cast<double*>(s_raw);                                   // [RHCCQ_MB_BATCH]
+    int* s_lab = reinterpret_cast<int*>(s_raw + RHCCQ_MB_BATCH * 8);                    // [RHCCQ_MB_BATCH]
+    uint32_t* s_col = reinterpret_cast<uint32_t*>(s_raw + RHCCQ_MB_BATCH * 12);         // [RHCCQ_MB_BATCH]
+    unsigned long long* s_chunk = reinterpret_cast<unsigned long long*>(s_raw);         // [RHCCQ_MB_THREADS]
+    uint32_t* s_xs = reinterpret_cast<uint32_t*>(s_raw + RHCCQ_MB_THREADS * 8);         // [RHCCQ_MB_SEED_CAP]
+    uint32_t* s_closest = s_xs + RHCCQ_MB_SEED_CAP;                                     // [RHCCQ_MB_SEED_CAP]
+    __shared__ double s_rv[RHCCQ_MB_MAXT];
     __shared__ int s_cand[RHCCQ_MB_MAXT];
     __shared__ double s_val;
     const int n_all = B.pal_cnt[p];
@@ -253,8 +262,12 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
     __syncthreads();
     const int ns = init_size;
     // colours of the subset, contiguous (the k-means++ passes below read them k * (T + 2) times)
-    uint32_t* xs = reinterpret_cast<uint32_t*>(W.perm_xs);
+    const bool seed_smem = ns <= RHCCQ_MB_SEED_CAP;
+    uint32_t* xs = seed_smem ? s_xs : reinterpret_cast<uint32_t*>(W.perm_xs);
+    uint32_t* closest = seed_smem ? s_closest : W.closest;
+    unsigned long long* chunk_incl = seed_smem ? s_chunk : W.cum;      // inclusive sums of the threads' chunks (blockDim entries)
     RHCCQ_PAR_FOR(j, ns) xs[j] = keys[W.nb[W.sub[j]]];
+    __syncthreads();
     // ---- k-means++ on the subset (_kmeans.py:216-282): first centre by choice(ns, p=uniform)
     if (threadIdx.x == 0) {
         // cdf = cumsum(ones / ns) / last;  searchsorted(cdf, u, side='right')
@@ -278,29 +291,37 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
     unsigned long long chunk_sum = 0;
     {
         const uint32_t cf = xs[s_cand[0]];
-        for (int j = c_lo; j < c_hi; ++j) { const uint32_t d = (uint32_t)rhccq_d2(xs[j], cf); W.closest[j] = d; chunk_sum += d; }
+        for (int j = c_lo; j < c_hi; ++j) { const uint32_t d = (uint32_t)rhccq_d2(xs[j], cf); closest[j] = d; chunk_sum += d; }
         RHCCQ_PAR_FOR(q, 3) W.center[q] = (double)((cf >> (16 - 8 * q)) & 255u);
     }
     long long pot = rhccq_block_sum<long long>((long long)chunk_sum, s_ll);
     for (int c = 1; c < k; ++c) {
         unsigned long long total;
-        unsigned long long run = rhccq_block_excl_scan<unsigned long long>(chunk_sum, &total, reinterpret_cast<unsigned long long*>(s_ll));
-        for (int j = c_lo; j < c_hi; ++j) { run += W.closest[j]; W.cum[j] = run; }          // inclusive
-        __syncthreads();
-        if (threadIdx.x == 0) for (int t = 0; t < T; ++t) s_own[t] = rhccq_mt_double(mt);       // uniform(size=T), in order
+        const unsigned long long run0 = rhccq_block_excl_scan<unsigned long long>(chunk_sum, &total, reinterpret_cast<unsigned long long*>(s_ll));
+        chunk_incl[threadIdx.x] = run0 + chunk_sum;
+        if (threadIdx.x == 0) for (int t = 0; t < T; ++t) s_rv[t] = rhccq_mt_double(mt);        // uniform(size=T), in order
         __syncthreads();
         RHCCQ_PAR_FOR(t, T) {                                      // the T searches side by side
-            const double rv = __dmul_rn(s_own[t], (double)pot);
-            int lo = 0, hi = ns;                                   // first j with cum[j] >= rv
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)W.cum[mid] < rv) lo = mid + 1; else hi = mid; }
-            s_cand[t] = lo < ns - 1 ? lo : ns - 1;
+            // first j with cum[j] >= rv, cum = running sum of `closest`: first the chunk whose running sum gets
+            // there (the sums of whole chunks are non-decreasing), then the element inside it
+            const double rv = __dmul_rn(s_rv[t], (double)pot);
+            int lo = 0, hi = (int)blockDim.x;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)chunk_incl[mid] < rv) lo = mid + 1; else hi = mid; }
+            int j = ns;
+            if (lo < (int)blockDim.x) {
+                unsigned long long run = lo > 0 ? chunk_incl[lo - 1] : 0ull;
+                const int j_lo = lo * per < ns ? lo * per : ns, j_hi = j_lo + per < ns ? j_lo + per : ns;
+                for (j = j_lo; j < j_hi; ++j) { run += closest[j]; if (!((double)run < rv)) break; }
+                if (j >= j_hi) j = ns;                              // (cannot happen: the chunk's sum reaches rv)
+            }
+            s_cand[t] = j < ns - 1 ? j : ns - 1;
         }
         __syncthreads();
         uint32_t xc[RHCCQ_MB_MAXT];
 #pragma unroll
         for (int t = 0; t < RHCCQ_MB_MAXT; ++t) { acc[t] = 0; xc[t] = t < T ? xs[s_cand[t]] : 0u; }
         for (int j = c_lo; j < c_hi; ++j) {
-            const uint32_t cj = xs[j], o = W.closest[j];
+            const uint32_t cj = xs[j], o = closest[j];
 #pragma unroll
             for (int t = 0; t < RHCCQ_MB_MAXT; ++t)
                 if (t < T) { const uint32_t d = (uint32_t)rhccq_d2(cj, xc[t]); acc[t] += d < o ? d : o; }
@@ -315,9 +336,9 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         for (int t = 1; t < RHCCQ_MB_MAXT; ++t) if (t == best) cs = xc[t];
         chunk_sum = 0;
         for (int j = c_lo; j < c_hi; ++j) {
-            const uint32_t d = (uint32_t)rhccq_d2(xs[j], cs), o = W.closest[j];
+            const uint32_t d = (uint32_t)rhccq_d2(xs[j], cs), o = closest[j];
             const uint32_t m = d < o ? d : o;
-            W.closest[j] = m;
+            closest[j] = m;
             chunk_sum += m;
         }
         RHCCQ_PAR_FOR(q, 3) W.center[3 * c + q] = (double)((cs >> (16 - 8 * q)) & 255u);
