@@ -16,6 +16,7 @@
 #define RHCCQ_MB_THREADS 512
 #define RHCCQ_MB_BATCH 1000
 #define RHCCQ_MB_MAXT 12
+#define RHCCQ_MB_SEED_GROUP 32       // seeding steps whose random numbers are drawn in one go
 #define RHCCQ_MB_SEED_CAP 3072      // subset sizes up to this are seeded out of shared memory (3 * batch = 3 000 is the usual one)
 #define RHCCQ_MB_CLUSTER 8           // CTAs (SMs) that walk one palette together
 
@@ -46,28 +47,31 @@ __device__ __forceinline__ uint32_t rhccq_mt_temper(uint32_t y) {
 // element; the state refill ("twist") has a dependency structure that one warp resolves in four phases
 // (elements 0..226 read only old values, 227..453 and 454..622 read values renewed one phase earlier,
 // element 623 reads the renewed elements 0 and 396).  Every thread must call.
+__device__ __forceinline__ void rhccq_mt_twist_warp0(const rhccq_mt& m) {
+    if (RHCCQ_WARP == 0) {
+        const int lo[4] = {0, 227, 454, 623}, hi[4] = {227, 454, 623, 624};
+        for (int ph = 0; ph < 4; ++ph) {
+            for (int k0 = lo[ph]; k0 < hi[ph]; k0 += RHCCQ_WARP_SIZE) {
+                const int k = k0 + RHCCQ_LANE;
+                uint32_t v = 0;
+                if (k < hi[ph]) {
+                    const uint32_t y = (m.s[k] & 0x80000000u) | (m.s[(k + 1) % 624] & 0x7fffffffu);
+                    v = m.s[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+                }
+                __syncwarp();                              // all reads of this round before its writes
+                if (k < hi[ph]) m.s[k] = v;
+                __syncwarp();
+            }
+        }
+    }
+}
 __device__ void rhccq_mt_fill_raw(const rhccq_mt& m, uint32_t* raw, int count) {
     int done = 0;
     while (done < count) {
         __syncthreads();
         int pos = *m.pos;
         if (pos >= 624) {
-            if (RHCCQ_WARP == 0) {
-                const int lo[4] = {0, 227, 454, 623}, hi[4] = {227, 454, 623, 624};
-                for (int ph = 0; ph < 4; ++ph) {
-                    for (int k0 = lo[ph]; k0 < hi[ph]; k0 += RHCCQ_WARP_SIZE) {
-                        const int k = k0 + RHCCQ_LANE;
-                        uint32_t v = 0;
-                        if (k < hi[ph]) {
-                            const uint32_t y = (m.s[k] & 0x80000000u) | (m.s[(k + 1) % 624] & 0x7fffffffu);
-                            v = m.s[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-                        }
-                        __syncwarp();                              // all reads of this round before its writes
-                        if (k < hi[ph]) m.s[k] = v;
-                        __syncwarp();
-                    }
-                }
-            }
+            rhccq_mt_twist_warp0(m);
             __syncthreads();
             pos = 0;
         }
@@ -76,6 +80,44 @@ __device__ void rhccq_mt_fill_raw(const rhccq_mt& m, uint32_t* raw, int count) {
         __syncthreads();
         if (threadIdx.x == 0) *m.pos = pos + take;
         done += take;
+    }
+    __syncthreads();
+}
+// For consumers whose number of draws depends on the values (masked rejection): every thread calls; the unread
+// outputs of the generator's current block (after a refill if it is exhausted) are tempered into buf[0..return)
+// and the position is left where it was — the one consuming thread adds what it used.
+__device__ int rhccq_mt_peek_block(const rhccq_mt& m, uint32_t* buf) {
+    __syncthreads();
+    int pos = *m.pos;
+    if (pos >= 624) {
+        rhccq_mt_twist_warp0(m);
+        __syncthreads();
+        if (threadIdx.x == 0) *m.pos = 0;
+        pos = 0;
+    }
+    RHCCQ_PAR_FOR(i, 624 - pos) buf[i] = rhccq_mt_temper(m.s[pos + i]);
+    __syncthreads();
+    return 624 - pos;
+}
+// `count` draws of randint(0, max + 1) (masked rejection, as rhccq_mt_below), in order, into out[] (or dropped)
+__device__ void rhccq_mt_below_seq(const rhccq_mt& m, uint32_t max, int count, int* out, uint32_t* buf, int* s_prog) {
+    if (max == 0) { if (out) RHCCQ_PAR_FOR(i, count) out[i] = 0; __syncthreads(); return; }
+    uint32_t mask = max;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    if (threadIdx.x == 0) *s_prog = 0;
+    while (true) {
+        const int avail = rhccq_mt_peek_block(m, buf);
+        if (threadIdx.x == 0) {
+            int i = *s_prog, r = 0;
+            while (i < count && r < avail) {
+                const uint32_t v = buf[r++] & mask;
+                if (v <= max) { if (out) out[i] = (int)v; ++i; }
+            }
+            *m.pos += r;
+            *s_prog = i;
+        }
+        __syncthreads();
+        if (*s_prog >= count) break;
     }
     __syncthreads();
 }
@@ -112,14 +154,15 @@ __device__ __forceinline__ void rhccq_mb_sum_vec(long long* v, int cnt, long lon
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int t = 0; t < RHCCQ_MB_MAXT; ++t) {
-        if (t < cnt) {
-            long long x = 0;
-            for (int w = 0; w < nwarp; ++w) x += sll[w * RHCCQ_MB_MAXT + t];
-            v[t] = x;
-        }
+    if ((int)threadIdx.x < cnt) {                                  // one thread per entry adds the warps' partial sums
+        long long x = 0;
+        for (int w = 0; w < nwarp; ++w) x += sll[w * RHCCQ_MB_MAXT + threadIdx.x];
+        sll[RHCCQ_MAX_WARPS * RHCCQ_MB_MAXT - RHCCQ_MB_MAXT + threadIdx.x] = x;       // (the last warp slot is free: nwarp <= 16 here)
     }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < RHCCQ_MB_MAXT; ++t)
+        if (t < cnt) v[t] = sll[RHCCQ_MAX_WARPS * RHCCQ_MB_MAXT - RHCCQ_MB_MAXT + t];
 #endif
 }
 
@@ -206,7 +249,10 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
     unsigned long long* s_chunk = reinterpret_cast<unsigned long long*>(s_raw);         // [RHCCQ_MB_THREADS]
     uint32_t* s_xs = reinterpret_cast<uint32_t*>(s_raw + RHCCQ_MB_THREADS * 8);         // [RHCCQ_MB_SEED_CAP]
     uint32_t* s_closest = s_xs + RHCCQ_MB_SEED_CAP;                                     // [RHCCQ_MB_SEED_CAP]
+    uint32_t* s_rbuf = reinterpret_cast<uint32_t*>(s_raw) + 1024;       // 624 raw generator outputs, beside a 1000-int array (never while the seeding arrays live)
     __shared__ double s_rv[RHCCQ_MB_MAXT];
+    __shared__ int s_prog;
+    __shared__ uint32_t s_rvraw[2 * RHCCQ_MB_MAXT * RHCCQ_MB_SEED_GROUP];
     __shared__ int s_cand[RHCCQ_MB_MAXT];
     __shared__ double s_val;
     const int n_all = B.pal_cnt[p];
@@ -253,12 +299,10 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
     batch = n < RHCCQ_MB_BATCH ? n : RHCCQ_MB_BATCH;
     const int init_size = rhccq_mb_init_size(n, k);
     // ---- RandomState(42); validation indices are drawn and dropped (n_init == 1); init subset
-    if (threadIdx.x == 0) {
-        rhccq_mt_seed(mt, 42u);
-        for (int i = 0; i < init_size; ++i) rhccq_mt_below(mt, (uint32_t)(n - 1));              // _kmeans.py:2110
-        if (init_size < n) for (int i = 0; i < init_size; ++i) W.sub[i] = (int)rhccq_mt_below(mt, (uint32_t)(n - 1));
-    }
-    if (init_size >= n) RHCCQ_PAR_FOR(i, n) W.sub[i] = i;
+    if (threadIdx.x == 0) rhccq_mt_seed(mt, 42u);
+    rhccq_mt_below_seq(mt, (uint32_t)(n - 1), init_size, nullptr, s_rbuf, &s_prog);    // _kmeans.py:2110
+    if (init_size < n) rhccq_mt_below_seq(mt, (uint32_t)(n - 1), init_size, W.sub, s_rbuf, &s_prog);
+    else RHCCQ_PAR_FOR(i, n) W.sub[i] = i;
     __syncthreads();
     const int ns = init_size;
     // colours of the subset, contiguous (the k-means++ passes below read them k * (T + 2) times)
@@ -299,7 +343,17 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         unsigned long long total;
         const unsigned long long run0 = rhccq_block_excl_scan<unsigned long long>(chunk_sum, &total, reinterpret_cast<unsigned long long*>(s_ll));
         chunk_incl[threadIdx.x] = run0 + chunk_sum;
-        if (threadIdx.x == 0) for (int t = 0; t < T; ++t) s_rv[t] = rhccq_mt_double(mt);        // uniform(size=T), in order
+        // uniform(size=T) of this step: the raw outputs of RHCCQ_MB_SEED_GROUP steps are drawn together by the whole
+        // CTA (nothing else consumes the stream during the seeding), two per double, in order
+        const int gi = (c - 1) % RHCCQ_MB_SEED_GROUP;
+        if (gi == 0) {
+            const int steps = k - c < RHCCQ_MB_SEED_GROUP ? k - c : RHCCQ_MB_SEED_GROUP;
+            rhccq_mt_fill_raw(mt, s_rvraw, 2 * T * steps);
+        }
+        RHCCQ_PAR_FOR(t, T) {
+            const uint32_t a = s_rvraw[2 * (gi * T + t)] >> 5, b = s_rvraw[2 * (gi * T + t) + 1] >> 6;
+            s_rv[t] = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+        }
         __syncthreads();
         RHCCQ_PAR_FOR(t, T) {                                      // the T searches side by side
             // first j with cum[j] >= rv, cum = running sum of `closest`: first the chunk whose running sum gets
@@ -350,6 +404,12 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                 const double pi = __ddiv_rn(1.0, (double)n);
                 double run = 0.0;
                 for (int i = 0; i < n; ++i) { run = __dadd_rn(run, pi); W.cdf[i] = run; }
+                s_val = run;
+            }
+            __syncthreads();
+            {                                                       // cdf /= cdf[-1], once instead of in every search step
+                const double last = s_val;
+                RHCCQ_PAR_FOR(i, n) W.cdf[i] = __ddiv_rn(W.cdf[i], last);
             }
         } while (0);
         __syncthreads();
@@ -362,7 +422,6 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         return;
     }
     // ---- mini-batch steps (_kmeans.py:2160-2215)
-    const double cdf_last = W.cdf[n - 1];
     const long long n_steps = (100LL * n) / batch;
     int n_since = 0, no_improvement = 0;                            // rank 0's bookkeeping
     bool have_ewa = false, have_min = false;
@@ -383,10 +442,14 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
             }
             __syncthreads();
             RHCCQ_PAR_FOR(i, batch) {
+                // searchsorted(cdf / last, u, side='right'): first g with cdf[g] > u. The cdf is that of n equal
+                // weights, so u * n is at most a step or two off; the walk makes the answer exact wherever it starts
                 const double u = s_own[i];
-                int lo = 0, hi = n;                                // searchsorted(cdf / last, u, side='right')
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ddiv_rn(W.cdf[mid], cdf_last) <= u) lo = mid + 1; else hi = mid; }
-                bidx[i] = lo < n ? lo : n - 1;
+                int g = (int)(u * (double)n);
+                g = g < 0 ? 0 : (g > n - 1 ? n - 1 : g);
+                while (g > 0 && W.cdf[g - 1] > u) --g;
+                while (g < n && W.cdf[g] <= u) ++g;
+                bidx[i] = g < n ? g : n - 1;
             }
             // _random_reassign (:2039-2054)
             n_since += batch;
@@ -449,9 +512,11 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         }
         rhccq_cluster_sync();
         if (rank == 0) {
+            RHCCQ_PAR_FOR(i, batch) s_own[i] = own_g[i];
+            __syncthreads();
             if (threadIdx.x == 0) {                                 // inertia in batch order
                 double in = 0.0;
-                for (int i = 0; i < batch; ++i) in = __dadd_rn(in, own_g[i]);
+                for (int i = 0; i < batch; ++i) in = __dadd_rn(in, s_own[i]);
                 s_val = in;
             }
             __syncthreads();
@@ -480,13 +545,28 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                     cnt = rhccq_block_sum<int>(cnt, s_i);
                 }
                 __syncthreads();
+                int* s_perm = reinterpret_cast<int*>(s_raw);            // (the batch's values are consumed: the buffer is free)
                 if (cnt > 0) {
-                    if (threadIdx.x == 0) {                             // choice(batch, replace=False, size=cnt) == permutation(batch)[:cnt]
-                        for (int i = 0; i < batch; ++i) W.perm[i] = i;
-                        for (int i = batch - 1; i >= 1; --i) {
-                            const int j = (int)rhccq_mt_below(mt, (uint32_t)i);
-                            const int t = W.perm[i]; W.perm[i] = W.perm[j]; W.perm[j] = t;
+                    // choice(batch, replace=False, size=cnt) == permutation(batch)[:cnt]: Fisher-Yates from the top, one
+                    // thread, in shared memory; the raw outputs it consumes are produced a generator block at a time
+                    // by the whole CTA
+                    RHCCQ_PAR_FOR(i, batch) s_perm[i] = i;
+                    if (threadIdx.x == 0) s_prog = batch - 1;
+                    while (true) {
+                        const int avail = rhccq_mt_peek_block(mt, s_rbuf);
+                        if (threadIdx.x == 0) {
+                            int i = s_prog, r = 0;
+                            while (i >= 1 && r < avail) {
+                                uint32_t mask = (uint32_t)i;
+                                mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+                                const uint32_t v = s_rbuf[r++] & mask;
+                                if (v <= (uint32_t)i) { const int t = s_perm[i]; s_perm[i] = s_perm[v]; s_perm[v] = t; --i; }
+                            }
+                            *mt.pos += r;
+                            s_prog = i;
                         }
+                        __syncthreads();
+                        if (s_prog < 1) break;
                     }
                     // rank of every flagged centre among the flagged ones, ascending
                     int* rank = reinterpret_cast<int*>(W.skey);
@@ -494,7 +574,7 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                     __syncthreads();
                     rhccq_block_excl_scan_array<int>(rank, k, s_i);
                     RHCCQ_PAR_FOR(q, k) if (W.flag[q]) {
-                        const uint32_t c = keys[W.nb[bidx[W.perm[rank[q]]]]];
+                        const uint32_t c = keys[W.nb[bidx[s_perm[rank[q]]]]];
                         cen_new[3 * q] = (double)rhccq_key_r(c); cen_new[3 * q + 1] = (double)rhccq_key_g(c); cen_new[3 * q + 2] = (double)rhccq_key_b(c);
                     }
                 }
