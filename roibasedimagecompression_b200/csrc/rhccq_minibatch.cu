@@ -556,11 +556,22 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                         const int avail = rhccq_mt_peek_block(mt, s_rbuf);
                         if (threadIdx.x == 0) {
                             int i = s_prog, r = 0;
+                            const uint32_t* __restrict__ rb = s_rbuf;       // (disjoint from the permutation: lets the raw
+                            int* __restrict__ pm = s_perm;                  //  values be fetched eight at a time, ahead of the swaps)
                             while (i >= 1 && r < avail) {
-                                uint32_t mask = (uint32_t)i;
-                                mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-                                const uint32_t v = s_rbuf[r++] & mask;
-                                if (v <= (uint32_t)i) { const int t = s_perm[i]; s_perm[i] = s_perm[v]; s_perm[v] = t; --i; }
+                                uint32_t raw8[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) raw8[j] = r + j < avail ? rb[r + j] : 0u;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    if (i >= 1 && r < avail) {
+                                        uint32_t mask = (uint32_t)i;
+                                        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+                                        const uint32_t v = raw8[j] & mask;
+                                        ++r;
+                                        if (v <= (uint32_t)i) { const int t = pm[i]; pm[i] = pm[v]; pm[v] = t; --i; }
+                                    }
+                                }
                             }
                             *mt.pos += r;
                             s_prog = i;
