@@ -119,8 +119,11 @@ int rhccq_palette_minibatch(const uint32_t* pal_keys, const int32_t* pal_off, co
 /* ------------------------------------------------------------------ a3/a4: cluster -> new palette rows
  * Replaces clustering.py:253-355 and split_large_cluster (:720-775): black rows first, clusters of at
  * most max_cpc[p] colours one row each in ascending label order, larger clusters split recursively by
- * KMeans(k, random_state=42, n_init='auto') in the exact arithmetic of oracle/kmeans_restated.py,
- * leaves in depth-first label order.  leaf[row] = new palette row; n_leaves[p] = new palette size.
+ * KMeans(k, random_state=42, n_init='auto') — scikit-learn's float64 arithmetic, decision for decision,
+ * as restated in oracle/kmeans_sklearn.c — leaves in depth-first label order.  leaf[row] = new palette
+ * row; n_leaves[p] = new palette size.  max_cpc[p] = -k runs that KMeans(k) once over the whole palette
+ * (the operator of clustering.py:751-752 by itself): leaf[row] = rank of the row's label among the
+ * non-empty labels.
  * rng: the rhccq_kmeans_rng_fill stream on the device.  n_clusters (may be NULL): the counters of
  * rhccq_palette_dbscan; a negative one is copied to n_leaves[p] and the problem is skipped. */
 int rhccq_palette_split(const uint32_t* pal_keys, const int32_t* pal_off, const int32_t* pal_cnt,

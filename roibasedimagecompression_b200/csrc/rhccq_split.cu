@@ -3,8 +3,8 @@
 //   rhccq_k_palette_split    small clusters -> one entry each, large clusters ->
 //                            recursive K-Means split
 //                            (/root/reference/encoder/compression/clustering.py:253-355, :720-775),
-//                            K-Means in the exact arithmetic of oracle/kmeans_restated.py
-//                            (which cites the scikit-learn lines it restates).
+//                            K-Means with the decisions of scikit-learn's float64 arithmetic as
+//                            restated in oracle/kmeans_sklearn.c (which cites the lines it follows).
 //
 // Shape of the work.  A stage-1 problem is ~3 000 colours: one top-level
 // K-Means (k = 12..25, ~25 Lloyd iterations) followed by ~10 small K-Means
@@ -21,9 +21,9 @@
 // The working set (20 bytes per colour) lives in shared memory when it fits
 // (two CTAs per SM for palettes of up to ~4 000 colours), otherwise in the
 // caller's global workspace.  Nothing here touches HBM beyond reading the
-// palette and writing one int per row: the kernel is bound by FP64 issue
-// (distances are evaluated in IEEE double without contraction, like the oracle)
-// and by barrier latency, not by memory bandwidth.
+// palette and writing one int per row (and, for the rare decisions that must be
+// re-evaluated in sequential float64, a scratch area in the global workspace):
+// the kernel is bound by FP64 issue and by barrier latency, not by memory bandwidth.
 #include "rhccq_common.cuh"
 #include "rhccq_kernels.h"
 
@@ -43,6 +43,7 @@ __device__ unsigned long long rhccq_split_prof[8];
 #endif
 #define RHCCQ_SPLIT_THREADS 256
 #define RHCCQ_KM_MAXT 12               // 2 + int(log(k)) for k < 22027
+#define RHCCQ_KM_CAND 16               // ints per candidate table: RHCCQ_KM_MAXT candidates + 2 flags
 #define RHCCQ_KC 128                   // centres of a CTA-level K-Means kept in shared memory
 #define RHCCQ_KW 8                     // centres of a warp-level K-Means
 #define RHCCQ_WARP_RANGE 1024          // largest range a single warp splits
@@ -226,7 +227,37 @@ __device__ __forceinline__ unsigned long long rhccq_warp_incl_scan_u64(unsigned 
     return v;
 }
 
-// ---------------------------------------------------------------- K-Means (exact arithmetic)
+// ---------------------------------------------------------------- K-Means in scikit-learn's arithmetic
+//
+// The labels must be those of KMeans(k, random_state=42, n_init='auto').fit_predict(colours) of
+// scikit-learn 1.9.0 as restated operation by operation in oracle/kmeans_sklearn.c (which cites the
+// scikit-learn / numpy / OpenBLAS lines and summation orders it follows).  Every DECISION of the
+// algorithm — which candidate a random draw selects, which candidate seeds a centre, which centre a
+// colour is nearest to, whether the centre shift is within the tolerance — is taken exactly as that
+// arithmetic takes it.  The values the decisions are taken on are sequential float64 sums
+// (np.cumsum, the M step in sample order, ddot / dgemv of the seeding), which a GPU cannot evaluate
+// quickly; so every decision is first evaluated on an exact-integer / well-conditioned form whose
+// distance from the float64 value is bounded, and only a decision that falls inside that bound is
+// re-evaluated in the sequential float64 form (by one thread, on scratch in global memory):
+//
+//   seeding   squared distances of uint8 colours are integers; the float64 distances of the centred
+//             data differ from them by < 1e-9 each.  Candidate = first index whose cumulative sum
+//             reaches r * pot: decided on the integer sums unless r * pot lies within
+//             2 n (1e-9 + ulp(pot)) of a cumulative sum.  Best candidate = smallest potential: decided
+//             on the integer potentials unless two different colours tie.
+//   E step    centres from exact integer sums, c = S / n - mean, are within eps_c of the float64
+//             centres (sequential sum of centred colours times 1/n); a colour whose two best scores
+//             are closer than the margin that eps_c allows is re-evaluated on the float64 centres.
+//   tolerance decided on the integer-derived values unless |shift - tol| is inside their error band.
+//
+// The bounds are derived next to each use; RHCCQ_KM_FORCE_EXACT (test builds) makes every decision
+// take the float64 path, and tests/ runs both builds against the oracle.
+#define RHCCQ_GEMM_P 192               // OpenBLAS DGEMM_DEFAULT_P (SkylakeX): Lloyd's dgemm is cut into blocks of k
+#define RHCCQ_GEMM_UNROLL_M 16
+#define RHCCQ_NBMAX_T 2048             // row block of OpenBLAS dgemv_t
+#define RHCCQ_SK_CHUNK 256             // samples per E-step chunk (sklearn/cluster/_k_means_common.pyx:13)
+#define RHCCQ_EX_PER_ROW 10            // doubles of global scratch per palette row (see rhccq_km_arrays::ex)
+
 __device__ __forceinline__ int rhccq_kmeans_local_trials(int k) {   // 2 + int(log(k)), sklearn/_kmeans.py:226
     const int e[] = {3, 8, 21, 55, 149, 404, 1097, 2981, 8104, 22027, 59875, 162755, 442414, 1202605};
     int t = 2;
@@ -239,70 +270,255 @@ __device__ __forceinline__ int rhccq_kmeans_local_trials(int k) {   // 2 + int(l
 template <class Cfg> struct rhccq_km_arrays {
     uint32_t* x;                        // colour at every position
     uint32_t* closest;                  // seeding: squared distance to the nearest chosen centre
-    typename Cfg::cum_t* cum;           // seeding: inclusive cumulative sum of closest over the range
+    typename Cfg::cum_t* cum;           // seeding: inclusive cumulative sum of closest over the range;
+                                        // Lloyd: second label array and the list of undecided positions
     typename Cfg::idx_t* label;         // Lloyd: cluster of every position
+    double* ex;                         // global scratch of the float64 re-evaluations, RHCCQ_EX_PER_ROW per position
 };
 // ... and the per-call centre tables (k entries, private to the calling group).
 struct rhccq_km_centers {
-    double* center;                     // [3k]
+    double* center;                     // [3k]  centred coordinates
     double* center_new;                 // [3k]
     double* term;                       // [k]
+    double* csn;                        // [k]   |c|^2 as einsum('ij,ij->i') evaluates it
     int* sums;                          // [3k]
     int* cnt;                           // [k]
-    int* hist;                          // [nsub * 4k] per-warp (r, g, b, count) accumulators, or nullptr
-    int* cand;                          // [RHCCQ_KM_MAXT]
+    int* hist;                          // unused
+    int* cand;                          // [RHCCQ_KM_MAXT + 2]: candidates, then two flag / counter slots
     int* poff;                          // [k * nsub] offsets of the counting partition, or nullptr (sort instead)
     int* wl;                            // worklist counter of the pruned E step, or nullptr (evaluate every centre)
 };
 
-__device__ __forceinline__ double rhccq_dist3(double x0, double x1, double x2, const double* c) {
-    const double d0 = __dsub_rn(x0, c[0]), d1 = __dsub_rn(x1, c[1]), d2 = __dsub_rn(x2, c[2]);
-    return __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
+__device__ __forceinline__ double rhccq_sk_norm3(double c0, double c1, double c2) {     // (c0^2 + c2^2) + c1^2
+    return __dadd_rn(__dadd_rn(__dmul_rn(c0, c0), __dmul_rn(c2, c2)), __dmul_rn(c1, c1));
+}
+__device__ __forceinline__ double rhccq_sk_dot_gemm(double x0, double x1, double x2, double c0, double c1, double c2) {
+    return __fma_rn(x2, c2, __fma_rn(x1, c1, __dmul_rn(x0, c0)));
+}
+__device__ __forceinline__ double rhccq_sk_dot_edge(double x0, double x1, double x2, double c0, double c1, double c2) {
+    return __fma_rn(x2, c2, __dadd_rn(__dmul_rn(x0, c0), __dmul_rn(x1, c1)));
+}
+__device__ __forceinline__ double rhccq_sk_dot_gemv(double x0, double x1, double x2, double c0, double c1, double c2) {
+    return __fma_rn(x2, c2, __fma_rn(x0, c0, __dmul_rn(x1, c1)));
+}
+struct rhccq_sk_pt { double x0, x1, x2; };
+__device__ __forceinline__ rhccq_sk_pt rhccq_sk_centred(uint32_t c, const double (&mean)[3]) {
+    rhccq_sk_pt p;
+    p.x0 = __dsub_rn((double)rhccq_key_r(c), mean[0]);
+    p.x1 = __dsub_rn((double)rhccq_key_g(c), mean[1]);
+    p.x2 = __dsub_rn((double)rhccq_key_b(c), mean[2]);
+    return p;
+}
+// _euclidean_distances(centre, X, squared=True) of the seeding: max(0, ((-2 x.c) + |c|^2) + |x|^2);
+// the first centre's product goes through dgemv, the candidates' through dgemm
+__device__ __forceinline__ double rhccq_sk_seed_dist(bool first, const rhccq_sk_pt& p, const double* c) {
+    const double dot = first ? rhccq_sk_dot_gemv(p.x0, p.x1, p.x2, c[0], c[1], c[2])
+                             : rhccq_sk_dot_gemm(c[0], c[1], c[2], p.x0, p.x1, p.x2);
+    double d = __dmul_rn(-2.0, dot);
+    d = __dadd_rn(d, rhccq_sk_norm3(c[0], c[1], c[2]));
+    d = __dadd_rn(d, rhccq_sk_norm3(p.x0, p.x1, p.x2));
+    return d > 0.0 ? d : 0.0;
+}
+// rows [lo, hi) of Lloyd's dgemm result (cluster index) that the 4-row edge kernel of a block after the
+// first computes (OpenBLAS level3.c blocking of M = k); empty for k <= RHCCQ_GEMM_P
+__device__ __forceinline__ void rhccq_sk_edge_rows(int k, int& lo, int& hi) {
+    lo = hi = 0;
+    if (k <= RHCCQ_GEMM_P) return;
+    int is = 0, min_i = k;
+    for (;;) {
+        min_i = k - is;
+        if (min_i >= 2 * RHCCQ_GEMM_P) min_i = RHCCQ_GEMM_P;
+        else if (min_i > RHCCQ_GEMM_P) min_i = ((min_i / 2 + RHCCQ_GEMM_UNROLL_M - 1) / RHCCQ_GEMM_UNROLL_M) * RHCCQ_GEMM_UNROLL_M;
+        if (is + min_i >= k) break;
+        is += min_i;
+    }
+    if (is > 0 && (min_i & 4)) { lo = is + (min_i & ~15) + (min_i & 8); hi = lo + 4; }
+}
+// Score of Lloyd's E step, |c|^2 - 2 x.c, of sample i (position inside the call) against centre j
+__device__ __forceinline__ double rhccq_sk_score(const rhccq_sk_pt& p, const double* c, double csn, bool edge) {
+    const double acc = edge ? rhccq_sk_dot_edge(p.x0, p.x1, p.x2, c[0], c[1], c[2])
+                            : rhccq_sk_dot_gemm(p.x0, p.x1, p.x2, c[0], c[1], c[2]);
+    return __fma_rn(-2.0, acc, csn);
+}
+__device__ __forceinline__ bool rhccq_sk_edge_sample(int i, int n) {   // inside a group of 12 of its chunk of 256
+    const int s = i & ~(RHCCQ_SK_CHUNK - 1), r = i - s;
+    const int m = n - s < RHCCQ_SK_CHUNK ? n - s : RHCCQ_SK_CHUNK;
+    return r < (m / 12) * 12;
 }
 
-// First minimum over centres of ((d0^2 + d1^2) + d2^2) in IEEE double, for NB points at once: every
-// centre is loaded once per NB points, and the NB distance chains are independent (the FP64 pipe is
-// the bound of this kernel).
+// ---- single-thread float64 kernels of the libraries underneath scikit-learn (oracle/kmeans_sklearn.c)
+// OpenBLAS ddot(v, ones)
+__device__ __noinline__ double rhccq_sk_ddot_ones(const double* x, int n) {
+    double dot = 0.0;
+    const int n1 = n & -16;
+    int i = 0;
+    if (n1) {
+        double a[4][8];
+        for (int q = 0; q < 4; ++q) for (int l = 0; l < 8; ++l) a[q][l] = 0.0;
+        const int n32 = n1 & ~31;
+        for (; i < n32; i += 32)
+            for (int q = 0; q < 4; ++q) for (int l = 0; l < 8; ++l) a[q][l] = __dadd_rn(a[q][l], x[i + 8 * q + l]);
+        double b[4][4];
+        for (int q = 0; q < 4; ++q) for (int l = 0; l < 4; ++l) b[q][l] = __dadd_rn(a[q][l], a[q][l + 4]);
+        for (; i < n1; i += 16)
+            for (int q = 0; q < 4; ++q) for (int l = 0; l < 4; ++l) b[q][l] = __dadd_rn(b[q][l], x[i + 4 * q + l]);
+        double c[4];
+        for (int l = 0; l < 4; ++l) c[l] = __dadd_rn(__dadd_rn(__dadd_rn(b[0][l], b[1][l]), b[2][l]), b[3][l]);
+        dot = __dadd_rn(__dadd_rn(c[0], c[2]), __dadd_rn(c[1], c[3]));
+    }
+    for (; i < n; ++i) dot = __dadd_rn(dot, x[i]);
+    return dot;
+}
+// OpenBLAS dgemv_t(D, ones), one column of length m: element i is min(f[i], distance of i to `cand`)
+// (cand == nullptr: f[i] itself); lanes = 4 or 2 (see rhccq_sk_gemv_lanes)
+struct rhccq_sk_col {
+    const double* f; const uint32_t* x; const double* cand; const double* mean;
+    __device__ __forceinline__ double operator()(int i) const {
+        const double a = f[i];
+        if (cand == nullptr) return a;
+        const double m3[3] = {mean[0], mean[1], mean[2]};
+        const double d = rhccq_sk_seed_dist(false, rhccq_sk_centred(x[i], m3), cand);
+        return a < d ? a : d;
+    }
+};
+__device__ __noinline__ double rhccq_sk_dgemv_t_ones(const rhccq_sk_col& v, int m, int lanes) {
+    double y = 0.0;
+    const int m3 = m & 3, m2 = (m & (RHCCQ_NBMAX_T - 1)) - m3;
+    int m1 = m & -4, nb = RHCCQ_NBMAX_T, at = 0;
+    while (nb == RHCCQ_NBMAX_T) {
+        m1 -= nb;
+        if (m1 < 0) { if (m2 == 0) break; nb = m2; }
+        double blk;
+        if (lanes == 4) {
+            double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+            for (int i = 0; i < nb; i += 4) {
+                l0 = __dadd_rn(l0, v(at + i)); l1 = __dadd_rn(l1, v(at + i + 1));
+                l2 = __dadd_rn(l2, v(at + i + 2)); l3 = __dadd_rn(l3, v(at + i + 3));
+            }
+            blk = __dadd_rn(__dadd_rn(l0, l2), __dadd_rn(l1, l3));
+        } else {
+            double l0 = 0, l1 = 0;
+            for (int i = 0; i < nb; i += 2) { l0 = __dadd_rn(l0, v(at + i)); l1 = __dadd_rn(l1, v(at + i + 1)); }
+            blk = __dadd_rn(l0, l1);
+        }
+        y = __dadd_rn(y, blk);
+        at += nb;
+    }
+    if (m3 == 3) y = __dadd_rn(y, __dadd_rn(__dadd_rn(v(at), v(at + 1)), v(at + 2)));
+    else if (m3 == 2) y = __dadd_rn(y, __dadd_rn(v(at), v(at + 1)));
+    else if (m3 == 1) y = __dadd_rn(y, v(at));
+    return y;
+}
+__device__ __forceinline__ int rhccq_sk_gemv_lanes(int j, int t) {   // column groups of 4, a pair if (t & 2), a single
+    const int g = (t >> 2) * 4;
+    if (j < g) return 4;
+    return ((t & 2) && j - g < 2) ? 2 : 4;
+}
+// numpy's pairwise summation of a contiguous vector
+__device__ __noinline__ double rhccq_sk_np_sum(const double* a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(rhccq_sk_np_sum(a, n2), rhccq_sk_np_sum(a + n2, n - n2));
+}
+// Float64 centres of the clusters of `lab` (M step in sample order, _average_centers): E[4j .. 4j+2]
+// centre, E[4j+3] = |c|^2.  One thread.
+template <class Cfg>
+__device__ __noinline__ void rhccq_sk_all_centers(const uint32_t* x, const typename Cfg::idx_t* lab, int n, int k,
+                                                  const double* mean, double* E) {
+    const double m3[3] = {mean[0], mean[1], mean[2]};
+    for (int q = 0; q < 4 * k; ++q) E[q] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int l = (int)(lab[i] & (typename Cfg::idx_t)~Cfg::FLAG);
+        const rhccq_sk_pt p = rhccq_sk_centred(x[i], m3);
+        E[4 * l] = __dadd_rn(E[4 * l], p.x0); E[4 * l + 1] = __dadd_rn(E[4 * l + 1], p.x1);
+        E[4 * l + 2] = __dadd_rn(E[4 * l + 2], p.x2); E[4 * l + 3] = __dadd_rn(E[4 * l + 3], 1.0);
+    }
+}
+// _average_centers on a table of (sum0, sum1, sum2, weight) rows, in place; then weight <- |c|^2
+__device__ __noinline__ void rhccq_sk_average(double* E, int k) {
+    int am = 0;
+    for (int j = 1; j < k; ++j) if (E[4 * j + 3] > E[4 * am + 3]) am = j;
+    for (int j = 0; j < k; ++j) {
+        if (E[4 * j + 3] > 0.0) {
+            const double alpha = __ddiv_rn(1.0, E[4 * j + 3]);
+            for (int d = 0; d < 3; ++d) E[4 * j + d] = __dmul_rn(E[4 * j + d], alpha);
+        } else {
+            for (int d = 0; d < 3; ++d) E[4 * j + d] = E[4 * am + d];
+        }
+    }
+    for (int j = 0; j < k; ++j) E[4 * j + 3] = rhccq_sk_norm3(E[4 * j], E[4 * j + 1], E[4 * j + 2]);
+}
+
+// First minimum over centres of the E-step score for RHCCQ_EB points at once (every centre is loaded once
+// per RHCCQ_EB points and the chains are independent: the FP64 pipe bounds this kernel).  und[u] is set
+// when another centre's score is within `margin` of the best one (margin 0: never).
 #define RHCCQ_EB 4
-__device__ __forceinline__ void rhccq_nearest_centers(const uint32_t (&c)[RHCCQ_EB], const double* center, int k,
-                                                      int (&bi)[RHCCQ_EB]) {
-    double x0[RHCCQ_EB], x1[RHCCQ_EB], x2[RHCCQ_EB], best[RHCCQ_EB];
+__device__ __forceinline__ void rhccq_nearest_centers(const uint32_t (&c)[RHCCQ_EB], const double (&mean)[3],
+                                                      const double* center, const double* csn, int k, double margin,
+                                                      int (&bi)[RHCCQ_EB], bool (&und)[RHCCQ_EB]) {
+    rhccq_sk_pt p[RHCCQ_EB];
+    double best[RHCCQ_EB], bpm[RHCCQ_EB], sec[RHCCQ_EB];
 #pragma unroll
     for (int u = 0; u < RHCCQ_EB; ++u) {
-        x0[u] = (double)rhccq_key_r(c[u]); x1[u] = (double)rhccq_key_g(c[u]); x2[u] = (double)rhccq_key_b(c[u]);
-        best[u] = rhccq_dist3(x0[u], x1[u], x2[u], center);
+        p[u] = rhccq_sk_centred(c[u], mean);
+        best[u] = rhccq_sk_score(p[u], center, csn[0], false);
+        bpm[u] = __dadd_rn(best[u], margin);
+        sec[u] = 1.0e300;
         bi[u] = 0;
     }
     for (int q = 1; q < k; ++q) {
-        const double c0 = center[3 * q], c1 = center[3 * q + 1], c2 = center[3 * q + 2];
+        const double c0 = center[3 * q], c1 = center[3 * q + 1], c2 = center[3 * q + 2], cs = csn[q];
 #pragma unroll
         for (int u = 0; u < RHCCQ_EB; ++u) {
-            const double d0 = __dsub_rn(x0[u], c0), d1 = __dsub_rn(x1[u], c1), d2 = __dsub_rn(x2[u], c2);
-            const double d = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-            if (d < best[u]) { best[u] = d; bi[u] = q; }
+            const double d = __fma_rn(-2.0, __fma_rn(p[u].x2, c2, __fma_rn(p[u].x1, c1, __dmul_rn(p[u].x0, c0))), cs);
+            if (d < bpm[u]) {
+                if (d < best[u]) { sec[u] = best[u]; best[u] = d; bi[u] = q; bpm[u] = __dadd_rn(d, margin); }
+                else if (d < sec[u]) sec[u] = d;
+            }
         }
     }
+#pragma unroll
+    for (int u = 0; u < RHCCQ_EB; ++u) und[u] = sec[u] < bpm[u];
+}
+// the same decision on the float64 centres E (one point, every centre, the dgemm edge rows included)
+__device__ __forceinline__ int rhccq_nearest_exact(uint32_t c, const double (&mean)[3], const double* E, int k,
+                                                   int i, int n, int e_lo, int e_hi) {
+    const rhccq_sk_pt p = rhccq_sk_centred(c, mean);
+    const bool es = e_hi > e_lo && rhccq_sk_edge_sample(i, n);
+    double best = rhccq_sk_score(p, E, E[3], es && 0 >= e_lo && 0 < e_hi);
+    int bi = 0;
+    for (int q = 1; q < k; ++q) {
+        const double d = rhccq_sk_score(p, E + 4 * q, E[4 * q + 3], es && q >= e_lo && q < e_hi);
+        if (d < best) { best = d; bi = q; }
+    }
+    return bi;
 }
 
-// M-step accumulation of one point into a table of (r, g, b, count) rows / into the sums and counts.
-// Plain shared-memory atomics: summing equal labels inside the warp first (match_any + reduce_add) was
-// measured twice as slow on B200 as letting the atomic unit serialise the conflicts.
-__device__ __forceinline__ void rhccq_acc_rows(int* rows, int stride, int bi, uint32_t c, bool valid) {
-    if (valid) {
-        int* h = rows + stride * bi;
-        atomicAdd(h, rhccq_key_r(c)); atomicAdd(h + 1, rhccq_key_g(c)); atomicAdd(h + 2, rhccq_key_b(c)); atomicAdd(h + 3, 1);
-    }
-}
-__device__ __forceinline__ void rhccq_acc_split(int* sums, int* cnt, int bi, uint32_t c, bool valid) {
-    if (valid) {
-        atomicAdd(&sums[3 * bi], rhccq_key_r(c)); atomicAdd(&sums[3 * bi + 1], rhccq_key_g(c));
-        atomicAdd(&sums[3 * bi + 2], rhccq_key_b(c)); atomicAdd(&cnt[bi], 1);
-    }
-}
+#ifdef RHCCQ_KM_FORCE_EXACT
+#define RHCCQ_KM_FORCED 1
+#else
+#define RHCCQ_KM_FORCED 0
+#endif
 
 // Labels of KMeans(k, random_state=42, n_init='auto').fit_predict on the n colours at positions
-// [lo, lo + n), as restated in oracle/kmeans_restated.py.  On return A.label holds the labels and
-// C.cnt the cluster sizes.  Group-uniform control flow; every thread of the group must call.
+// [lo, lo + n).  On return A.label holds the labels and C.cnt the cluster sizes.  Group-uniform control
+// flow; every thread of the group must call.
 template <class G, class Cfg>
 __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<Cfg>& A, const rhccq_km_centers& C, int lo, int n, int k,
                              const double* __restrict__ rng) {
@@ -312,15 +528,18 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
     const uint32_t* x = A.x + lo;
     uint32_t* closest = A.closest + lo;
     cum_t* cum = A.cum + lo;
-    idx_t* label = A.label + lo;
+    double* ex = A.ex + (size_t)RHCCQ_EX_PER_ROW * lo;              // float64 scratch of this call
+    int* flag = C.cand + RHCCQ_KM_MAXT;                             // two group-shared ints
     // contiguous chunk of the caller (scans need a fixed element order)
     const int per = (n + gsz - 1) / gsz;
     const int c_lo = tid * per < n ? tid * per : n;
     const int c_hi = c_lo + per < n ? c_lo + per : n;
 
     RHCCQ_PROF_T0();
-    // ---- k-means++ seeding (kmeans_restated.kmeans_pp_seeds)
+    // ---- k-means++ seeding (sklearn/cluster/_kmeans.py:216-282)
     const int T = rhccq_kmeans_local_trials(k);
+    // RandomState.choice(n, p=uniform) walks the normalised cumulative sum of 1/n: floor(u n) for this u
+    // and every n up to 20 000 (tests/test_oracle_golden.py checks the whole range against numpy's form)
     int first = (int)__dmul_rn(rng[0], (double)n);
     if (first > n - 1) first = n - 1;
     long long acc[RHCCQ_KM_MAXT];
@@ -340,17 +559,26 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
         acc[0] = (long long)chunk_sum;
         for (int d = 0; d < 3; ++d) { acc[1 + d] = p1[d]; acc[4 + d] = p2[d]; }
         g.sum_vec(acc, 7);
-        for (int q = tid; q < 3; q += gsz) C.center[q] = (double)((cf >> (16 - 8 * q)) & 255u);
     }
     long long pot = acc[0];
     const long long S1[3] = {acc[1], acc[2], acc[3]}, S2[3] = {acc[4], acc[5], acc[6]};
-    int ri = 1;
+    // X.mean(axis=0): the sums are exact integers, one rounding in the division
+    const double mean[3] = {__ddiv_rn((double)S1[0], (double)n), __ddiv_rn((double)S1[1], (double)n),
+                            __ddiv_rn((double)S1[2], (double)n)};
+    for (int q = tid; q < 3; q += gsz)
+        C.center[q] = __dsub_rn((double)((x[first] >> (16 - 8 * q)) & 255u), mean[q]);
+    int ri = 1, prev_slot = -1;
     for (int c = 1; c < k; ++c) {
+        // ---- candidates: searchsorted(cumsum(closest), r * pot), clipped (:247-252)
+        // |float64 cumulative sum - integer one| <= n (1e-9 + ulp(pot)/2) and the same for r * pot, so the
+        // integer search decides unless r * pot is within und_a of one of the two sums it falls between
+        const double und_a = RHCCQ_KM_FORCED ? 1.0e300
+                                             : __dmul_rn(2.0 * (double)n, __dadd_rn(1.0e-9, __dmul_rn((double)pot, 2.3e-16)));
+        if (tid == 0) flag[0] = 0;
         if (G::kCta) {
-            // Candidates without materialising the cumulative sum: every thread publishes the sum of its chunk;
-            // one warp per trial scans the chunk sums (shuffles), finds the chunk in which the inclusive sum
-            // first reaches r * pot, then the element inside it — the same element a search of the cumulative
-            // array gives (searchsorted(cum, r * pot, side='left'), clipped).  One barrier instead of five.
+            // Without materialising the cumulative sum: every thread publishes the sum of its chunk; one warp
+            // per trial scans the chunk sums (shuffles), finds the chunk in which the inclusive sum first
+            // reaches r * pot, then the element inside it.
             g.csum[tid] = (unsigned long long)chunk_sum;
             g.sync();
             const int E = (gsz + RHCCQ_WARP_SIZE - 1) / RHCCQ_WARP_SIZE;     // chunk sums per lane
@@ -361,6 +589,7 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                 const unsigned long long incl = rhccq_warp_incl_scan_u64(loc);
                 const unsigned m = rhccq_ballot((double)incl >= rv);
                 int found = n - 1;                                  // beyond the total: clipped
+                int und = 1;
                 if (m != 0u) {
                     const int L = __ffs((int)m) - 1;
                     unsigned long long pre = rhccq_shfl(incl - loc, L);
@@ -376,13 +605,23 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                     const int j0 = cix * per < n ? cix * per : n, j1 = j0 + per < n ? j0 + per : n;
                     for (int base = j0; base < j1; base += RHCCQ_WARP_SIZE) {
                         const int j = base + RHCCQ_LANE;
-                        const unsigned long long inc = rhccq_warp_incl_scan_u64(j < j1 ? (unsigned long long)closest[j] : 0ull);
+                        const unsigned long long own = j < j1 ? (unsigned long long)closest[j] : 0ull;
+                        const unsigned long long inc = rhccq_warp_incl_scan_u64(own);
                         const unsigned mm = rhccq_ballot(j < j1 && (double)(pre + inc) >= rv);
-                        if (mm != 0u) { found = base + __ffs((int)mm) - 1; break; }
+                        if (mm != 0u) {
+                            const int w = __ffs((int)mm) - 1;
+                            found = base + w;
+                            const unsigned long long at = pre + rhccq_shfl(inc, w), below = at - rhccq_shfl(own, w);
+                            und = ((double)at - rv < und_a) || (rv - (double)below <= und_a);
+                            break;
+                        }
                         pre += rhccq_shfl(inc, RHCCQ_WARP_SIZE - 1);
                     }
                 }
-                if (RHCCQ_LANE == 0) C.cand[t] = found < n - 1 ? found : n - 1;
+                if (RHCCQ_LANE == 0) {
+                    C.cand[t] = found < n - 1 ? found : n - 1;
+                    if (und) atomicOr(&flag[0], 1);
+                }
             }
             g.sync();
         } else {
@@ -391,7 +630,6 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
             cum_t run = g.template excl_scan<cum_t>(chunk_sum, &total);
             for (int j = c_lo; j < c_hi; ++j) { run += closest[j]; cum[j] = run; }
             g.sync();
-            // candidates: searchsorted(cum, r * pot, side='left'), clipped
             for (int t = tid; t < T; t += gsz) {
                 const double rv = __dmul_rn(rng[ri + t], (double)pot);
                 int l = 0, h = n;                                   // first j with cum[j] >= rv
@@ -399,29 +637,101 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                     const int mid = (l + h) >> 1;
                     if ((double)cum[mid] < rv) l = mid + 1; else h = mid;
                 }
+                int und = 1;
+                if (l < n) {
+                    const double at = (double)cum[l], below = l > 0 ? (double)cum[l - 1] : 0.0;
+                    und = (at - rv < und_a) || (rv - below <= und_a);
+                }
                 C.cand[t] = l < n - 1 ? l : n - 1;
+                if (und) atomicOr(&flag[0], 1);
+            }
+            g.sync();
+        }
+        bool have_f = false;
+        if (flag[0]) {
+            // float64 re-evaluation: closest distances of the centred data to the c centres chosen so far,
+            // the potential as the previous step's BLAS call summed it, np.cumsum, np.searchsorted
+            for (int j = c_lo; j < c_hi; ++j) {
+                const rhccq_sk_pt p = rhccq_sk_centred(x[j], mean);
+                double f = rhccq_sk_seed_dist(true, p, C.center);
+                for (int s = 1; s < c; ++s) { const double d = rhccq_sk_seed_dist(false, p, C.center + 3 * s); f = d < f ? d : f; }
+                ex[j] = f;
+            }
+            have_f = true;
+            g.sync();
+            if (tid == 0) {
+                rhccq_sk_col col; col.f = ex; col.x = x; col.cand = nullptr; col.mean = mean;
+                const double pot_f = prev_slot < 0 ? rhccq_sk_ddot_ones(ex, n)
+                                                   : rhccq_sk_dgemv_t_ones(col, n, rhccq_sk_gemv_lanes(prev_slot, T));
+                double rv[RHCCQ_KM_MAXT];
+                int fnd[RHCCQ_KM_MAXT];
+                for (int t = 0; t < T; ++t) { rv[t] = __dmul_rn(rng[ri + t], pot_f); fnd[t] = -1; }
+                double s = 0.0;
+                int open = T;
+                for (int i = 0; i < n && open > 0; ++i) {
+                    s = __dadd_rn(s, ex[i]);
+                    for (int t = 0; t < T; ++t) if (fnd[t] < 0 && !(s < rv[t])) { fnd[t] = i; --open; }
+                }
+                for (int t = 0; t < T; ++t) C.cand[t] = fnd[t] < 0 ? n - 1 : fnd[t];
             }
             g.sync();
         }
         ri += T;
+        // ---- potentials of the candidates (:255-261), integer form
         uint32_t xc[RHCCQ_KM_MAXT];
+        int cj[RHCCQ_KM_MAXT];
 #pragma unroll
-        for (int t = 0; t < RHCCQ_KM_MAXT; ++t) { acc[t] = 0; xc[t] = t < T ? x[C.cand[t]] : 0u; }
+        for (int t = 0; t < RHCCQ_KM_MAXT; ++t) { acc[t] = 0; cj[t] = t < T ? C.cand[t] : 0; xc[t] = t < T ? x[cj[t]] : 0u; }
         for (int j = c_lo; j < c_hi; ++j) {
-            const uint32_t cj = x[j], o = closest[j];
+            const uint32_t cjx = x[j], o = closest[j];
 #pragma unroll
             for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {
                 if (t < T) {
-                    const uint32_t d = (uint32_t)rhccq_d2(cj, xc[t]);
+                    const uint32_t d = (uint32_t)rhccq_d2(cjx, xc[t]);
                     acc[t] += d < o ? d : o;
                 }
             }
         }
         g.sum_vec(acc, T);
-        int best = 0;
+        int best = 0, tie = 0;
         long long best_pot = acc[0];
 #pragma unroll
         for (int t = 1; t < RHCCQ_KM_MAXT; ++t) if (t < T && acc[t] < best_pot) { best_pot = acc[t]; best = t; }
+        // np.argmin of the float64 potentials (:264): they are within n (1e-9 + ulp) << 1/2 of the integers, so
+        // only candidates that tie in the integers — and are different colours — need the float64 sums
+#pragma unroll
+        for (int t = 0; t < RHCCQ_KM_MAXT; ++t)
+            if (t < T && t != best && (acc[t] == best_pot || RHCCQ_KM_FORCED) && cj[t] != cj[best]) tie = 1;
+        if (tie) {
+            if (!have_f) {
+                for (int j = c_lo; j < c_hi; ++j) {
+                    const rhccq_sk_pt p = rhccq_sk_centred(x[j], mean);
+                    double f = rhccq_sk_seed_dist(true, p, C.center);
+                    for (int s = 1; s < c; ++s) { const double d = rhccq_sk_seed_dist(false, p, C.center + 3 * s); f = d < f ? d : f; }
+                    ex[j] = f;
+                }
+            }
+            g.sync();
+            if (tid == 0) {
+                double bp = 0.0;
+                int bs = -1;
+                for (int t = 0; t < T; ++t) {
+                    if (!RHCCQ_KM_FORCED && acc[t] != best_pot) continue;
+                    const rhccq_sk_pt pc = rhccq_sk_centred(x[cj[t]], mean);
+                    const double cc[3] = {pc.x0, pc.x1, pc.x2};
+                    rhccq_sk_col col; col.f = ex; col.x = x; col.cand = cc; col.mean = mean;
+                    const double pf = rhccq_sk_dgemv_t_ones(col, n, rhccq_sk_gemv_lanes(t, T));
+                    if (bs < 0 || pf < bp) { bp = pf; bs = t; }
+                }
+                flag[1] = bs;
+            }
+            g.sync();
+            best = flag[1];
+            best_pot = acc[0];
+#pragma unroll
+            for (int t = 1; t < RHCCQ_KM_MAXT; ++t) if (t == best) best_pot = acc[t];
+            g.sync();                                               // flag[1] is rewritten in a later step
+        }
         uint32_t cs = xc[0];
 #pragma unroll
         for (int t = 1; t < RHCCQ_KM_MAXT; ++t) if (t == best) cs = xc[t];
@@ -433,13 +743,15 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
             closest[j] = m;
             chunk_sum += m;
         }
-        for (int q = tid; q < 3; q += gsz) C.center[3 * c + q] = (double)((cs >> (16 - 8 * q)) & 255u);
+        for (int q = tid; q < 3; q += gsz) C.center[3 * c + q] = __dsub_rn((double)((cs >> (16 - 8 * q)) & 255u), mean[q]);
         pot = best_pot;
-        // the next pass writes cum / cand only after a collective, which orders it after the reads above
+        prev_slot = best;
+        // the next pass writes cum / cand / flag only after a collective, which orders it after the reads above
     }
 
     if (g.size() > RHCCQ_WARP_SIZE) RHCCQ_PROF(1);
-    // ---- tolerance (kmeans_restated.tolerance)
+    // ---- tolerance: mean(var(X, axis=0)) * 1e-4 (sklearn/_kmeans.py:285-293).  The exact variances differ
+    // from numpy's sequential float64 ones by < n 2^-52 relative; the decision below re-evaluates inside a band.
     double tol;
     {
         const double nn = __dmul_rn((double)n, (double)n);
@@ -447,54 +759,123 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
         for (int d = 0; d < 3; ++d) v[d] = __ddiv_rn((double)((long long)n * S2[d] - S1[d] * S1[d]), nn);
         tol = __dmul_rn(__ddiv_rn(__dadd_rn(__dadd_rn(v[0], v[1]), v[2]), 3.0), 1e-4);
     }
+    // centre error of the integer form against the float64 M step: the sequential sum of n_j centred colours
+    // (|x| <= 255, partial sums <= 255 n_j) rounds by <= n_j ulp(255 n_j) / 2 <= 2.9e-14 n_j^2, divided by n_j
+    const double eps_c = __dmul_rn(4.0e-14, (double)(n + 8));
+    // two scores (|c|^2 - 2 x.c, gradient 2 |c - x|_1 <= 1530) on centres eps_c off, plus their own rounding
+    const double margin_full = RHCCQ_KM_FORCED ? 1.0e300 : __dadd_rn(__dmul_rn(4000.0, eps_c), 1.0e-9);
+    int e_lo, e_hi;
+    rhccq_sk_edge_rows(k, e_lo, e_hi);
 
-    // ---- Lloyd (kmeans_restated.kmeans_labels)
+    // ---- Lloyd (sklearn/_kmeans.py:703-757)
     //
-    // The cluster sums of the M step are kept incrementally: a point only touches them when its label
-    // changes (- old cluster, + new cluster; integers, so the result is the sum over the members exactly).
-    // After the first few iterations a few percent of the points move, which takes the shared-memory
-    // atomics — the main cost next to the distances — off the critical path.  An empty-cluster relocation
-    // edits the sums without changing labels, so the iteration after one recounts from scratch.
+    // The cluster sums are kept incrementally as exact integers: a point only touches them when its label
+    // changes.  Two label arrays alternate so that the labels the current centres were averaged from stay
+    // readable: the float64 centres are recomputed from them when a decision needs them.
     const idx_t NOLABEL = (idx_t)(Cfg::FLAG - 1u);                  // never a real label (k < FLAG - 1)
-    for (int j = tid; j < n; j += gsz) label[j] = NOLABEL;
-    for (int q = tid; q < k; q += gsz) { C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0; }
+    idx_t* lab_prev = A.label + lo;                                 // labels the centres `cen` come from
+    idx_t* lab_cur = reinterpret_cast<idx_t*>(cum);                 // labels the E step writes
+    idx_t* und_list = reinterpret_cast<idx_t*>(cum) + n;            // positions whose E-step decision is open
+    for (int j = tid; j < n; j += gsz) lab_prev[j] = NOLABEL;
+    for (int q = tid; q < k; q += gsz) {
+        C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0;
+        C.csn[q] = rhccq_sk_norm3(C.center[3 * q], C.center[3 * q + 1], C.center[3 * q + 2]);
+    }
     double* cen = C.center;                                         // current / next centre tables, swapped per iteration
     double* cen_new = C.center_new;
-    g.sync();
-    bool strict = false, recount = true;                            // recount: add every point, subtract none
-    for (int it = 0; it < 300; ++it) {
-        // E step.  A point whose distance to the centre of its previous cluster is (safely) less than half
-        // the distance from that centre to the nearest other centre keeps its cluster by the triangle
-        // inequality — every other centre is strictly farther by a margin far above the rounding of the
-        // distance evaluation — so it skips the loop over the centres.  The result is identical to
-        // evaluating every centre; the other points (about 40 %) are compacted into a worklist so that the
-        // warps of the full loop stay full.  Worth its extra pass only for large problems.
-        int changed = 0;
-        const bool prune = it > 0 && !recount && C.wl != nullptr && (long long)n * k >= RHCCQ_PRUNE_MIN_WORK;
-        uint32_t* wl = reinterpret_cast<uint32_t*>(closest);       // dead after the seeding; positions of this range
+    double* E_old = ex;                                             // float64 centres of the E step [4k]
+    double* E_new = ex + 4 * (size_t)k;                             // float64 centres after the M step [4k]
+    double* s2 = ex + 8 * (size_t)k;                                // center_shift ** 2 [k]
+    uint32_t* wl = reinterpret_cast<uint32_t*>(closest);           // dead after the seeding; positions of this range
+    bool recount = true;                                            // add every point to the sums, subtract none
+    bool cen_exact = true;                                          // `cen` holds the float64 centres themselves (seeds; after a relocation)
+    bool e_old_ready = false;                                       // E_old holds the float64 centres of this E step
+    int changed = 0;
+
+    // float64 centres of the current E step (thread 0 of the group)
+    auto build_e_old = [&]() {
+        if (cen_exact) {
+            for (int q = 0; q < k; ++q) {
+                E_old[4 * q] = cen[3 * q]; E_old[4 * q + 1] = cen[3 * q + 1]; E_old[4 * q + 2] = cen[3 * q + 2];
+                E_old[4 * q + 3] = C.csn[q];
+            }
+        } else {
+            rhccq_sk_all_centers<Cfg>(x, lab_prev, n, k, mean, E_old);
+            rhccq_sk_average(E_old, k);
+        }
+    };
+    // center_shift_tot <= tol on E_old / E_new in float64: _center_shift, (shift ** 2).sum(), np.var (thread 0)
+    auto exact_converged = [&]() -> int {
+        for (int q = 0; q < k; ++q) {
+            double res = 0.0;
+            for (int d = 0; d < 3; ++d) { const double a = __dsub_rn(E_new[4 * q + d], E_old[4 * q + d]); res = __dadd_rn(res, __dmul_rn(a, a)); }
+            const double sh = __dsqrt_rn(res);
+            s2[q] = __dmul_rn(sh, sh);
+        }
+        double var[3];
+        for (int d = 0; d < 3; ++d) {
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) {
+                const double xv = __dsub_rn((double)((x[i] >> (16 - 8 * d)) & 255u), mean[d]);
+                s = __dadd_rn(s, __dmul_rn(xv, xv));
+            }
+            var[d] = __ddiv_rn(s, (double)n);
+        }
+        const double tol_e = __dmul_rn(__ddiv_rn(__dadd_rn(__dadd_rn(var[0], var[1]), var[2]), 3.0), 1e-4);
+        return rhccq_sk_np_sum(s2, k) <= tol_e ? 1 : 0;
+    };
+    // one point's new label: label arrays, change flag, integer sums
+    auto commit = [&](int j, uint32_t c, int bi, bool update) {
+        const int old = (int)lab_prev[j];
+        lab_cur[j] = (idx_t)bi;
+        if (!update) return;
+        if (old != bi) changed = 1;
+        if (old != bi || recount) {
+            const int r = rhccq_key_r(c), gg = rhccq_key_g(c), b = rhccq_key_b(c);
+            if (!recount && old != (int)NOLABEL) {
+                atomicAdd(&C.sums[3 * old], -r); atomicAdd(&C.sums[3 * old + 1], -gg); atomicAdd(&C.sums[3 * old + 2], -b);
+                atomicAdd(&C.cnt[old], -1);
+            }
+            atomicAdd(&C.sums[3 * bi], r); atomicAdd(&C.sums[3 * bi + 1], gg); atomicAdd(&C.sums[3 * bi + 2], b);
+            atomicAdd(&C.cnt[bi], 1);
+        }
+    };
+    // E step: lab_cur <- nearest centre of every point (first minimum of the float64 scores).  `update`: keep the
+    // integer sums and the change flag (false for the closing E step, :737-749).
+    auto e_step = [&](bool first_iter, bool update) {
+        // Pruning: a point whose distance to the centre of its previous cluster is safely less than half the
+        // distance from that centre to the nearest other centre keeps its cluster by the triangle inequality —
+        // every other centre is farther by >= 5e-5 in the squared distance, a hundred times the margin below.
+        const double margin = cen_exact ? (RHCCQ_KM_FORCED ? 1.0e300 : (e_hi > e_lo ? 1.0e-9 : 0.0)) : margin_full;
+        const bool prune = !first_iter && !recount && !RHCCQ_KM_FORCED && C.wl != nullptr
+                           && (long long)n * k >= RHCCQ_PRUNE_MIN_WORK;
+        g.sync();                                                   // the tables below may still be read by slower threads
+        if (tid == 0) flag[0] = 0;                                  // number of open decisions
+        e_old_ready = false;
         if (prune) {
-            g.sync();                                               // slower threads may still be summing the last shift from term
             for (int q = tid; q < k; q += gsz) {
                 const double* cq = cen + 3 * q;
                 double m = 1.0e300;
                 for (int r = 0; r < k; ++r) {
                     if (r == q) continue;
-                    const double d = rhccq_dist3(cq[0], cq[1], cq[2], cen + 3 * r);
+                    const double d0 = __dsub_rn(cq[0], cen[3 * r]), d1 = __dsub_rn(cq[1], cen[3 * r + 1]), d2 = __dsub_rn(cq[2], cen[3 * r + 2]);
+                    const double d = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
                     m = d < m ? d : m;
                 }
-                // usable only when the centres are at least 1 apart: then the margin below (1e-6 relative)
-                // is thousands of times the rounding error of a distance (< 1e-9 absolute)
-                C.term[q] = m >= 1.0 ? __dmul_rn(__dmul_rn(0.25, m), 0.999999) : 0.0;
+                C.term[q] = m >= 1.0 ? __dmul_rn(__dmul_rn(0.25, m), 0.9999) : 0.0;
             }
             if (tid == 0) *C.wl = 0;
             g.sync();
             for (int j = tid; j - RHCCQ_LANE < n; j += gsz) {          // warp-uniform trip count
                 bool push = false;
                 if (j < n) {
-                    const uint32_t c = x[j];
-                    const int a = (int)label[j];
-                    const double u = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c), (double)rhccq_key_b(c), cen + 3 * a);
+                    const rhccq_sk_pt p = rhccq_sk_centred(x[j], mean);
+                    const int a = (int)lab_prev[j];
+                    const double* ca = cen + 3 * a;
+                    const double d0 = __dsub_rn(p.x0, ca[0]), d1 = __dsub_rn(p.x1, ca[1]), d2 = __dsub_rn(p.x2, ca[2]);
+                    const double u = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
                     push = !(u < C.term[a]);
+                    if (!push) lab_cur[j] = (idx_t)a;
                 }
                 const unsigned m = rhccq_ballot(push);                 // one counter bump per warp
                 int base = 0;
@@ -502,12 +883,13 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                 base = rhccq_shfl(base, 0);
                 if (push) wl[base + __popc(m & rhccq_lanemask_lt())] = (uint32_t)j;
             }
-            g.sync();
         }
+        g.sync();
         const int n_work = prune ? *C.wl : n;
         for (int i0 = tid; i0 < n_work; i0 += RHCCQ_EB * gsz) {
             uint32_t cb[RHCCQ_EB];
             int bb[RHCCQ_EB], jj[RHCCQ_EB];
+            bool und[RHCCQ_EB];
 #pragma unroll
             for (int u = 0; u < RHCCQ_EB; ++u) {
                 const int i = i0 + u * gsz;
@@ -515,119 +897,153 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                 jj[u] = prune ? (int)wl[is] : is;
                 cb[u] = x[jj[u]];
             }
-            rhccq_nearest_centers(cb, cen, k, bb);
+            rhccq_nearest_centers(cb, mean, cen, C.csn, k, margin, bb, und);
 #pragma unroll
             for (int u = 0; u < RHCCQ_EB; ++u) {
                 if (i0 + u * gsz >= n_work) continue;
-                const int j = jj[u], bi = bb[u], old = (int)label[j];
-                if (old != bi) { changed = 1; label[j] = (idx_t)bi; }
-                if (old != bi || recount) {
-                    const uint32_t c = cb[u];
-                    const int r = rhccq_key_r(c), gg = rhccq_key_g(c), b = rhccq_key_b(c);
-                    if (!recount && old != (int)NOLABEL) {
-                        atomicAdd(&C.sums[3 * old], -r); atomicAdd(&C.sums[3 * old + 1], -gg); atomicAdd(&C.sums[3 * old + 2], -b);
-                        atomicAdd(&C.cnt[old], -1);
-                    }
-                    atomicAdd(&C.sums[3 * bi], r); atomicAdd(&C.sums[3 * bi + 1], gg); atomicAdd(&C.sums[3 * bi + 2], b);
-                    atomicAdd(&C.cnt[bi], 1);
-                }
+                if (und[u]) und_list[atomicAdd(&flag[0], 1)] = (idx_t)jj[u];   // decided below, on the float64 centres
+                else commit(jj[u], cb[u], bb[u], update);
             }
         }
+        g.sync();
+        const int n_und = flag[0];
+        if (n_und > 0) {
+            if (tid == 0) build_e_old();
+            e_old_ready = true;
+            g.sync();
+            for (int i = tid; i < n_und; i += gsz) {
+                const int j = (int)und_list[i];
+                commit(j, x[j], rhccq_nearest_exact(x[j], mean, E_old, k, j, n, e_lo, e_hi), update);
+            }
+        }
+    };
+
+    g.sync();
+    bool strict = false;
+    for (int it = 0; it < 300; ++it) {
+        changed = 0;
+        e_step(it == 0, true);
         recount = false;
         changed = g.any(changed);
         int empty = 0;
         for (int q = tid; q < k; q += gsz) if (C.cnt[q] == 0) ++empty;
         const int n_empty = k <= gsz ? g.count(empty) : g.sum_i(empty);    // k <= gsz: at most one cluster per thread
+        int decided = 0;
+        bool next_exact = false;
         if (n_empty > 0) {
-            // relocate empty clusters to the points farthest from their centre
-            // (_k_means_common.pyx:177-211): farthest first, ties to the lower index.
-            double mx = 0.0;
-            for (int j = tid; j < n; j += gsz) {
-                const uint32_t c = x[j];
-                const double d = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c), (double)rhccq_key_b(c),
-                                             cen + 3 * (int)label[j]);
-                if (d > mx) mx = d;
-            }
-            mx = g.max_d(mx);
-            if (mx != 0.0) {
-                // the empty set is fixed before any relocation (a donor cluster may drop to zero later)
-                for (int q = tid; q < k; q += gsz) C.term[q] = C.cnt[q] == 0 ? 1.0 : 0.0;
-                g.sync();
-                int e = 0;
-                for (int done = 0; done < n_empty; ++done) {
-                    while (C.term[e] == 0.0) ++e;                   // next empty cluster, ascending (group-uniform)
-                    double bm = -1.0;
-                    int bj = 0x7fffffff;
-                    for (int j = tid; j < n; j += gsz) {
-                        const uint32_t lj = label[j];
-                        if (lj & Cfg::FLAG) continue;               // already taken
-                        const uint32_t c = x[j];
-                        const double d = rhccq_dist3((double)rhccq_key_r(c), (double)rhccq_key_g(c),
-                                                     (double)rhccq_key_b(c), cen + 3 * (int)lj);
-                        if (d > bm) { bm = d; bj = j; }             // ascending j: the first maximum stays
+            // Empty clusters (_k_means_common.pyx:167-211): everything in float64, one thread.  The points
+            // farthest from their (old) centres, farthest first, ties to the higher index, give their colour to
+            // the empty clusters in ascending order; the donor's sum loses it by one float64 subtraction.
+            if (tid == 0) {
+                if (!e_old_ready) build_e_old();
+                rhccq_sk_all_centers<Cfg>(x, lab_cur, n, k, mean, E_new);
+                for (int q = 0; q < k; ++q) s2[q] = E_new[4 * q + 3] == 0.0 ? 1.0 : 0.0;   // the empty set is fixed first
+                double mx = 0.0;
+                for (int i = 0; i < n; ++i) {
+                    const rhccq_sk_pt p = rhccq_sk_centred(x[i], mean);
+                    const double* ce = E_old + 4 * (int)lab_cur[i];
+                    const double a0 = __dsub_rn(p.x0, ce[0]), a1 = __dsub_rn(p.x1, ce[1]), a2 = __dsub_rn(p.x2, ce[2]);
+                    const double d = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+                    if (d > mx) mx = d;
+                }
+                if (mx != 0.0) {
+                    int e = 0;
+                    for (int done = 0; done < n_empty; ++done) {
+                        while (s2[e] == 0.0) ++e;
+                        double bm = -1.0;
+                        int bj = 0;
+                        for (int i = 0; i < n; ++i) {
+                            if (lab_cur[i] & Cfg::FLAG) continue;                  // already taken
+                            const rhccq_sk_pt p = rhccq_sk_centred(x[i], mean);
+                            const double* ce = E_old + 4 * (int)lab_cur[i];
+                            const double a0 = __dsub_rn(p.x0, ce[0]), a1 = __dsub_rn(p.x1, ce[1]), a2 = __dsub_rn(p.x2, ce[2]);
+                            const double d = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+                            if (d >= bm) { bm = d; bj = i; }                         // ascending i: the last maximum stays
+                        }
+                        const int o = (int)lab_cur[bj];
+                        const rhccq_sk_pt p = rhccq_sk_centred(x[bj], mean);
+                        E_new[4 * o] = __dsub_rn(E_new[4 * o], p.x0); E_new[4 * o + 1] = __dsub_rn(E_new[4 * o + 1], p.x1);
+                        E_new[4 * o + 2] = __dsub_rn(E_new[4 * o + 2], p.x2);
+                        E_new[4 * o + 3] = __dsub_rn(E_new[4 * o + 3], 1.0);
+                        E_new[4 * e] = p.x0; E_new[4 * e + 1] = p.x1; E_new[4 * e + 2] = p.x2; E_new[4 * e + 3] = 1.0;
+                        lab_cur[bj] = (idx_t)(o | Cfg::FLAG);
+                        ++e;
                     }
-                    const double gm = g.max_d(bm);
-                    bj = g.min_i(bm == gm ? bj : 0x7fffffff);
+                    for (int i = 0; i < n; ++i) lab_cur[i] = (idx_t)(lab_cur[i] & (idx_t)~Cfg::FLAG);
+                }
+                rhccq_sk_average(E_new, k);
+                flag[1] = exact_converged();
+                for (int q = 0; q < k; ++q) {
+                    cen_new[3 * q] = E_new[4 * q]; cen_new[3 * q + 1] = E_new[4 * q + 1]; cen_new[3 * q + 2] = E_new[4 * q + 2];
+                    C.csn[q] = E_new[4 * q + 3];
+                }
+            }
+            g.sync();
+            decided = flag[1];
+            next_exact = true;
+            recount = true;                                         // the integer sums no longer follow the labels
+            for (int q = tid; q < k; q += gsz) { C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0; }
+        } else {
+            for (int q = tid; q < k; q += gsz) {
+                const double cn = (double)C.cnt[q];
+                const double c0 = __dsub_rn(__ddiv_rn((double)C.sums[3 * q], cn), mean[0]);
+                const double c1 = __dsub_rn(__ddiv_rn((double)C.sums[3 * q + 1], cn), mean[1]);
+                const double c2 = __dsub_rn(__ddiv_rn((double)C.sums[3 * q + 2], cn), mean[2]);
+                cen_new[3 * q] = c0; cen_new[3 * q + 1] = c1; cen_new[3 * q + 2] = c2;
+                const double a0 = __dsub_rn(c0, cen[3 * q]), a1 = __dsub_rn(c1, cen[3 * q + 1]), a2 = __dsub_rn(c2, cen[3 * q + 2]);
+                C.term[q] = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+            }
+            g.sync();
+            double shift = 0.0;
+            if (k <= 64) {
+                for (int q = 0; q < k; ++q) shift = __dadd_rn(shift, C.term[q]);         // every thread, same order
+            } else {
+                if (tid == 0) for (int q = 0; q < k; ++q) shift = __dadd_rn(shift, C.term[q]);
+                shift = g.bcast_d(shift);
+            }
+            if (changed) {
+                // center_shift_tot <= tol (:724-733).  Each centre coordinate is within eps_c of its float64 value,
+                // so the shift is within 4 sqrt(3) eps_c sqrt(k shift) of the float64 one, the tolerance within
+                // n 2^-52 relative.  Inside that band: float64 centres, shifts, numpy's pairwise sum, np.var.
+                const double big = shift > tol ? shift : tol;
+                const double band = __dadd_rn(__dmul_rn(__dmul_rn(16.0, eps_c), sqrt(__dmul_rn((double)k, big))), __dmul_rn(1.0e-9, tol));
+                const double diff = shift > tol ? __dsub_rn(shift, tol) : __dsub_rn(tol, shift);
+                if (diff <= band || RHCCQ_KM_FORCED) {
+                    g.sync();
                     if (tid == 0) {
-                        const int old = (int)label[bj];
-                        const uint32_t c = x[bj];
-                        C.sums[3 * old] -= rhccq_key_r(c); C.sums[3 * old + 1] -= rhccq_key_g(c); C.sums[3 * old + 2] -= rhccq_key_b(c);
-                        C.sums[3 * e] = rhccq_key_r(c); C.sums[3 * e + 1] = rhccq_key_g(c); C.sums[3 * e + 2] = rhccq_key_b(c);
-                        C.cnt[e] = 1;
-                        C.cnt[old] -= 1;
-                        label[bj] = (idx_t)(old | Cfg::FLAG);
+                        if (!e_old_ready) build_e_old();
+                        rhccq_sk_all_centers<Cfg>(x, lab_cur, n, k, mean, E_new);
+                        rhccq_sk_average(E_new, k);
+                        flag[1] = exact_converged();
                     }
                     g.sync();
-                    ++e;
+                    decided = flag[1];
+                } else {
+                    decided = shift <= tol ? 1 : 0;
                 }
-                for (int j = tid; j < n; j += gsz) label[j] = (idx_t)(label[j] & ~Cfg::FLAG);
-                recount = true;                                     // the sums no longer follow the labels
-                g.sync();
             }
-        }
-        for (int q = tid; q < k; q += gsz) {
-            double c0, c1, c2;
-            if (C.cnt[q] > 0) {
-                const double cn = (double)C.cnt[q];
-                c0 = __ddiv_rn((double)C.sums[3 * q], cn);
-                c1 = __ddiv_rn((double)C.sums[3 * q + 1], cn);
-                c2 = __ddiv_rn((double)C.sums[3 * q + 2], cn);
-            } else {
-                c0 = __ddiv_rn((double)S1[0], (double)n);
-                c1 = __ddiv_rn((double)S1[1], (double)n);
-                c2 = __ddiv_rn((double)S1[2], (double)n);
-            }
-            cen_new[3 * q] = c0; cen_new[3 * q + 1] = c1; cen_new[3 * q + 2] = c2;
-            const double a0 = __dsub_rn(c0, cen[3 * q]), a1 = __dsub_rn(c1, cen[3 * q + 1]), a2 = __dsub_rn(c2, cen[3 * q + 2]);
-            C.term[q] = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
-            if (recount) { C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0; }
-        }
-        g.sync();
-        double shift = 0.0;
-        if (k <= 64) {
-            for (int q = 0; q < k; ++q) shift = __dadd_rn(shift, C.term[q]);             // fixed order, every thread
-        } else {
-            if (tid == 0) for (int q = 0; q < k; ++q) shift = __dadd_rn(shift, C.term[q]);
-            shift = g.bcast_d(shift);
+            g.sync();                                               // term / csn are rewritten next
+            for (int q = tid; q < k; q += gsz) C.csn[q] = rhccq_sk_norm3(cen_new[3 * q], cen_new[3 * q + 1], cen_new[3 * q + 2]);
         }
         { double* t = cen; cen = cen_new; cen_new = t; }
-        if (!changed) { strict = true; break; }
-        if (shift <= tol) break;
+        { idx_t* t = lab_prev; lab_prev = lab_cur; lab_cur = t; }
+        cen_exact = next_exact;
+        if (!changed) { strict = true; break; }                     // :717-722
+        if (decided) break;                                         // :724-733
     }
-    if (!strict) {
-        for (int j0 = tid; j0 < n; j0 += RHCCQ_EB * gsz) {
-            uint32_t cb[RHCCQ_EB];
-            int bb[RHCCQ_EB];
-#pragma unroll
-            for (int u = 0; u < RHCCQ_EB; ++u) { const int j = j0 + u * gsz; cb[u] = x[j < n ? j : j0]; }
-            rhccq_nearest_centers(cb, cen, k, bb);
-#pragma unroll
-            for (int u = 0; u < RHCCQ_EB; ++u) { const int j = j0 + u * gsz; if (j < n) label[j] = (idx_t)bb[u]; }
-        }
+    if (!strict) {                                                  // :737-749: labels that match the final centres
+        e_step(false, false);
+        idx_t* t = lab_prev; lab_prev = lab_cur; lab_cur = t;
+    }
+    // the result belongs in A.label (the partition that follows overwrites `cum`)
+    g.sync();
+    if (lab_prev != A.label + lo) {
+        idx_t* dst = A.label + lo;
+        for (int j = tid; j < n; j += gsz) dst[j] = lab_prev[j];
     }
     for (int q = tid; q < k; q += gsz) C.cnt[q] = 0;
     g.sync();
-    for (int j = tid; j < n; j += gsz) atomicAdd(&C.cnt[(int)label[j]], 1);
+    for (int j = tid; j < n; j += gsz) atomicAdd(&C.cnt[(int)A.label[lo + j]], 1);
     g.sync();
     if (g.size() > RHCCQ_WARP_SIZE) RHCCQ_PROF(2);
 }
@@ -668,6 +1084,7 @@ __device__ __forceinline__ void rhccq_carve_centers(rhccq_km_centers& C, unsigne
     C.center = cv.take<double>(3 * kc);
     C.center_new = cv.take<double>(3 * kc);
     C.term = cv.take<double>(kc);
+    C.csn = cv.take<double>(kc);
     C.sums = cv.take<int>(3 * kc);
     C.cnt = cv.take<int>(kc);
 }
@@ -679,7 +1096,7 @@ __host__ __device__ static inline size_t rhccq_split_row_bytes(size_t rows) {
            + rhccq_carve_bytes(rows, sizeof(idx_t)) * 2 + rhccq_carve_bytes(rows, sizeof(typename Cfg::q_t));
 }
 __host__ __device__ static inline size_t rhccq_split_center_bytes(size_t kc) {
-    return rhccq_carve_bytes(3 * kc, 8) * 2 + rhccq_carve_bytes(kc, 8) + rhccq_carve_bytes(3 * kc, 4)
+    return rhccq_carve_bytes(3 * kc, 8) * 2 + rhccq_carve_bytes(kc, 8) * 2 + rhccq_carve_bytes(3 * kc, 4)
            + rhccq_carve_bytes(kc, 4);
 }
 
@@ -690,7 +1107,8 @@ size_t rhccq_palette_split_ws_bytes(int max_rows) {
                                                               : rhccq_split_row_bytes<rhccq_cfg_large>(r);
     // never 0 and never within the shared-memory budget: the caller must always pass a workspace (the
     // centre tables of a K-Means with more than RHCCQ_KC centres live there)
-    const size_t need = rows + rhccq_split_center_bytes(r);
+    // ... and the float64 scratch of the decisions that are re-evaluated in scikit-learn's own arithmetic
+    const size_t need = rows + rhccq_split_center_bytes(r) + rhccq_carve_bytes((size_t)RHCCQ_EX_PER_ROW * r, 8);
     return need > RHCCQ_SMEM_BUDGET ? need : (size_t)RHCCQ_SMEM_BUDGET + 16;
 }
 
@@ -799,7 +1217,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
                                             const double* __restrict__ rng, int rng_len, int* __restrict__ leaf,
                                             int* __restrict__ n_leaves, int max_rows, unsigned char* row_base,
                                             unsigned char* small_base, unsigned char* cent_s, int kc_s,
-                                            unsigned char* cent_g, int kc_g) {
+                                            unsigned char* cent_g, int kc_g, double* ex) {
     typedef typename Cfg::idx_t idx_t;
     typedef typename Cfg::q_t q_t;
     __shared__ long long s_ll[RHCCQ_MAX_WARPS * RHCCQ_KM_MAXT + 2];
@@ -811,7 +1229,10 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     const uint32_t* keys = B.pal_keys + B.pal_off[p];
     const int* lab = labels + B.pal_off[p];
     int* lf = leaf + B.pal_off[p];
-    const int mcpc = max_cpc[p];
+    // max_cpc[p] = -k: one KMeans(k) over the whole palette and nothing else (the third-party operator of
+    // clustering.py:751-752 by itself): every row is a member of one root, the k children are the leaves
+    const int kforce = max_cpc[p] < 0 ? -max_cpc[p] : 0;
+    const int mcpc = kforce ? 0 : max_cpc[p];
     if (n < 0 || (status_in != nullptr && status_in[p] < 0)) {     // upstream error: pass it on
         if (threadIdx.x == 0) n_leaves[p] = n < 0 ? -2 : status_in[p];
         return;
@@ -829,6 +1250,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
         W.A.label = cv.take<idx_t>(max_rows);
         W.perm = cv.take<idx_t>(max_rows);
         W.queue = cv.take<q_t>(max_rows);
+        W.A.ex = ex;
     }
     // CTA-level centre tables: in shared memory for k <= kc_s, else in the global workspace (k <= kc_g)
     rhccq_km_centers CS, CG;
@@ -837,11 +1259,11 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     // small shared tables: per-warp centre sets, per-warp M-step histograms, candidate slots
     rhccq_carver sv(small_base);
     const size_t nw = (size_t)RHCCQ_NWARPS;                        // the tables are sized for the launch's warps
-    int* cand = sv.take<int>((nw + 1) * RHCCQ_KM_MAXT);
-    double* wcent = sv.take<double>(nw * 7 * RHCCQ_KW);
+    int* cand = sv.take<int>((nw + 1) * RHCCQ_KM_CAND);
+    double* wcent = sv.take<double>(nw * 8 * RHCCQ_KW);
     int* wint = sv.take<int>(nw * 5 * RHCCQ_KW);
     int* poff = sv.take<int>(nw * RHCCQ_KC);
-    CS.cand = CG.cand = cand + nw * RHCCQ_KM_MAXT;
+    CS.cand = CG.cand = cand + nw * RHCCQ_KM_CAND;
 
     // ---- entries that need no K-Means.  csize / crank live in the (still unused) seeding arrays.
     int* csize = reinterpret_cast<int*>(W.A.x);
@@ -960,7 +1382,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
         for (int e = head; e < tail; ++e) {
             const q_t qe = W.queue[e];
             const int lo = Cfg::q_lo(qe), hi = Cfg::q_hi(qe), cnt = hi - lo;
-            int k = (cnt + mcpc - 1) / mcpc;                        // clustering.py:739-742
+            int k = kforce ? kforce : (cnt + mcpc - 1) / mcpc;      // clustering.py:739-742
             if (k < 2) k = 2;
             if (k > cnt) k = cnt;
             if (cnt <= RHCCQ_WARP_RANGE && k <= RHCCQ_KW) continue;  // a warp's job
@@ -975,13 +1397,13 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
                 C.hist = nullptr;
                 C.poff = poff;
                 C.wl = &s_wl;
-                rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
+                rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, kforce ? 0x7fffffff : mcpc, rng, &s_tail, max_rows, &s_err);
             } else {
                 rhccq_km_centers C = CG;
                 C.hist = nullptr;
                 C.poff = nullptr;
                 C.wl = nullptr;
-                rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
+                rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, kforce ? 0x7fffffff : mcpc, rng, &s_tail, max_rows, &s_err);
             }
         }
         __syncthreads();
@@ -997,20 +1419,20 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
             if (e >= tail) break;
             const q_t qe = W.queue[e];
             const int lo = Cfg::q_lo(qe), hi = Cfg::q_hi(qe), cnt = hi - lo;
-            int k = (cnt + mcpc - 1) / mcpc;
+            int k = kforce ? kforce : (cnt + mcpc - 1) / mcpc;
             if (k < 2) k = 2;
             if (k > cnt) k = cnt;
             if (!(cnt <= RHCCQ_WARP_RANGE && k <= RHCCQ_KW)) continue;
             if (1 + (k - 1) * rhccq_kmeans_local_trials(k) > rng_len) { s_err = 2; continue; }
             rhccq_km_centers C;
-            double* wc = wcent + (size_t)RHCCQ_WARP * 7 * RHCCQ_KW;
+            double* wc = wcent + (size_t)RHCCQ_WARP * 8 * RHCCQ_KW;
             int* wi = wint + (size_t)RHCCQ_WARP * 5 * RHCCQ_KW;
-            C.center = wc; C.center_new = wc + 3 * RHCCQ_KW; C.term = wc + 6 * RHCCQ_KW;
+            C.center = wc; C.center_new = wc + 3 * RHCCQ_KW; C.term = wc + 6 * RHCCQ_KW; C.csn = wc + 7 * RHCCQ_KW;
             C.sums = wi; C.cnt = wi + 3 * RHCCQ_KW; C.poff = wi + 4 * RHCCQ_KW;
             C.hist = nullptr;
-            C.cand = cand + RHCCQ_WARP * RHCCQ_KM_MAXT;
+            C.cand = cand + RHCCQ_WARP * RHCCQ_KM_CAND;
             C.wl = wlc + RHCCQ_WARP;
-            rhccq_split_range<rhccq_grp_warp, Cfg>(gw, W, C, lo, hi, k, mcpc, rng, &s_tail, max_rows, &s_err);
+            rhccq_split_range<rhccq_grp_warp, Cfg>(gw, W, C, lo, hi, k, kforce ? 0x7fffffff : mcpc, rng, &s_tail, max_rows, &s_err);
         }
         head = tail;
         __syncthreads();
@@ -1057,6 +1479,7 @@ rhccq_k_palette_split(rhccq_palette_batch B, const int* __restrict__ labels, con
     unsigned char* row_base = ROWS_SMEM ? dyn + small_bytes : slice;    // compile-time: keeps the address space known
     unsigned char* cent_s = dyn + small_bytes + (ROWS_SMEM ? row_bytes : 0);
     unsigned char* cent_g = slice ? slice + row_bytes : nullptr;
+    double* ex = slice ? reinterpret_cast<double*>(slice + row_bytes + rhccq_split_center_bytes((size_t)max_rows)) : nullptr;
     // problems are handed out by a grid-wide cursor when there is one (palettes take unequal time); it lives in
     // the row area of workspace slice 0, which is unused while the rows are in shared memory
     int* cursor = (ROWS_SMEM && gws) ? reinterpret_cast<int*>(gws) : nullptr;
@@ -1070,7 +1493,7 @@ rhccq_k_palette_split(rhccq_palette_batch B, const int* __restrict__ labels, con
         }
         if (p >= B.n_problems) break;
         rhccq_palette_split_problem<Cfg>(B, p, labels, status_in, max_cpc, rng, rng_len, leaf, n_leaves, max_rows,
-                                         row_base, dyn, cent_s, kc_s, cent_g, max_rows);
+                                         row_base, dyn, cent_s, kc_s, cent_g, max_rows, ex);
         __syncthreads();
     }
 }
@@ -1081,8 +1504,8 @@ static size_t rhccq_split_small_bytes(int threads) {
 #else
     const size_t nw = (size_t)threads / 32;
 #endif
-    return rhccq_carve_bytes((nw + 1) * RHCCQ_KM_MAXT, 4)
-           + rhccq_carve_bytes(nw * 7 * RHCCQ_KW, 8) + rhccq_carve_bytes(nw * 5 * RHCCQ_KW, 4)
+    return rhccq_carve_bytes((nw + 1) * RHCCQ_KM_CAND, 4)
+           + rhccq_carve_bytes(nw * 8 * RHCCQ_KW, 8) + rhccq_carve_bytes(nw * 5 * RHCCQ_KW, 4)
            + rhccq_carve_bytes(nw * RHCCQ_KC, 4);
 }
 
@@ -1101,9 +1524,9 @@ static int rhccq_launch_split_cfg(const rhccq_palette_batch& B, const int* label
     const size_t slices = ws.ws ? ws.ws_bytes / slice : 0;
     // everything the kernel needs next to its ~3.3 KB of static shared memory, within the 227 KB of an SM
     const int rows_in_smem = small + row_bytes + cent_s + 4096 <= 227 * 1024;
-    if (!rows_in_smem && slices == 0) {
-        rhccq_set_error("rhccq_palette_split: the per-row working set (%zu bytes) exceeds shared memory and the "
-                        "workspace (%zu bytes) holds no slice of %zu bytes", row_bytes, ws.ws_bytes, slice);
+    if (slices == 0) {
+        rhccq_set_error("rhccq_palette_split: the workspace (%zu bytes) holds no slice of %zu bytes (float64 scratch, "
+                        "centre tables%s)", ws.ws_bytes, slice, rows_in_smem ? "" : ", per-row working set");
         return -1;
     }
     // one CTA per problem, at most one per workspace slice (a CTA without a slice could not run a K-Means

@@ -100,6 +100,29 @@ def palette_split(be: Backend, pal_keys, pal_off, pal_cnt, labels, n_clusters, m
     return leaf, nl
 
 
+def kmeans_labels(be: Backend, colors, k: int):
+    """``KMeans(n_clusters=k, random_state=42, n_init='auto').fit_predict(colors.astype(float))`` — the
+    third-party operator the reference calls at clustering.py:751-752 — through rhccq_palette_split with
+    max_cpc = -k.  Returns int64 labels; labels are ranks among the non-empty clusters (identical to
+    scikit-learn's unless a cluster ends empty, which scikit-learn reports with a ConvergenceWarning)."""
+    import numpy as np
+    c = np.ascontiguousarray(np.asarray(colors).astype(np.uint8).reshape(-1, 3)).astype(np.int64)
+    n = int(c.shape[0])
+    if not 1 <= int(k) <= n:
+        raise ValueError(f"n_samples={n} should be >= n_clusters={k}.")
+    if (c == 0).all(axis=1).any():
+        raise NotImplementedError("black rows never reach K-Means in the reference (clustering.py:185-192)")
+    keys = _as_dev(be, ((c[:, 0] << 16) | (c[:, 1] << 8) | c[:, 2]).astype(np.int32), I32)
+    off = _as_dev(be, np.zeros(1, np.int32), I32)
+    cnt = _as_dev(be, np.full(1, n, np.int32), I32)
+    lab = be.zeros((n,), I32)
+    ncl = _as_dev(be, np.ones(1, np.int32), I32)
+    mc = _as_dev(be, np.full(1, -int(k), np.int32), I32)
+    leaf, nl = palette_split(be, keys, off, cnt, lab, ncl, mc, max_rows=n)
+    check_counts("rhccq_palette_split", nl)
+    return leaf.cpu().numpy().astype(np.int64)
+
+
 def palette_finish(be: Backend, pal_keys, pal_off, pal_cnt, leaf, n_leaves, *, max_rows: int):
     """Truncated means — rhccq_palette_finish.  Returns new_keys (same layout as pal_keys)."""
     P = pal_cnt.numel()

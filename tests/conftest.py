@@ -53,6 +53,13 @@ def emu_backend():
     return Backend(EMU_SO, "cpu")
 
 
+@pytest.fixture(scope="session")
+def emu_exact_backend(emu_backend):
+    """The emulation build with -DRHCCQ_KM_FORCE_EXACT: every K-Means decision takes the float64 path."""
+    from roibasedimagecompression_b200._lib import Backend
+    return Backend(EMU_SO.replace("librhccq_emu.so", "librhccq_emu_exact.so"), "cpu")
+
+
 @pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
 def backend(request):
     """The kernels under test: the emulation build on CPU, the nvcc build on the GPU box."""
