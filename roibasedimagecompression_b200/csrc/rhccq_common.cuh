@@ -21,6 +21,7 @@
 struct rhccq_emu_dim3 { unsigned x, y, z; };
 struct int2 { int x, y; };
 struct uint4 { unsigned x, y, z, w; };
+struct float4 { float x, y, z, w; };
 extern rhccq_emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 extern unsigned char* rhccq_emu_dyn_smem;
 void rhccq_emu_prepare_smem(size_t bytes);
@@ -49,6 +50,8 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline double __dsqrt_rn(double a) { return sqrt(a); }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }

@@ -30,19 +30,21 @@
 // Optional phase timers (cycles summed over all CTAs into rhccq_split_prof[8]); compiled in with
 // -DRHCCQ_SPLIT_PROFILE by tools/split_phases.py only.
 #if defined(RHCCQ_SPLIT_PROFILE) && !defined(RHCCQ_HOST_EMU)
-__device__ unsigned long long rhccq_split_prof[8];
+__device__ unsigned long long rhccq_split_prof[16];
+#define RHCCQ_COUNT(slot, v) atomicAdd(&rhccq_split_prof[slot], (unsigned long long)(v))
 #define RHCCQ_PROF_T0() long long prof_t_ = clock64()
 #define RHCCQ_PROF(slot) do { if (threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&rhccq_split_prof[slot], (unsigned long long)(n_ - prof_t_)); prof_t_ = n_; } } while (0)
 #else
 #define RHCCQ_PROF_T0() do {} while (0)
 #define RHCCQ_PROF(slot) do {} while (0)
+#define RHCCQ_COUNT(slot, v) do {} while (0)
 #endif
 
-#ifndef RHCCQ_PRUNE_MIN_WORK
-#define RHCCQ_PRUNE_MIN_WORK 20000     // n * k from which the pruned E step pays for its extra pass
-#endif
 #define RHCCQ_SPLIT_THREADS 256
 #define RHCCQ_KM_MAXT 12               // 2 + int(log(k)) for k < 22027
+#ifndef RHCCQ_PRUNE_MIN_K
+#define RHCCQ_PRUNE_MIN_K 10            // centres from which the E step prunes by the triangle inequality
+#endif
 #define RHCCQ_KM_CAND 16               // ints per candidate table: RHCCQ_KM_MAXT candidates + 2 flags
 #define RHCCQ_KC 128                   // centres of a CTA-level K-Means kept in shared memory
 #define RHCCQ_KW 8                     // centres of a warp-level K-Means
@@ -90,6 +92,8 @@ struct rhccq_cfg_large {
 struct rhccq_grp_cta {
     static const bool kCta = true;
     long long* sll;                    // RHCCQ_MAX_WARPS * RHCCQ_KM_MAXT + 2 elements of shared scratch
+    long long* svb;                    // 2 x RHCCQ_MAX_WARPS * RHCCQ_KM_MAXT: sum_vec alternates between the halves
+    mutable int svp;                   // which half the next sum_vec uses (same in every thread)
     unsigned long long* csum;          // one slot per thread: chunk sums of the seeding
     __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
     __device__ __forceinline__ int size() const { return (int)blockDim.x; }
@@ -115,14 +119,17 @@ struct rhccq_grp_cta {
     __device__ __forceinline__ void sum_vec(long long* v, int cnt) const {
 #ifndef RHCCQ_HOST_EMU
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-        __syncthreads();                                          // scratch may still be read by a previous call
+        // one barrier: consecutive calls use different halves, and a half is rewritten only two calls later,
+        // after every thread has passed the barrier of the call in between
+        long long* buf = svb + (size_t)svp * (RHCCQ_SPLIT_MAX_WARPS * RHCCQ_KM_MAXT);
+        svp ^= 1;
 #pragma unroll
         for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {                   // unrolled: v stays in registers
             if (t < cnt) {
                 long long x = v[t];
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-                if (lane == 0) sll[warp * RHCCQ_KM_MAXT + t] = x;
+                if (lane == 0) buf[warp * RHCCQ_KM_MAXT + t] = x;
             }
         }
         __syncthreads();
@@ -130,7 +137,7 @@ struct rhccq_grp_cta {
         for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {
             if (t < cnt) {
                 long long x = 0;
-                for (int w = 0; w < nwarp; ++w) x += sll[w * RHCCQ_KM_MAXT + t];
+                for (int w = 0; w < nwarp; ++w) x += buf[w * RHCCQ_KM_MAXT + t];
                 v[t] = x;
             }
         }
@@ -281,6 +288,8 @@ struct rhccq_km_centers {
     double* center_new;                 // [3k]
     double* term;                       // [k]
     double* csn;                        // [k]   |c|^2 as einsum('ij,ij->i') evaluates it
+    float* cf;                          // [4k]  (-2 c0, -2 c1, -2 c2, |c|^2) in float32: first level of the E step
+    int* hb;                            // [k] float32 pruning threshold of every centre; nullptr: every point is evaluated
     int* sums;                          // [3k]
     int* cnt;                           // [k]
     int* hist;                          // unused
@@ -465,39 +474,49 @@ __device__ __noinline__ void rhccq_sk_average(double* E, int k) {
     for (int j = 0; j < k; ++j) E[4 * j + 3] = rhccq_sk_norm3(E[4 * j], E[4 * j + 1], E[4 * j + 2]);
 }
 
-// First minimum over centres of the E-step score for RHCCQ_EB points at once (every centre is loaded once
-// per RHCCQ_EB points and the chains are independent: the FP64 pipe bounds this kernel).  und[u] is set
-// when another centre's score is within `margin` of the best one (margin 0: never).
+// First level of the E step: the scores |c|^2 - 2 x.c of RHCCQ_EB points against every centre in float32
+// (every centre is one 16-byte load per RHCCQ_EB points; the chains are independent and branch-free).
+// Error of one float32 score against the float64 score on the same centres: inputs x - mean and -2 c
+// rounded to float32 (<= 3.1e-5 each, |x| <= 255, |2c| <= 510), |c|^2 (<= ulp(2e5)/2 = 0.008) and three
+// fused steps (<= 0.016 each): <= 0.13.  und[u] is set when the runner-up is within RHCCQ_F32_MARGIN = 0.5
+// of the best; such a point goes to the second level: the float64 scores on the integer-derived centres, one warp per
+// point, and from there — when two scores are within `margin` — to the third: the float64 centres themselves.
 #define RHCCQ_EB 4
-__device__ __forceinline__ void rhccq_nearest_centers(const uint32_t (&c)[RHCCQ_EB], const double (&mean)[3],
-                                                      const double* center, const double* csn, int k, double margin,
-                                                      int (&bi)[RHCCQ_EB], bool (&und)[RHCCQ_EB]) {
-    rhccq_sk_pt p[RHCCQ_EB];
-    double best[RHCCQ_EB], bpm[RHCCQ_EB], sec[RHCCQ_EB];
+#define RHCCQ_F32_MARGIN 0.5f
+template <int NB>
+__device__ __forceinline__ void rhccq_nearest_centers_f32(const uint32_t (&c)[NB], const float (&meanf)[3],
+                                                          const float* cf, int k, int (&bi)[NB], bool (&und)[NB]) {
+    float x0[NB], x1[NB], x2[NB], best[NB], sec[NB];
+    const float4* c4 = reinterpret_cast<const float4*>(cf);
+    {
+        const float4 q0 = c4[0];
 #pragma unroll
-    for (int u = 0; u < RHCCQ_EB; ++u) {
-        p[u] = rhccq_sk_centred(c[u], mean);
-        best[u] = rhccq_sk_score(p[u], center, csn[0], false);
-        bpm[u] = __dadd_rn(best[u], margin);
-        sec[u] = 1.0e300;
-        bi[u] = 0;
+        for (int u = 0; u < NB; ++u) {
+            x0[u] = __fsub_rn((float)rhccq_key_r(c[u]), meanf[0]);
+            x1[u] = __fsub_rn((float)rhccq_key_g(c[u]), meanf[1]);
+            x2[u] = __fsub_rn((float)rhccq_key_b(c[u]), meanf[2]);
+            best[u] = fmaf(x0[u], q0.x, fmaf(x1[u], q0.y, fmaf(x2[u], q0.z, q0.w)));
+            sec[u] = 3.0e38f;
+            bi[u] = 0;
+        }
     }
+#pragma unroll 2
     for (int q = 1; q < k; ++q) {
-        const double c0 = center[3 * q], c1 = center[3 * q + 1], c2 = center[3 * q + 2], cs = csn[q];
+        const float4 cq = c4[q];
 #pragma unroll
-        for (int u = 0; u < RHCCQ_EB; ++u) {
-            const double d = __fma_rn(-2.0, __fma_rn(p[u].x2, c2, __fma_rn(p[u].x1, c1, __dmul_rn(p[u].x0, c0))), cs);
-            if (d < bpm[u]) {
-                if (d < best[u]) { sec[u] = best[u]; best[u] = d; bi[u] = q; bpm[u] = __dadd_rn(d, margin); }
-                else if (d < sec[u]) sec[u] = d;
-            }
+        for (int u = 0; u < NB; ++u) {
+            const float d = fmaf(x0[u], cq.x, fmaf(x1[u], cq.y, fmaf(x2[u], cq.z, cq.w)));
+            sec[u] = fminf(sec[u], fmaxf(d, best[u]));              // runner-up so far
+            const bool lt = d < best[u];
+            best[u] = lt ? d : best[u];
+            bi[u] = lt ? q : bi[u];
         }
     }
 #pragma unroll
-    for (int u = 0; u < RHCCQ_EB; ++u) und[u] = sec[u] < bpm[u];
+    for (int u = 0; u < NB; ++u) und[u] = !(sec[u] - best[u] > RHCCQ_F32_MARGIN);
 }
 // the same decision on the float64 centres E (one point, every centre, the dgemm edge rows included)
-__device__ __forceinline__ int rhccq_nearest_exact(uint32_t c, const double (&mean)[3], const double* E, int k,
+__device__ __noinline__ int rhccq_nearest_exact(uint32_t c, const double (&mean)[3], const double* E, int k,
                                                    int i, int n, int e_lo, int e_hi) {
     const rhccq_sk_pt p = rhccq_sk_centred(c, mean);
     const bool es = e_hi > e_lo && rhccq_sk_edge_sample(i, n);
@@ -515,6 +534,138 @@ __device__ __forceinline__ int rhccq_nearest_exact(uint32_t c, const double (&me
 #else
 #define RHCCQ_KM_FORCED 0
 #endif
+
+// ---- the float64 re-evaluations: rare, kept out of line (and unrolled nowhere) so that they cost no
+// instruction-cache space next to the hot loops
+// float64 closest distances of positions [j0, j1) to the c centres chosen so far (every thread, its chunk)
+__device__ __noinline__ void rhccq_sk_closest_f(const uint32_t* x, int j0, int j1, const double* mean, const double* cen,
+                                                int c, double* f) {
+    const double m3[3] = {mean[0], mean[1], mean[2]};
+#pragma unroll 1
+    for (int j = j0; j < j1; ++j) {
+        const rhccq_sk_pt p = rhccq_sk_centred(x[j], m3);
+        double v = rhccq_sk_seed_dist(true, p, cen);
+#pragma unroll 1
+        for (int s = 1; s < c; ++s) { const double d = rhccq_sk_seed_dist(false, p, cen + 3 * s); v = d < v ? d : v; }
+        f[j] = v;
+    }
+}
+// candidates of one seeding step on the float64 values: the potential as the previous step's BLAS call summed
+// it, np.cumsum, np.searchsorted(side='left'), clipped (one thread)
+__device__ __noinline__ void rhccq_sk_draw(const uint32_t* x, int n, const double* mean, const double* f, int prev_slot,
+                                           int T, const double* rng_step, int* cand) {
+    rhccq_sk_col col; col.f = f; col.x = x; col.cand = nullptr; col.mean = mean;
+    const double pot_f = prev_slot < 0 ? rhccq_sk_ddot_ones(f, n)
+                                       : rhccq_sk_dgemv_t_ones(col, n, rhccq_sk_gemv_lanes(prev_slot, T));
+    double rv[RHCCQ_KM_MAXT];
+    int fnd[RHCCQ_KM_MAXT];
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) { rv[t] = __dmul_rn(rng_step[t], pot_f); fnd[t] = -1; }
+    double s = 0.0;
+    int open = T;
+#pragma unroll 1
+    for (int i = 0; i < n && open > 0; ++i) {
+        s = __dadd_rn(s, f[i]);
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) if (fnd[t] < 0 && !(s < rv[t])) { fnd[t] = i; --open; }
+    }
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) cand[t] = fnd[t] < 0 ? n - 1 : fnd[t];
+}
+// np.argmin of the float64 potentials over the candidate slots of `mask` (one thread)
+__device__ __noinline__ int rhccq_sk_best(const uint32_t* x, int n, const double* mean, const double* f, int T,
+                                          const int* cand, unsigned mask) {
+    const double m3[3] = {mean[0], mean[1], mean[2]};
+    double bp = 0.0;
+    int bs = -1;
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        if (!((mask >> t) & 1u)) continue;
+        const rhccq_sk_pt pc = rhccq_sk_centred(x[cand[t]], m3);
+        const double cc[3] = {pc.x0, pc.x1, pc.x2};
+        rhccq_sk_col col; col.f = f; col.x = x; col.cand = cc; col.mean = mean;
+        const double pf = rhccq_sk_dgemv_t_ones(col, n, rhccq_sk_gemv_lanes(t, T));
+        if (bs < 0 || pf < bp) { bp = pf; bs = t; }
+    }
+    return bs;
+}
+// float64 centres of an E step (one thread): the table itself when it holds them, else the M step of `lab`
+template <class Cfg>
+__device__ __noinline__ void rhccq_sk_e_old(const uint32_t* x, const typename Cfg::idx_t* lab, int n, int k, const double* mean,
+                                            const double* cen, const double* csn, bool cen_exact, double* E) {
+    if (cen_exact) {
+#pragma unroll 1
+        for (int q = 0; q < k; ++q) { E[4 * q] = cen[3 * q]; E[4 * q + 1] = cen[3 * q + 1]; E[4 * q + 2] = cen[3 * q + 2]; E[4 * q + 3] = csn[q]; }
+    } else {
+        rhccq_sk_all_centers<Cfg>(x, lab, n, k, mean, E);
+        rhccq_sk_average(E, k);
+    }
+}
+// center_shift_tot <= tol in float64: _center_shift, (shift ** 2).sum(), np.var (one thread)
+__device__ __noinline__ int rhccq_sk_converged(const uint32_t* x, int n, int k, const double* mean, const double* E_old,
+                                               const double* E_new, double* s2) {
+#pragma unroll 1
+    for (int q = 0; q < k; ++q) {
+        double res = 0.0;
+#pragma unroll 1
+        for (int d = 0; d < 3; ++d) { const double a = __dsub_rn(E_new[4 * q + d], E_old[4 * q + d]); res = __dadd_rn(res, __dmul_rn(a, a)); }
+        const double sh = __dsqrt_rn(res);
+        s2[q] = __dmul_rn(sh, sh);
+    }
+    double var[3];
+#pragma unroll 1
+    for (int d = 0; d < 3; ++d) {
+        double s = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            const double xv = __dsub_rn((double)((x[i] >> (16 - 8 * d)) & 255u), mean[d]);
+            s = __dadd_rn(s, __dmul_rn(xv, xv));
+        }
+        var[d] = __ddiv_rn(s, (double)n);
+    }
+    const double tol_e = __dmul_rn(__ddiv_rn(__dadd_rn(__dadd_rn(var[0], var[1]), var[2]), 3.0), 1e-4);
+    return rhccq_sk_np_sum(s2, k) <= tol_e ? 1 : 0;
+}
+// Empty clusters (_k_means_common.pyx:167-211), one thread.  E_new <- float64 M step of `lab`; the points
+// farthest from their (old) centres, farthest first, ties to the higher index, give their colour to the empty
+// clusters in ascending order and the donor's sum loses it by one float64 subtraction; then _average_centers.
+template <class Cfg>
+__device__ __noinline__ void rhccq_sk_relocate(const uint32_t* x, typename Cfg::idx_t* lab, int n, int k, int n_empty,
+                                               const double* mean, const double* E_old, double* E_new, double* s2) {
+    typedef typename Cfg::idx_t idx_t;
+    const double m3[3] = {mean[0], mean[1], mean[2]};
+    rhccq_sk_all_centers<Cfg>(x, lab, n, k, mean, E_new);
+#pragma unroll 1
+    for (int q = 0; q < k; ++q) s2[q] = E_new[4 * q + 3] == 0.0 ? 1.0 : 0.0;       // the empty set is fixed first
+    int e = 0;
+#pragma unroll 1
+    for (int done = 0; done < n_empty; ++done) {
+        while (s2[e] == 0.0) ++e;
+        double bm = -1.0;
+        int bj = 0;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            if (lab[i] & Cfg::FLAG) continue;                                  // already taken
+            const rhccq_sk_pt p = rhccq_sk_centred(x[i], m3);
+            const double* ce = E_old + 4 * (int)lab[i];
+            const double a0 = __dsub_rn(p.x0, ce[0]), a1 = __dsub_rn(p.x1, ce[1]), a2 = __dsub_rn(p.x2, ce[2]);
+            const double d = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
+            if (d >= bm) { bm = d; bj = i; }                                   // ascending i: the last maximum stays
+        }
+        if (done == 0 && bm == 0.0) break;                                     // np.max(distances) == 0: nothing to relocate
+        const int o = (int)lab[bj];
+        const rhccq_sk_pt p = rhccq_sk_centred(x[bj], m3);
+        E_new[4 * o] = __dsub_rn(E_new[4 * o], p.x0); E_new[4 * o + 1] = __dsub_rn(E_new[4 * o + 1], p.x1);
+        E_new[4 * o + 2] = __dsub_rn(E_new[4 * o + 2], p.x2);
+        E_new[4 * o + 3] = __dsub_rn(E_new[4 * o + 3], 1.0);
+        E_new[4 * e] = p.x0; E_new[4 * e + 1] = p.x1; E_new[4 * e + 2] = p.x2; E_new[4 * e + 3] = 1.0;
+        lab[bj] = (idx_t)(o | Cfg::FLAG);
+        ++e;
+    }
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) lab[i] = (idx_t)(lab[i] & (idx_t)~Cfg::FLAG);
+    rhccq_sk_average(E_new, k);
+}
 
 // Labels of KMeans(k, random_state=42, n_init='auto').fit_predict on the n colours at positions
 // [lo, lo + n).  On return A.label holds the labels and C.cnt the cluster sizes.  Group-uniform control
@@ -565,6 +716,7 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
     // X.mean(axis=0): the sums are exact integers, one rounding in the division
     const double mean[3] = {__ddiv_rn((double)S1[0], (double)n), __ddiv_rn((double)S1[1], (double)n),
                             __ddiv_rn((double)S1[2], (double)n)};
+    const float meanf[3] = {(float)mean[0], (float)mean[1], (float)mean[2]};
     for (int q = tid; q < 3; q += gsz)
         C.center[q] = __dsub_rn((double)((x[first] >> (16 - 8 * q)) & 255u), mean[q]);
     int ri = 1, prev_slot = -1;
@@ -649,31 +801,12 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
         }
         bool have_f = false;
         if (flag[0]) {
-            // float64 re-evaluation: closest distances of the centred data to the c centres chosen so far,
-            // the potential as the previous step's BLAS call summed it, np.cumsum, np.searchsorted
-            for (int j = c_lo; j < c_hi; ++j) {
-                const rhccq_sk_pt p = rhccq_sk_centred(x[j], mean);
-                double f = rhccq_sk_seed_dist(true, p, C.center);
-                for (int s = 1; s < c; ++s) { const double d = rhccq_sk_seed_dist(false, p, C.center + 3 * s); f = d < f ? d : f; }
-                ex[j] = f;
-            }
+            // float64 re-evaluation of the draws
+            if (tid == 0) RHCCQ_COUNT(12, 1);
+            rhccq_sk_closest_f(x, c_lo, c_hi, mean, C.center, c, ex);
             have_f = true;
             g.sync();
-            if (tid == 0) {
-                rhccq_sk_col col; col.f = ex; col.x = x; col.cand = nullptr; col.mean = mean;
-                const double pot_f = prev_slot < 0 ? rhccq_sk_ddot_ones(ex, n)
-                                                   : rhccq_sk_dgemv_t_ones(col, n, rhccq_sk_gemv_lanes(prev_slot, T));
-                double rv[RHCCQ_KM_MAXT];
-                int fnd[RHCCQ_KM_MAXT];
-                for (int t = 0; t < T; ++t) { rv[t] = __dmul_rn(rng[ri + t], pot_f); fnd[t] = -1; }
-                double s = 0.0;
-                int open = T;
-                for (int i = 0; i < n && open > 0; ++i) {
-                    s = __dadd_rn(s, ex[i]);
-                    for (int t = 0; t < T; ++t) if (fnd[t] < 0 && !(s < rv[t])) { fnd[t] = i; --open; }
-                }
-                for (int t = 0; t < T; ++t) C.cand[t] = fnd[t] < 0 ? n - 1 : fnd[t];
-            }
+            if (tid == 0) rhccq_sk_draw(x, n, mean, ex, prev_slot, T, rng + ri, C.cand);
             g.sync();
         }
         ri += T;
@@ -682,18 +815,35 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
         int cj[RHCCQ_KM_MAXT];
 #pragma unroll
         for (int t = 0; t < RHCCQ_KM_MAXT; ++t) { acc[t] = 0; cj[t] = t < T ? C.cand[t] : 0; xc[t] = t < T ? x[cj[t]] : 0u; }
-        for (int j = c_lo; j < c_hi; ++j) {
-            const uint32_t cjx = x[j], o = closest[j];
+        if (per <= 20000) {                                         // 20 000 x 195 075 < 2^32: 32-bit partial sums
+            uint32_t a32[RHCCQ_KM_MAXT];
 #pragma unroll
-            for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {
-                if (t < T) {
+            for (int t = 0; t < RHCCQ_KM_MAXT; ++t) a32[t] = 0u;
+            for (int j = c_lo; j < c_hi; ++j) {
+                const uint32_t cjx = x[j], o = closest[j];
+#pragma unroll
+                for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {
+                    if (t >= T) break;                              // uniform: no predicated-off slots are issued
+                    const uint32_t d = (uint32_t)rhccq_d2(cjx, xc[t]);
+                    a32[t] += d < o ? d : o;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < RHCCQ_KM_MAXT; ++t) acc[t] = (long long)a32[t];
+        } else {
+            for (int j = c_lo; j < c_hi; ++j) {
+                const uint32_t cjx = x[j], o = closest[j];
+#pragma unroll
+                for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {
+                    if (t >= T) break;
                     const uint32_t d = (uint32_t)rhccq_d2(cjx, xc[t]);
                     acc[t] += d < o ? d : o;
                 }
             }
         }
         g.sum_vec(acc, T);
-        int best = 0, tie = 0;
+        int best = 0;
+        unsigned tied = 0u;
         long long best_pot = acc[0];
 #pragma unroll
         for (int t = 1; t < RHCCQ_KM_MAXT; ++t) if (t < T && acc[t] < best_pot) { best_pot = acc[t]; best = t; }
@@ -701,30 +851,15 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
         // only candidates that tie in the integers — and are different colours — need the float64 sums
 #pragma unroll
         for (int t = 0; t < RHCCQ_KM_MAXT; ++t)
-            if (t < T && t != best && (acc[t] == best_pot || RHCCQ_KM_FORCED) && cj[t] != cj[best]) tie = 1;
+            if (t < T && (acc[t] == best_pot || RHCCQ_KM_FORCED)) tied |= 1u << t;
+        bool tie = false;
+#pragma unroll
+        for (int t = 0; t < RHCCQ_KM_MAXT; ++t) if (((tied >> t) & 1u) && cj[t] != cj[best]) tie = true;
         if (tie) {
-            if (!have_f) {
-                for (int j = c_lo; j < c_hi; ++j) {
-                    const rhccq_sk_pt p = rhccq_sk_centred(x[j], mean);
-                    double f = rhccq_sk_seed_dist(true, p, C.center);
-                    for (int s = 1; s < c; ++s) { const double d = rhccq_sk_seed_dist(false, p, C.center + 3 * s); f = d < f ? d : f; }
-                    ex[j] = f;
-                }
-            }
+            if (tid == 0) RHCCQ_COUNT(13, 1);
+            if (!have_f) rhccq_sk_closest_f(x, c_lo, c_hi, mean, C.center, c, ex);
             g.sync();
-            if (tid == 0) {
-                double bp = 0.0;
-                int bs = -1;
-                for (int t = 0; t < T; ++t) {
-                    if (!RHCCQ_KM_FORCED && acc[t] != best_pot) continue;
-                    const rhccq_sk_pt pc = rhccq_sk_centred(x[cj[t]], mean);
-                    const double cc[3] = {pc.x0, pc.x1, pc.x2};
-                    rhccq_sk_col col; col.f = ex; col.x = x; col.cand = cc; col.mean = mean;
-                    const double pf = rhccq_sk_dgemv_t_ones(col, n, rhccq_sk_gemv_lanes(t, T));
-                    if (bs < 0 || pf < bp) { bp = pf; bs = t; }
-                }
-                flag[1] = bs;
-            }
+            if (tid == 0) flag[1] = rhccq_sk_best(x, n, mean, ex, T, C.cand, tied);
             g.sync();
             best = flag[1];
             best_pot = acc[0];
@@ -775,60 +910,30 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
     const idx_t NOLABEL = (idx_t)(Cfg::FLAG - 1u);                  // never a real label (k < FLAG - 1)
     idx_t* lab_prev = A.label + lo;                                 // labels the centres `cen` come from
     idx_t* lab_cur = reinterpret_cast<idx_t*>(cum);                 // labels the E step writes
-    idx_t* und_list = reinterpret_cast<idx_t*>(cum) + n;            // positions whose E-step decision is open
+    idx_t* wl = reinterpret_cast<idx_t*>(cum) + n;                  // positions the E step evaluates; Cfg::FLAG: decision open
+    bool prune_valid = false;                                       // C.hb holds the pruning thresholds of the centres `cen`
     for (int j = tid; j < n; j += gsz) lab_prev[j] = NOLABEL;
     for (int q = tid; q < k; q += gsz) {
         C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0;
         C.csn[q] = rhccq_sk_norm3(C.center[3 * q], C.center[3 * q + 1], C.center[3 * q + 2]);
+        C.cf[4 * q] = (float)__dmul_rn(-2.0, C.center[3 * q]); C.cf[4 * q + 1] = (float)__dmul_rn(-2.0, C.center[3 * q + 1]);
+        C.cf[4 * q + 2] = (float)__dmul_rn(-2.0, C.center[3 * q + 2]); C.cf[4 * q + 3] = (float)C.csn[q];
     }
     double* cen = C.center;                                         // current / next centre tables, swapped per iteration
     double* cen_new = C.center_new;
     double* E_old = ex;                                             // float64 centres of the E step [4k]
     double* E_new = ex + 4 * (size_t)k;                             // float64 centres after the M step [4k]
     double* s2 = ex + 8 * (size_t)k;                                // center_shift ** 2 [k]
-    uint32_t* wl = reinterpret_cast<uint32_t*>(closest);           // dead after the seeding; positions of this range
     bool recount = true;                                            // add every point to the sums, subtract none
     bool cen_exact = true;                                          // `cen` holds the float64 centres themselves (seeds; after a relocation)
-    bool e_old_ready = false;                                       // E_old holds the float64 centres of this E step
+    bool final_pass = false;                                        // the closing E step (:737-749): labels only
     int changed = 0;
 
-    // float64 centres of the current E step (thread 0 of the group)
-    auto build_e_old = [&]() {
-        if (cen_exact) {
-            for (int q = 0; q < k; ++q) {
-                E_old[4 * q] = cen[3 * q]; E_old[4 * q + 1] = cen[3 * q + 1]; E_old[4 * q + 2] = cen[3 * q + 2];
-                E_old[4 * q + 3] = C.csn[q];
-            }
-        } else {
-            rhccq_sk_all_centers<Cfg>(x, lab_prev, n, k, mean, E_old);
-            rhccq_sk_average(E_old, k);
-        }
-    };
-    // center_shift_tot <= tol on E_old / E_new in float64: _center_shift, (shift ** 2).sum(), np.var (thread 0)
-    auto exact_converged = [&]() -> int {
-        for (int q = 0; q < k; ++q) {
-            double res = 0.0;
-            for (int d = 0; d < 3; ++d) { const double a = __dsub_rn(E_new[4 * q + d], E_old[4 * q + d]); res = __dadd_rn(res, __dmul_rn(a, a)); }
-            const double sh = __dsqrt_rn(res);
-            s2[q] = __dmul_rn(sh, sh);
-        }
-        double var[3];
-        for (int d = 0; d < 3; ++d) {
-            double s = 0.0;
-            for (int i = 0; i < n; ++i) {
-                const double xv = __dsub_rn((double)((x[i] >> (16 - 8 * d)) & 255u), mean[d]);
-                s = __dadd_rn(s, __dmul_rn(xv, xv));
-            }
-            var[d] = __ddiv_rn(s, (double)n);
-        }
-        const double tol_e = __dmul_rn(__ddiv_rn(__dadd_rn(__dadd_rn(var[0], var[1]), var[2]), 3.0), 1e-4);
-        return rhccq_sk_np_sum(s2, k) <= tol_e ? 1 : 0;
-    };
     // one point's new label: label arrays, change flag, integer sums
-    auto commit = [&](int j, uint32_t c, int bi, bool update) {
+    auto commit = [&](int j, uint32_t c, int bi) {
         const int old = (int)lab_prev[j];
         lab_cur[j] = (idx_t)bi;
-        if (!update) return;
+        if (final_pass) return;
         if (old != bi) changed = 1;
         if (old != bi || recount) {
             const int r = rhccq_key_r(c), gg = rhccq_key_g(c), b = rhccq_key_b(c);
@@ -840,89 +945,140 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
             atomicAdd(&C.cnt[bi], 1);
         }
     };
-    // E step: lab_cur <- nearest centre of every point (first minimum of the float64 scores).  `update`: keep the
-    // integer sums and the change flag (false for the closing E step, :737-749).
-    auto e_step = [&](bool first_iter, bool update) {
+
+    g.sync();
+    for (int it = 0; ; ++it) {
+        // ---- E step: lab_cur <- nearest centre of every point (first minimum of the float64 scores)
+        //
         // Pruning: a point whose distance to the centre of its previous cluster is safely less than half the
-        // distance from that centre to the nearest other centre keeps its cluster by the triangle inequality —
-        // every other centre is farther by >= 5e-5 in the squared distance, a hundred times the margin below.
+        // distance from that centre to the nearest other centre keeps its cluster by the triangle inequality.
+        // In float32: u = |x - c_a|^2 < 0.24975 m - 0.5 with m the squared distance from c_a to the nearest other
+        // centre; the float32 errors of u and m are below 0.15 and 0.3, so the true u is below 0.24975 m - 0.27 and
+        // every other centre is farther by m (1 - 2 sqrt(0.24975)) >= 5e-4 m >= 1e-3 in the squared distance (m > 2
+        // for the test to pass at all) — far above every margin of the levels below, so none of them is consulted.
         const double margin = cen_exact ? (RHCCQ_KM_FORCED ? 1.0e300 : (e_hi > e_lo ? 1.0e-9 : 0.0)) : margin_full;
-        const bool prune = !first_iter && !recount && !RHCCQ_KM_FORCED && C.wl != nullptr
-                           && (long long)n * k >= RHCCQ_PRUNE_MIN_WORK;
-        g.sync();                                                   // the tables below may still be read by slower threads
-        if (tid == 0) flag[0] = 0;                                  // number of open decisions
-        e_old_ready = false;
+        const bool prune = C.hb != nullptr && prune_valid && !RHCCQ_KM_FORCED;
+        bool e_old_ready = false;                                   // E_old holds the float64 centres of this E step
+        changed = 0;
+        if (tid == 0) { flag[0] = 0; flag[1] = 0; }                 // open decisions; length of the worklist
+        g.sync();
         if (prune) {
-            for (int q = tid; q < k; q += gsz) {
-                const double* cq = cen + 3 * q;
-                double m = 1.0e300;
-                for (int r = 0; r < k; ++r) {
-                    if (r == q) continue;
-                    const double d0 = __dsub_rn(cq[0], cen[3 * r]), d1 = __dsub_rn(cq[1], cen[3 * r + 1]), d2 = __dsub_rn(cq[2], cen[3 * r + 2]);
-                    const double d = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-                    m = d < m ? d : m;
-                }
-                C.term[q] = m >= 1.0 ? __dmul_rn(__dmul_rn(0.25, m), 0.9999) : 0.0;
-            }
-            if (tid == 0) *C.wl = 0;
-            g.sync();
+            const float* thr = reinterpret_cast<const float*>(C.hb);
             for (int j = tid; j - RHCCQ_LANE < n; j += gsz) {          // warp-uniform trip count
                 bool push = false;
                 if (j < n) {
-                    const rhccq_sk_pt p = rhccq_sk_centred(x[j], mean);
+                    const uint32_t c = x[j];
                     const int a = (int)lab_prev[j];
-                    const double* ca = cen + 3 * a;
-                    const double d0 = __dsub_rn(p.x0, ca[0]), d1 = __dsub_rn(p.x1, ca[1]), d2 = __dsub_rn(p.x2, ca[2]);
-                    const double u = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-                    push = !(u < C.term[a]);
+                    const float d0 = fmaf(0.5f, C.cf[4 * a], __fsub_rn((float)rhccq_key_r(c), meanf[0]));
+                    const float d1 = fmaf(0.5f, C.cf[4 * a + 1], __fsub_rn((float)rhccq_key_g(c), meanf[1]));
+                    const float d2 = fmaf(0.5f, C.cf[4 * a + 2], __fsub_rn((float)rhccq_key_b(c), meanf[2]));
+                    push = !(fmaf(d0, d0, fmaf(d1, d1, d2 * d2)) < thr[a]);
                     if (!push) lab_cur[j] = (idx_t)a;
                 }
                 const unsigned m = rhccq_ballot(push);                 // one counter bump per warp
                 int base = 0;
-                if (RHCCQ_LANE == 0 && m) base = atomicAdd(C.wl, __popc(m));
+                if (RHCCQ_LANE == 0 && m) base = atomicAdd(&flag[1], __popc(m));
                 base = rhccq_shfl(base, 0);
-                if (push) wl[base + __popc(m & rhccq_lanemask_lt())] = (uint32_t)j;
+                if (push) wl[base + __popc(m & rhccq_lanemask_lt())] = (idx_t)j;
+            }
+        } else {
+            for (int j = tid; j < n; j += gsz) wl[j] = (idx_t)j;
+        }
+        g.sync();
+        const int n_work = prune ? flag[1] : n;
+        // few points: one per thread (short dependent chains, every warp busy); many: RHCCQ_EB consecutive entries per
+        // thread (every centre is loaded once per RHCCQ_EB points)
+        if (n_work <= 2 * gsz) {
+            for (int i = tid; i < n_work; i += gsz) {
+                const int j = (int)wl[i];
+                const uint32_t cb[1] = {x[j]};
+                int bb[1];
+                bool und[1];
+                rhccq_nearest_centers_f32<1>(cb, meanf, C.cf, k, bb, und);
+                if (und[0] || RHCCQ_KM_FORCED) { wl[i] = (idx_t)(j | Cfg::FLAG); atomicAdd(&flag[0], 1); }   // decided below
+                else commit(j, cb[0], bb[0]);
+            }
+        } else {
+            for (int i0 = RHCCQ_EB * tid; i0 < n_work; i0 += RHCCQ_EB * gsz) {
+                uint32_t cb[RHCCQ_EB];
+                int bb[RHCCQ_EB], jj[RHCCQ_EB];
+                bool und[RHCCQ_EB];
+#pragma unroll
+                for (int u = 0; u < RHCCQ_EB; ++u) {
+                    const int i = i0 + u;
+                    jj[u] = (int)wl[i < n_work ? i : i0];               // slots past the end redo an entry and drop it
+                    cb[u] = x[jj[u]];
+                }
+                rhccq_nearest_centers_f32<RHCCQ_EB>(cb, meanf, C.cf, k, bb, und);
+#pragma unroll
+                for (int u = 0; u < RHCCQ_EB; ++u) {
+                    const int i = i0 + u;
+                    if (i >= n_work) continue;
+                    if (und[u] || RHCCQ_KM_FORCED) { wl[i] = (idx_t)(jj[u] | Cfg::FLAG); atomicAdd(&flag[0], 1); }
+                    else commit(jj[u], cb[u], bb[u]);
+                }
             }
         }
         g.sync();
-        const int n_work = prune ? *C.wl : n;
-        for (int i0 = tid; i0 < n_work; i0 += RHCCQ_EB * gsz) {
-            uint32_t cb[RHCCQ_EB];
-            int bb[RHCCQ_EB], jj[RHCCQ_EB];
-            bool und[RHCCQ_EB];
-#pragma unroll
-            for (int u = 0; u < RHCCQ_EB; ++u) {
-                const int i = i0 + u * gsz;
-                const int is = i < n_work ? i : i0;                     // lanes past the end redo an entry and drop it
-                jj[u] = prune ? (int)wl[is] : is;
-                cb[u] = x[jj[u]];
-            }
-            rhccq_nearest_centers(cb, mean, cen, C.csn, k, margin, bb, und);
-#pragma unroll
-            for (int u = 0; u < RHCCQ_EB; ++u) {
-                if (i0 + u * gsz >= n_work) continue;
-                if (und[u]) und_list[atomicAdd(&flag[0], 1)] = (idx_t)jj[u];   // decided below, on the float64 centres
-                else commit(jj[u], cb[u], bb[u], update);
-            }
-        }
-        g.sync();
-        const int n_und = flag[0];
-        if (n_und > 0) {
-            if (tid == 0) build_e_old();
-            e_old_ready = true;
+        const int n_und1 = flag[0];
+        if (tid == 0) { RHCCQ_COUNT(8, 1); RHCCQ_COUNT(14, n_und1); }
+        if (n_und1 > 0) {
+            // second level: float64 scores on the integer-derived centres
+            g.sync();                                               // every thread has read the count
+            if (tid == 0) flag[0] = 0;
             g.sync();
-            for (int i = tid; i < n_und; i += gsz) {
-                const int j = (int)und_list[i];
-                commit(j, x[j], rhccq_nearest_exact(x[j], mean, E_old, k, j, n, e_lo, e_hi), update);
+#pragma unroll 1
+            for (int base = g.sub() * RHCCQ_WARP_SIZE; base < n_work; base += g.nsub() * RHCCQ_WARP_SIZE) {
+                // the lanes look at 32 entries of the worklist; every open one is then decided by the whole warp,
+                // lanes over the centres
+                const int il = base + RHCCQ_LANE;
+                unsigned open = rhccq_ballot(il < n_work && (wl[il] & Cfg::FLAG) != 0);
+#pragma unroll 1
+                while (open) {
+                    const int i = base + __ffs((int)open) - 1;
+                    open &= open - 1u;
+                    const int j = (int)(wl[i] & (idx_t)~Cfg::FLAG);
+                    const rhccq_sk_pt p = rhccq_sk_centred(x[j], mean);
+                    double best = 1.0e300, sec = 1.0e300;
+                    int bi = 0x7fffffff;
+#pragma unroll 1
+                    for (int q = RHCCQ_LANE; q < k; q += RHCCQ_WARP_SIZE) {
+                        const double d = rhccq_sk_score(p, cen + 3 * q, C.csn[q], false);
+                        if (d < best) { sec = best; best = d; bi = q; }
+                        else if (d < sec) sec = d;
+                    }
+#pragma unroll
+                    for (int o = RHCCQ_WARP_SIZE >> 1; o > 0; o >>= 1) {
+                        const double ob = rhccq_shfl_xor(best, o), os = rhccq_shfl_xor(sec, o);
+                        const int oi = rhccq_shfl_xor(bi, o);
+                        const double hi = ob > best ? ob : best, lo2 = os < sec ? os : sec;
+                        sec = hi < lo2 ? hi : lo2;                      // runner-up of the union
+                        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                    }
+                    __syncwarp();
+                    if (RHCCQ_LANE == 0) {
+                        if (sec < __dadd_rn(best, margin)) atomicAdd(&flag[0], 1);
+                        else { commit(j, x[j], bi); wl[i] = (idx_t)j; }
+                    }
+                    __syncwarp();
+                }
+            }
+            g.sync();
+            if (flag[0] > 0) {
+                // third level: the float64 centres of scikit-learn's M step, one thread
+                if (tid == 0) { RHCCQ_COUNT(15, 1); }
+                if (tid == 0) rhccq_sk_e_old<Cfg>(x, lab_prev, n, k, mean, cen, C.csn, cen_exact, E_old);
+                e_old_ready = true;
+                g.sync();
+#pragma unroll 1
+                for (int i = tid; i < n_work; i += gsz) {
+                    if (!(wl[i] & Cfg::FLAG)) continue;
+                    const int j = (int)(wl[i] & (idx_t)~Cfg::FLAG);
+                    commit(j, x[j], rhccq_nearest_exact(x[j], mean, E_old, k, j, n, e_lo, e_hi));
+                }
             }
         }
-    };
-
-    g.sync();
-    bool strict = false;
-    for (int it = 0; it < 300; ++it) {
-        changed = 0;
-        e_step(it == 0, true);
+        if (final_pass) { idx_t* t = lab_prev; lab_prev = lab_cur; lab_cur = t; break; }
         recount = false;
         changed = g.any(changed);
         int empty = 0;
@@ -931,48 +1087,12 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
         int decided = 0;
         bool next_exact = false;
         if (n_empty > 0) {
-            // Empty clusters (_k_means_common.pyx:167-211): everything in float64, one thread.  The points
-            // farthest from their (old) centres, farthest first, ties to the higher index, give their colour to
-            // the empty clusters in ascending order; the donor's sum loses it by one float64 subtraction.
+            // everything in float64, one thread; the new centres are the float64 ones themselves
             if (tid == 0) {
-                if (!e_old_ready) build_e_old();
-                rhccq_sk_all_centers<Cfg>(x, lab_cur, n, k, mean, E_new);
-                for (int q = 0; q < k; ++q) s2[q] = E_new[4 * q + 3] == 0.0 ? 1.0 : 0.0;   // the empty set is fixed first
-                double mx = 0.0;
-                for (int i = 0; i < n; ++i) {
-                    const rhccq_sk_pt p = rhccq_sk_centred(x[i], mean);
-                    const double* ce = E_old + 4 * (int)lab_cur[i];
-                    const double a0 = __dsub_rn(p.x0, ce[0]), a1 = __dsub_rn(p.x1, ce[1]), a2 = __dsub_rn(p.x2, ce[2]);
-                    const double d = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
-                    if (d > mx) mx = d;
-                }
-                if (mx != 0.0) {
-                    int e = 0;
-                    for (int done = 0; done < n_empty; ++done) {
-                        while (s2[e] == 0.0) ++e;
-                        double bm = -1.0;
-                        int bj = 0;
-                        for (int i = 0; i < n; ++i) {
-                            if (lab_cur[i] & Cfg::FLAG) continue;                  // already taken
-                            const rhccq_sk_pt p = rhccq_sk_centred(x[i], mean);
-                            const double* ce = E_old + 4 * (int)lab_cur[i];
-                            const double a0 = __dsub_rn(p.x0, ce[0]), a1 = __dsub_rn(p.x1, ce[1]), a2 = __dsub_rn(p.x2, ce[2]);
-                            const double d = __dadd_rn(__dadd_rn(__dmul_rn(a0, a0), __dmul_rn(a1, a1)), __dmul_rn(a2, a2));
-                            if (d >= bm) { bm = d; bj = i; }                         // ascending i: the last maximum stays
-                        }
-                        const int o = (int)lab_cur[bj];
-                        const rhccq_sk_pt p = rhccq_sk_centred(x[bj], mean);
-                        E_new[4 * o] = __dsub_rn(E_new[4 * o], p.x0); E_new[4 * o + 1] = __dsub_rn(E_new[4 * o + 1], p.x1);
-                        E_new[4 * o + 2] = __dsub_rn(E_new[4 * o + 2], p.x2);
-                        E_new[4 * o + 3] = __dsub_rn(E_new[4 * o + 3], 1.0);
-                        E_new[4 * e] = p.x0; E_new[4 * e + 1] = p.x1; E_new[4 * e + 2] = p.x2; E_new[4 * e + 3] = 1.0;
-                        lab_cur[bj] = (idx_t)(o | Cfg::FLAG);
-                        ++e;
-                    }
-                    for (int i = 0; i < n; ++i) lab_cur[i] = (idx_t)(lab_cur[i] & (idx_t)~Cfg::FLAG);
-                }
-                rhccq_sk_average(E_new, k);
-                flag[1] = exact_converged();
+                if (!e_old_ready) rhccq_sk_e_old<Cfg>(x, lab_prev, n, k, mean, cen, C.csn, cen_exact, E_old);
+                rhccq_sk_relocate<Cfg>(x, lab_cur, n, k, n_empty, mean, E_old, E_new, s2);
+                flag[1] = rhccq_sk_converged(x, n, k, mean, E_old, E_new, s2);
+#pragma unroll 1
                 for (int q = 0; q < k; ++q) {
                     cen_new[3 * q] = E_new[4 * q]; cen_new[3 * q + 1] = E_new[4 * q + 1]; cen_new[3 * q + 2] = E_new[4 * q + 2];
                     C.csn[q] = E_new[4 * q + 3];
@@ -981,8 +1101,13 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
             g.sync();
             decided = flag[1];
             next_exact = true;
+            prune_valid = false;                                    // C.hb was not recomputed for the relocated centres
             recount = true;                                         // the integer sums no longer follow the labels
-            for (int q = tid; q < k; q += gsz) { C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0; }
+            for (int q = tid; q < k; q += gsz) {
+                C.cnt[q] = 0; C.sums[3 * q] = 0; C.sums[3 * q + 1] = 0; C.sums[3 * q + 2] = 0;
+                C.cf[4 * q] = (float)__dmul_rn(-2.0, cen_new[3 * q]); C.cf[4 * q + 1] = (float)__dmul_rn(-2.0, cen_new[3 * q + 1]);
+                C.cf[4 * q + 2] = (float)__dmul_rn(-2.0, cen_new[3 * q + 2]); C.cf[4 * q + 3] = (float)C.csn[q];
+            }
         } else {
             for (int q = tid; q < k; q += gsz) {
                 const double cn = (double)C.cnt[q];
@@ -1011,10 +1136,11 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                 if (diff <= band || RHCCQ_KM_FORCED) {
                     g.sync();
                     if (tid == 0) {
-                        if (!e_old_ready) build_e_old();
+                        RHCCQ_COUNT(11, 1);
+                        if (!e_old_ready) rhccq_sk_e_old<Cfg>(x, lab_prev, n, k, mean, cen, C.csn, cen_exact, E_old);
                         rhccq_sk_all_centers<Cfg>(x, lab_cur, n, k, mean, E_new);
                         rhccq_sk_average(E_new, k);
-                        flag[1] = exact_converged();
+                        flag[1] = rhccq_sk_converged(x, n, k, mean, E_old, E_new, s2);
                     }
                     g.sync();
                     decided = flag[1];
@@ -1023,17 +1149,36 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                 }
             }
             g.sync();                                               // term / csn are rewritten next
-            for (int q = tid; q < k; q += gsz) C.csn[q] = rhccq_sk_norm3(cen_new[3 * q], cen_new[3 * q + 1], cen_new[3 * q + 2]);
+            for (int q = tid; q < k; q += gsz) {
+                C.csn[q] = rhccq_sk_norm3(cen_new[3 * q], cen_new[3 * q + 1], cen_new[3 * q + 2]);
+                C.cf[4 * q] = (float)__dmul_rn(-2.0, cen_new[3 * q]); C.cf[4 * q + 1] = (float)__dmul_rn(-2.0, cen_new[3 * q + 1]);
+                C.cf[4 * q + 2] = (float)__dmul_rn(-2.0, cen_new[3 * q + 2]); C.cf[4 * q + 3] = (float)C.csn[q];
+            }
+            if (C.hb != nullptr) {
+                // pruning thresholds of the new centres: 0.24975 m - 0.5, m = squared distance to the nearest other centre
+                g.sync();
+                float* thr = reinterpret_cast<float*>(C.hb);
+                for (int q = g.sub(); q < k; q += g.nsub()) {           // one warp per centre, lanes over the others
+                    float m = 3.0e38f;
+                    const float q0 = C.cf[4 * q], q1 = C.cf[4 * q + 1], q2 = C.cf[4 * q + 2];
+                    for (int r = RHCCQ_LANE; r < k; r += RHCCQ_WARP_SIZE) {
+                        const float d0 = q0 - C.cf[4 * r], d1 = q1 - C.cf[4 * r + 1], d2 = q2 - C.cf[4 * r + 2];
+                        const float d = 0.25f * fmaf(d0, d0, fmaf(d1, d1, d2 * d2));      // cf holds -2 c
+                        m = (r != q && d < m) ? d : m;
+                    }
+#pragma unroll
+                    for (int o = RHCCQ_WARP_SIZE >> 1; o > 0; o >>= 1) m = fminf(m, rhccq_shfl_xor(m, o));
+                    if (RHCCQ_LANE == 0) thr[q] = fmaf(0.24975f, m, -0.5f);
+                }
+                prune_valid = true;
+            }
         }
         { double* t = cen; cen = cen_new; cen_new = t; }
         { idx_t* t = lab_prev; lab_prev = lab_cur; lab_cur = t; }
         cen_exact = next_exact;
-        if (!changed) { strict = true; break; }                     // :717-722
-        if (decided) break;                                         // :724-733
-    }
-    if (!strict) {                                                  // :737-749: labels that match the final centres
-        e_step(false, false);
-        idx_t* t = lab_prev; lab_prev = lab_cur; lab_cur = t;
+        if (!changed) break;                                        // strict convergence (:717-722): the labels stand
+        if (decided || it == 299) final_pass = true;                // :724-733 / max_iter: one E step with the final centres
+        g.sync();                                                   // the tables above are read by the next E step
     }
     // the result belongs in A.label (the partition that follows overwrites `cum`)
     g.sync();
@@ -1085,6 +1230,8 @@ __device__ __forceinline__ void rhccq_carve_centers(rhccq_km_centers& C, unsigne
     C.center_new = cv.take<double>(3 * kc);
     C.term = cv.take<double>(kc);
     C.csn = cv.take<double>(kc);
+    C.cf = cv.take<float>(4 * kc);
+    C.hb = cv.take<int>(kc);
     C.sums = cv.take<int>(3 * kc);
     C.cnt = cv.take<int>(kc);
 }
@@ -1096,8 +1243,8 @@ __host__ __device__ static inline size_t rhccq_split_row_bytes(size_t rows) {
            + rhccq_carve_bytes(rows, sizeof(idx_t)) * 2 + rhccq_carve_bytes(rows, sizeof(typename Cfg::q_t));
 }
 __host__ __device__ static inline size_t rhccq_split_center_bytes(size_t kc) {
-    return rhccq_carve_bytes(3 * kc, 8) * 2 + rhccq_carve_bytes(kc, 8) * 2 + rhccq_carve_bytes(3 * kc, 4)
-           + rhccq_carve_bytes(kc, 4);
+    return rhccq_carve_bytes(3 * kc, 8) * 2 + rhccq_carve_bytes(kc, 8) * 2 + rhccq_carve_bytes(4 * kc, 4)
+           + rhccq_carve_bytes(kc, 4) + rhccq_carve_bytes(3 * kc, 4) + rhccq_carve_bytes(kc, 4);
 }
 
 size_t rhccq_palette_split_ws_bytes(int max_rows) {
@@ -1221,6 +1368,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     typedef typename Cfg::idx_t idx_t;
     typedef typename Cfg::q_t q_t;
     __shared__ long long s_ll[RHCCQ_MAX_WARPS * RHCCQ_KM_MAXT + 2];
+    __shared__ long long s_sv[2 * RHCCQ_SPLIT_MAX_WARPS * RHCCQ_KM_MAXT];
     __shared__ int s_scan[RHCCQ_MAX_WARPS + 2];
     __shared__ int s_tail, s_err, s_base, s_claim, s_wl;
     __shared__ int wlc[RHCCQ_MAX_WARPS];
@@ -1262,6 +1410,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
     int* cand = sv.take<int>((nw + 1) * RHCCQ_KM_CAND);
     double* wcent = sv.take<double>(nw * 8 * RHCCQ_KW);
     int* wint = sv.take<int>(nw * 5 * RHCCQ_KW);
+    float* wcf = sv.take<float>(nw * 4 * RHCCQ_KW);
     int* poff = sv.take<int>(nw * RHCCQ_KC);
     CS.cand = CG.cand = cand + nw * RHCCQ_KM_CAND;
 
@@ -1370,7 +1519,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
 
     RHCCQ_PROF(0);                                                 // prologue
     // ---- level-synchronous splitting
-    rhccq_grp_cta gc; gc.sll = s_ll;
+    rhccq_grp_cta gc; gc.sll = s_ll; gc.svb = s_sv; gc.svp = 0;
     gc.csum = reinterpret_cast<unsigned long long*>(poff);         // the partition table is idle during a seeding (8 B x threads fit)
     rhccq_grp_warp gw; gw.csum = nullptr;
     int head = 0;
@@ -1394,6 +1543,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
             }
             if (in_smem) {
                 rhccq_km_centers C = CS;
+                if (k < RHCCQ_PRUNE_MIN_K) C.hb = nullptr;
                 C.hist = nullptr;
                 C.poff = poff;
                 C.wl = &s_wl;
@@ -1403,6 +1553,7 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
                 C.hist = nullptr;
                 C.poff = nullptr;
                 C.wl = nullptr;
+                C.hb = nullptr;                                      // k * k centre pairs per iteration would not pay
                 rhccq_split_range<rhccq_grp_cta, Cfg>(gc, W, C, lo, hi, k, kforce ? 0x7fffffff : mcpc, rng, &s_tail, max_rows, &s_err);
             }
         }
@@ -1429,6 +1580,8 @@ __device__ __forceinline__ void rhccq_palette_split_problem(const rhccq_palette_
             int* wi = wint + (size_t)RHCCQ_WARP * 5 * RHCCQ_KW;
             C.center = wc; C.center_new = wc + 3 * RHCCQ_KW; C.term = wc + 6 * RHCCQ_KW; C.csn = wc + 7 * RHCCQ_KW;
             C.sums = wi; C.cnt = wi + 3 * RHCCQ_KW; C.poff = wi + 4 * RHCCQ_KW;
+            C.cf = wcf + (size_t)RHCCQ_WARP * 4 * RHCCQ_KW;
+            C.hb = nullptr;                                          // k <= RHCCQ_KW centres: evaluating them all is cheaper than pruning
             C.hist = nullptr;
             C.cand = cand + RHCCQ_WARP * RHCCQ_KM_CAND;
             C.wl = wlc + RHCCQ_WARP;
@@ -1506,6 +1659,7 @@ static size_t rhccq_split_small_bytes(int threads) {
 #endif
     return rhccq_carve_bytes((nw + 1) * RHCCQ_KM_CAND, 4)
            + rhccq_carve_bytes(nw * 8 * RHCCQ_KW, 8) + rhccq_carve_bytes(nw * 5 * RHCCQ_KW, 4)
+           + rhccq_carve_bytes(nw * 4 * RHCCQ_KW, 4)
            + rhccq_carve_bytes(nw * RHCCQ_KC, 4);
 }
 
@@ -1522,8 +1676,8 @@ static int rhccq_launch_split_cfg(const rhccq_palette_batch& B, const int* label
     const size_t cent_s = rhccq_split_center_bytes(kc_s);
     const size_t slice = rhccq_palette_split_ws_bytes(max_rows);
     const size_t slices = ws.ws ? ws.ws_bytes / slice : 0;
-    // everything the kernel needs next to its ~3.3 KB of static shared memory, within the 227 KB of an SM
-    const int rows_in_smem = small + row_bytes + cent_s + 4096 <= 227 * 1024;
+    // everything the kernel needs next to its ~6.4 KB of static shared memory, within the 227 KB of an SM
+    const int rows_in_smem = small + row_bytes + cent_s + 7168 <= 227 * 1024;
     if (slices == 0) {
         rhccq_set_error("rhccq_palette_split: the workspace (%zu bytes) holds no slice of %zu bytes (float64 scratch, "
                         "centre tables%s)", ws.ws_bytes, slice, rows_in_smem ? "" : ", per-row working set");
@@ -1570,7 +1724,7 @@ int rhccq_launch_palette_split(const rhccq_palette_batch& B, const int* labels, 
 #if defined(RHCCQ_SPLIT_PROFILE) && !defined(RHCCQ_HOST_EMU)
 // tools/split_phases.py: copy out (reset != 0: clear) the phase counters
 extern "C" int rhccq_split_prof_read(unsigned long long* host_out, int reset) {
-    if (reset) { unsigned long long z[8] = {0}; return (int)cudaMemcpyToSymbol(rhccq_split_prof, z, sizeof z); }
-    return (int)cudaMemcpyFromSymbol(host_out, rhccq_split_prof, 8 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[16] = {0}; return (int)cudaMemcpyToSymbol(rhccq_split_prof, z, sizeof z); }
+    return (int)cudaMemcpyFromSymbol(host_out, rhccq_split_prof, 16 * sizeof(unsigned long long));
 }
 #endif
