@@ -151,35 +151,122 @@ def cpu_pool():
     return mp.get_context("fork").Pool(cores), cores
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+_REF = None
+
+
+def _ref_modules():
+    """The reference's own modules (encoder/compression/{clustering,merging,regions,image}.py), unmodified, from the
+    git-ignored copy __graft_entry__.build() makes under baseline/_ref/ where /root/reference is mounted; None
+    when that copy is absent."""
+    global _REF
+    if _REF is None:
+        if not os.path.exists(os.path.join(REF_DIR, "encoder", "compression", "clustering.py")):
+            _REF = False
+        else:
+            import contextlib, io, warnings
+            sys.dont_write_bytecode = True
+            sys.path.insert(0, REF_DIR)
+            warnings.filterwarnings("ignore")
+            with contextlib.redirect_stdout(io.StringIO()):
+                from encoder.compression import clustering, merging, regions, image
+            _REF = (clustering, merging, regions, image)
+    return _REF or None
+
+
+def _ref_quiet():
+    """Worker start: the reference prints ~25 lines per call; and one scikit-learn thread per process (the segments
+    are spread over one process per core: OpenMP teams on top of that only oversubscribe the cores)."""
+    sys.stdout = open(os.devnull, "w")
+    try:
+        from threadpoolctl import threadpool_limits
+        globals()["_REF_LIMIT"] = threadpool_limits(1)
+    except ImportError:
+        pass
+
+
+def _ref_seg_job(args):
+    """One pass of the reference's per-segment loop (encoder/compression/subregions.py:315-449) on its own
+    get_all_unique_colors / compute_clustering_params / cluster_palette_colors_parallel; the driver module itself
+    needs scikit-image (SLIC), so the loop is walked with the label map supplied, as tests/golden/make_golden.py does."""
+    clustering = _ref_modules()[0]
+    img, region, sid, q = args
+    minr, minc, maxr, maxc = region["bbox"]
+    region_image = img[minr:maxr, minc:maxc]
+    mask = (region["segments"] == sid) & region["bbox_mask"]
+    rows, cols = np.where(mask)
+    if len(rows) == 0:
+        return None
+    h, w = region_image.shape[:2]
+    r0, r1 = max(0, rows.min() - 2), min(h - 1, rows.max() + 2)
+    c0, c1 = max(0, cols.min() - 2), min(w - 1, cols.max() + 2)
+    crop, cm = region_image[r0:r1 + 1, c0:c1 + 1], mask[r0:r1 + 1, c0:c1 + 1]
+    seg_img = np.zeros_like(crop)
+    seg_img[cm] = crop[cm]                                           # synth images hold no true black: no repaint
+    comp = clustering.get_all_unique_colors(seg_img, (int(r0 + minr), int(c0 + minc)))
+    eps, _, mcpc = clustering.compute_clustering_params(comp["actual_colors"], q, "lab")
+    return clustering.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=mcpc)
+
+
+def reference_encode_frame(img: np.ndarray, tile: int, pool, qualities=(20, 10)):
+    """encoder/compression/test.py:100-142 on the reference's own functions, stage-1 segments over `pool`."""
+    import contextlib, io
+    _, merging, regions, image = _ref_modules()
+    from roibasedimagecompression_b200.synth import tile_regions
+    H, W, _ = img.shape
+    roi, non = tile_regions(H, W, tile)
+    stage1 = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for regs, q in ((roi, qualities[0]), (non, qualities[1])):
+            out = []
+            for region in regs:
+                ids = np.unique(region["segments"])
+                jobs = [(img, region, int(sid), q) for sid in ids[ids != 0]]
+                comps = [c for c in (pool.map(_ref_seg_job, jobs, chunksize=2) if pool else map(_ref_seg_job, jobs)) if c is not None]
+                out.append(merging.merge_region_components_simple(comps, tuple(region["bbox"])) if len(comps) > 1 else comps)
+            stage1.append(out)
+        q2 = [min(100, 2 * q) for q in qualities]
+        r = regions.region_quantization(stage1[0], H, W, quality=q2[0])
+        n = regions.region_quantization(stage1[1], H, W, quality=q2[1])
+        return image.quantize_image(r + n, H, W, quality=min(100, sum(q2)))
+
+
 def run_reference(args, rank: int):
-    """--impl reference: the CPU implementation of the same path (the oracle port of the reference's
-    Python modules; the reference itself cannot travel to the GPU box) on all host cores.  One step =
-    one frame of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores — its unmodified
+    modules from baseline/_ref (scikit-learn included), the independent stage-1 segments spread over processes;
+    the oracle port when that copy is absent.  One step = a bounded sample of the workload: the top-left
+    512x256 of a frame, 32 segments (the reference needs ~4 s of one core per 64x64 segment: 40 core-minutes for
+    a 1920x1080 frame)."""
     if rank != 0:
         return
     B, H, W, tile, desc = WORKLOADS[args.workload]
     from roibasedimagecompression_b200.synth import synth
-    pool, cores = cpu_pool()
+    ref = _ref_modules()
+    sh, sw = (256, 512) if ref else (H, W)
+    import multiprocessing as mp
+    cores = min(os.cpu_count() or 1, 64)
+    pool = mp.get_context("fork").Pool(cores, initializer=_ref_quiet if ref else None) if cores > 1 else None
     times = []
     for s in range(args.warmup + args.steps):
-        img = synth(H, W, 1234 + (s % B))
+        img = np.ascontiguousarray(synth(H, W, 1234 + (s % B))[:sh, :sw])
         t0 = time.perf_counter()
-        oracle_encode_frame(img, tile, pool)
+        (reference_encode_frame if ref else oracle_encode_frame)(img, tile, pool)
         dt = time.perf_counter() - t0
         if s >= args.warmup:
             times.append(dt)
     if pool:
         pool.terminate()
     ms = 1e3 * float(np.mean(times))
-    v = H * W / 1e6 / (ms / 1e3)
+    v = sh * sw / 1e6 / (ms / 1e3)
+    what = ("the reference's own modules (baseline/_ref: encoder/compression/{clustering,merging,regions,image}.py, "
+            "scikit-learn)") if ref else "oracle/rhccq_oracle.py (numpy port; baseline/_ref absent)"
     print(json.dumps({
         "impl": "reference", "metric": "encode megapixels/sec (DBSCAN+region quantize)", "value": v,
         "unit": "MPx/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload + ": " + desc, "step": f"one {W}x{H} frame of the batch per step"},
-        "cpu_baseline": {"value": v, "unit": "MPx/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} frames of {W}x{H} (oracle/rhccq_oracle.py, stage-1 segments over "
-                                   f"{cores} processes)"},
+        "config": {"workload": args.workload + ": " + desc, "step": f"the top-left {sw}x{sh} of one frame of the batch per step"},
+        "cpu_baseline": {"value": v, "unit": "MPx/s", "cores": cores, "kind": "reference" if ref else "port",
+                         "sample": f"{args.steps} samples of {sw}x{sh} ({what}, stage-1 segments over {cores} processes)"},
         "e2e": {"value": v, "unit": "MPx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -319,8 +406,47 @@ def dbscan_probe(be, args, eps=None, min_pts=None):
                          "algorithmic_bytes_per_launch": DBSCAN_BYTES_PER_POINT * n, "avg_launch_ms": cms / cn}}
 
 
+def encode_probe(be, B, H, W, tile, steps, warmup):
+    """Device-resident and end-to-end encode of B synthetic HxW images (tile segmentation): ms, MPx/s, kernels."""
+    import torch
+    from roibasedimagecompression_b200 import pipeline
+    imgs_np, labs_np, table = make_inputs(B, H, W, tile, 1234)
+    h_img, h_lab = torch.from_numpy(imgs_np).pin_memory(), torch.from_numpy(labs_np).pin_memory()
+    d_img, d_lab = h_img.cuda(), h_lab.cuda()
+    for _ in range(warmup):
+        res = pipeline.encode_batch(be, d_img, d_lab, table)
+    pipeline.finish_checks(res)
+    torch.cuda.synchronize()
+    be.kernel_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        res = pipeline.encode_batch(be, d_img, d_lab, table)
+    e1.record(); torch.cuda.synchronize()
+    kt = be.kernel_times_ms(); be.kernel_timing(False)
+    ms = e0.elapsed_time(e1) / steps
+    enc = pipeline.HostEncoder(be, table)
+    for _ in enc.encode_many([(h_img, h_lab)] * 2):
+        pass
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for pals, idx in enc.encode_many([(h_img, h_lab)] * steps):
+        pass
+    torch.cuda.synchronize()
+    e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    px = B * H * W
+    return {"workload": f"{B} x {W}x{H} synthetic image(s), {tile} px checker tiles, qualities 20/10->40/20->60",
+            "ms_per_step": ms, "value": px / 1e6 / (ms / 1e3), "unit": "MPx/s", "steps": steps, "warmup": warmup,
+            "palette_colours": int(len(pals[0])),
+            "e2e": {"value": px / 1e6 / (e_ms / 1e3), "unit": "MPx/s", "ms_per_step": e_ms,
+                    "h2d_bytes_per_step": enc.h2d_bytes, "d2h_bytes_per_step": enc.d2h_bytes + sum(p.size for p in pals)},
+            "kernels_ms_per_step": {k: t / steps for k, (c, t) in sorted(kt.items(), key=lambda kv: -kv[1][1])}}
+
+
 # --------------------------------------------------------------------------- strip-sharded DBSCAN (C4)
-def run_strips(args, be, rank, world, local, H, W, desc):
+def measure_strips(args, be, rank, world, local, H, W, desc, steps, warmup):
+    """One 7680x4320 image as strips of rows + halo, one strip per rank (BASELINE configs[3]); returns the bench
+    line (every rank; rank 0 prints it or embeds it in the default line)."""
     import torch
     import torch.distributed as dist
     from roibasedimagecompression_b200 import dbscan as D
@@ -338,8 +464,8 @@ def run_strips(args, be, rank, world, local, H, W, desc):
     st = D.StripDbscan(be, eng, (l1 - l0) * W, l0 * W, ((r0 - l0) * W, (r1 - l0) * W),
                        [((a - l0) * W, (b - l0) * W) for a, b in zone])
     info = {}
-    for _ in range(args.warmup):
-        labels, core = st.run(d_rows, info)
+    for _ in range(warmup):
+        labels, core = st.run(d_rows)
     torch.cuda.synchronize()
     sampler = ClockSampler(local); sampler.start()
     if world > 1: dist.barrier()
@@ -347,12 +473,13 @@ def run_strips(args, be, rank, world, local, H, W, desc):
     l0_launch = be.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        labels, core = st.run(d_rows, info)
+    for _ in range(steps):
+        labels, core = st.run(d_rows)
     e1.record(); torch.cuda.synchronize()
     if world > 1: dist.barrier()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
+    st.run(d_rows, info)                                            # (outside the timed region: reads counters back)
+    ms = e0.elapsed_time(e1) / steps
     l_launches = be.launches - l0_launch
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
@@ -360,7 +487,7 @@ def run_strips(args, be, rank, world, local, H, W, desc):
     # the count kernel of this rank's strip (per-kernel CUDA events, separate short pass) against the HBM roofline
     be.kernel_timing(True)
     for _ in range(2):
-        st.run(d_rows, info)
+        st.run(d_rows)
     torch.cuda.synchronize()
     kt = be.kernel_times_ms(); be.kernel_timing(False)
     cn, cms = kt["rhccq_dbscan_lattice_count"]
@@ -380,28 +507,35 @@ def run_strips(args, be, rank, world, local, H, W, desc):
     h_out = torch.empty(own1 - own0, dtype=torch.int32).pin_memory()
     def e2e_step():
         d_rows.copy_(h_rows, non_blocking=True)
-        lab, _ = st.run(d_rows, info)
+        lab, _ = st.run(d_rows)
         h_out.copy_(lab, non_blocking=True)                         # (labels of the rank's own rows)
     e2e_step(); torch.cuda.synchronize()
     if world > 1: dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
-    e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    halo = max(r0 - l0, l1 - r1)                                    # rows this rank reads beyond its own (largest side)
     if world > 1:
-        t = torch.tensor([e_ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e_ms = float(t.item())
+        t = torch.tensor([e_ms, float(halo)], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms, halo = float(t[0].item()), int(t[1].item())
     e2e = {"value": n / (e_ms / 1e3), "unit": "points/s", "ms_per_step": e_ms,
            "h2d_bytes_per_step": int(h_rows.numel()), "d2h_bytes_per_step": int(h_out.numel() * 4)}
-    out = {"metric": "DBSCAN points/sec, one image strip-sharded (halo + NCCL boundary-edge merge)", "value": n / (ms / 1e3),
-           "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "c4: " + desc, "eps": eps, "min_pts": min_pts, "rows_per_rank": r1 - r0,
-                      "halo_rows": r0 - l0, "engine": "lattice kernels on uint8 rows", "boundary_edges_total": info.get("edges_total"),
-                      "clusters": info.get("roots_total"), "l2": "points larger than L2"},
-           "clocks": clocks, "gpu_launches": l_launches,
-           "e2e": e2e, "roofline": roofline}
+    return {"metric": "DBSCAN points/sec, one image strip-sharded (halo + NCCL boundary-edge merge)", "value": n / (ms / 1e3),
+            "unit": "points/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c4: " + desc, "eps": eps, "min_pts": min_pts, "rows_per_rank": r1 - r0,
+                       "halo_rows": halo, "engine": "lattice kernels on uint8 rows", "boundary_edges_total": info.get("edges_total"),
+                       "clusters": info.get("roots_total"), "l2": "points larger than L2"},
+            "clocks": clocks, "gpu_launches": l_launches,
+            "e2e": e2e, "roofline": roofline}
+
+
+def run_strips(args, be, rank, world, local, H, W, desc):
+    import torch.distributed as dist
+    out = measure_strips(args, be, rank, world, local, H, W, desc, args.steps, args.warmup)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -418,6 +552,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-dbscan", action="store_true", help="skip the short DBSCAN probe of the default line")
+    ap.add_argument("--no-c3", action="store_true", help="skip the 3840x2160 legs of the default line")
+    ap.add_argument("--no-strips", action="store_true", help="N > 1: skip the strip-sharded leg of the default line")
     ap.add_argument("--eps", type=float, default=3.0, help="c5 workloads: DBSCAN radius")
     ap.add_argument("--min-pts", type=int, default=8, help="c5 workloads: DBSCAN min_samples")
     args = ap.parse_args()
@@ -438,8 +574,6 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"                        # the version banner goes to stdout: keep it to one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     be = lib()                                                      # raises without librhccq.so / a B200
     B, H, W, tile, desc = WORKLOADS[args.workload]
@@ -497,17 +631,36 @@ def main():
                    "share": (t / args.steps) / ms_step} for k, (n, t) in sorted(ktimes.items(), key=lambda kv: -kv[1][1])}
     top, (top_n, top_ms) = max(ktimes.items(), key=lambda kv: kv[1][1])
     peak, peak_src = _peaks()
-    # every launch of the per-segment / per-pixel kernels covers all pixels of the rank's batch
-    achieved = ALGO_BYTES_PER_PIXEL * px_rank / 1e9 / ((top_ms / top_n) / 1e3)
-    roofline = {"kernel": top, "bound": "hbm", "note": "the dominant kernel of the encode is FP64-issue/latency bound (recursive "
+    # every launch of the per-segment / per-pixel kernels covers all pixels of the rank's batch.  The dominant entry
+    # point is launched once per stage on very unlike inputs (stage 1: every segment; stages 2 / 3: a few merged
+    # palettes), so the roofline figure is that of its LONGEST launch (mean over the timed steps), per launch below.
+    n_top = max(int(round(top_n / args.steps)), 1)
+    per_launch = [[] for _ in range(n_top)]
+    seen = {}
+    for i, (name, t) in enumerate(trace):
+        if name != top:
+            continue
+        stp = i // per_step if per_step else 0
+        j = seen.get(stp, 0)
+        seen[stp] = j + 1
+        if j < n_top:
+            per_launch[j].append(t)
+    launch_ms = [float(np.mean(v)) if v else 0.0 for v in per_launch]
+    dom = int(np.argmax(launch_ms))
+    algo = ALGO_BYTES_PER_PIXEL * px_rank
+    achieved = algo / 1e9 / (launch_ms[dom] / 1e3)
+    roofline = {"kernel": top, "bound": "hbm", "note": "the dominant kernel of the encode is latency / issue bound (recursive "
                 "K-Means on palettes in shared memory, DESIGN.md section 4); its HBM fraction is small by construction. "
                 "The HBM-shaped kernel of the path is the neighbour count: see the dbscan object of this line.",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, top), (None, None))[0],
                 "traffic_source": NCU_TRAFFIC.get((args.workload, top), (None, None))[1], "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIXEL * px_rank,
-                "avg_launch_ms": top_ms / top_n, "share_of_step": (top_ms / args.steps) / ms_step,
-                "step_gbs": ALGO_BYTES_PER_PIXEL * px_rank / 1e9 / (ms_step / 1e3)}
+                "algorithmic_bytes_per_launch": algo, "launch": f"launch {dom} of {n_top} per step (the stage-{dom + 1} call)",
+                "launch_ms": launch_ms[dom],
+                "launches": [{"stage": j + 1, "ms": launch_ms[j], "achieved": algo / 1e9 / (launch_ms[j] / 1e3) if launch_ms[j] else None,
+                              "frac": algo / 1e9 / (launch_ms[j] / 1e3) / peak if launch_ms[j] else None} for j in range(n_top)],
+                "share_of_step": (top_ms / args.steps) / ms_step,
+                "step_gbs": algo / 1e9 / (ms_step / 1e3)}
 
     # ---- end to end: host buffers in, host buffers out
     enc = pipeline.HostEncoder(be, table)
@@ -535,6 +688,19 @@ def main():
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "kernels": kernels,
         "last_step_launches_ms": last_step,
     }
+
+    # ---- BASELINE configs[2]: one 3840x2160 image through the same three stages (and eight of them in one batch,
+    # where the sequential MiniBatchKMeans chain of the stage-2 palettes amortises)
+    if rank == 0 and world == 1 and args.workload == "c2" and not args.no_c3:
+        out["c3"] = encode_probe(be, 1, 2160, 3840, 64, steps=5, warmup=3)
+        out["c3x8"] = encode_probe(be, 8, 2160, 3840, 64, steps=3, warmup=3)
+
+    # ---- BASELINE configs[3] beside the image-sharded line when there is more than one rank: one 7680x4320 image
+    # as strips of rows, the boundary union-find edges all-gathered over NCCL (every rank takes part)
+    if world > 1 and args.workload == "c2" and not args.no_strips:
+        B4, H4, W4, _, desc4 = WORKLOADS["c4"]
+        strips = measure_strips(args, be, rank, world, local, H4, W4, desc4, steps=20, warmup=5)
+        out["strips"] = strips
 
     # ---- the DBSCAN operator itself on pixel features (BASELINE configs 3-5), short run: neighbour-count roofline
     if rank == 0 and world == 1 and not args.no_dbscan:

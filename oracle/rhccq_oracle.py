@@ -437,6 +437,8 @@ def merge_region_components_simple(region_components: Sequence[dict], roi_bbox) 
         sh, sw = seg["shape"]
         pal = pack_rgb(np.asarray(seg["palette"], dtype=np.uint8).reshape(-1, 3))
         idx = np.asarray(seg["indices"]).astype(np.int64).reshape(sh, sw)
+        if len(pal) == 0:                                        # :69-72: no index is below len(palette)
+            continue
         r0 = seg["top_left"][0] - minr
         c0 = seg["top_left"][1] - minc
         rr, cc = np.meshgrid(np.arange(sh) + r0, np.arange(sw) + c0, indexing="ij")

@@ -981,22 +981,23 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                 base = rhccq_shfl(base, 0);
                 if (push) wl[base + __popc(m & rhccq_lanemask_lt())] = (idx_t)j;
             }
-        } else {
-            for (int j = tid; j < n; j += gsz) wl[j] = (idx_t)j;
         }
         g.sync();
+        // without pruning every position is evaluated in place and the open ones are collected at the head of wl
         const int n_work = prune ? flag[1] : n;
         // few points: one per thread (short dependent chains, every warp busy); many: RHCCQ_EB consecutive entries per
         // thread (every centre is loaded once per RHCCQ_EB points)
         if (n_work <= 2 * gsz) {
             for (int i = tid; i < n_work; i += gsz) {
-                const int j = (int)wl[i];
+                const int j = prune ? (int)wl[i] : i;
                 const uint32_t cb[1] = {x[j]};
                 int bb[1];
                 bool und[1];
                 rhccq_nearest_centers_f32<1>(cb, meanf, C.cf, k, bb, und);
-                if (und[0] || RHCCQ_KM_FORCED) { wl[i] = (idx_t)(j | Cfg::FLAG); atomicAdd(&flag[0], 1); }   // decided below
-                else commit(j, cb[0], bb[0]);
+                if (und[0] || RHCCQ_KM_FORCED) {                        // decided below
+                    const int slot = atomicAdd(&flag[0], 1);
+                    wl[prune ? i : slot] = (idx_t)(j | Cfg::FLAG);
+                } else commit(j, cb[0], bb[0]);
             }
         } else {
             for (int i0 = RHCCQ_EB * tid; i0 < n_work; i0 += RHCCQ_EB * gsz) {
@@ -1006,7 +1007,8 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
 #pragma unroll
                 for (int u = 0; u < RHCCQ_EB; ++u) {
                     const int i = i0 + u;
-                    jj[u] = (int)wl[i < n_work ? i : i0];               // slots past the end redo an entry and drop it
+                    const int is = i < n_work ? i : i0;                 // slots past the end redo an entry and drop it
+                    jj[u] = prune ? (int)wl[is] : is;
                     cb[u] = x[jj[u]];
                 }
                 rhccq_nearest_centers_f32<RHCCQ_EB>(cb, meanf, C.cf, k, bb, und);
@@ -1014,13 +1016,16 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                 for (int u = 0; u < RHCCQ_EB; ++u) {
                     const int i = i0 + u;
                     if (i >= n_work) continue;
-                    if (und[u] || RHCCQ_KM_FORCED) { wl[i] = (idx_t)(jj[u] | Cfg::FLAG); atomicAdd(&flag[0], 1); }
-                    else commit(jj[u], cb[u], bb[u]);
+                    if (und[u] || RHCCQ_KM_FORCED) {
+                        const int slot = atomicAdd(&flag[0], 1);
+                        wl[prune ? i : slot] = (idx_t)(jj[u] | Cfg::FLAG);
+                    } else commit(jj[u], cb[u], bb[u]);
                 }
             }
         }
         g.sync();
         const int n_und1 = flag[0];
+        const int n_scan = prune ? n_work : n_und1;                 // entries of wl that may carry Cfg::FLAG
         if (tid == 0) { RHCCQ_COUNT(8, 1); RHCCQ_COUNT(14, n_und1); }
         if (n_und1 > 0) {
             // second level: float64 scores on the integer-derived centres
@@ -1028,11 +1033,11 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
             if (tid == 0) flag[0] = 0;
             g.sync();
 #pragma unroll 1
-            for (int base = g.sub() * RHCCQ_WARP_SIZE; base < n_work; base += g.nsub() * RHCCQ_WARP_SIZE) {
+            for (int base = g.sub() * RHCCQ_WARP_SIZE; base < n_scan; base += g.nsub() * RHCCQ_WARP_SIZE) {
                 // the lanes look at 32 entries of the worklist; every open one is then decided by the whole warp,
                 // lanes over the centres
                 const int il = base + RHCCQ_LANE;
-                unsigned open = rhccq_ballot(il < n_work && (wl[il] & Cfg::FLAG) != 0);
+                unsigned open = rhccq_ballot(il < n_scan && (wl[il] & Cfg::FLAG) != 0);
 #pragma unroll 1
                 while (open) {
                     const int i = base + __ffs((int)open) - 1;
@@ -1071,7 +1076,7 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                 e_old_ready = true;
                 g.sync();
 #pragma unroll 1
-                for (int i = tid; i < n_work; i += gsz) {
+                for (int i = tid; i < n_scan; i += gsz) {
                     if (!(wl[i] & Cfg::FLAG)) continue;
                     const int j = (int)(wl[i] & (idx_t)~Cfg::FLAG);
                     commit(j, x[j], rhccq_nearest_exact(x[j], mean, E_old, k, j, n, e_lo, e_hi));

@@ -138,12 +138,20 @@ def cluster_palette_colors_parallel(quality, compressed_data, eps=10.0, min_samp
     keys = _rgb_to_keys(palette)
     if not np.any(keys != 0):                                                          # :197-199
         return compressed_data
-    if len(np.unique(keys)) != n_orig:
-        raise ValueError("palette rows must be distinct (true for every reference call site: the output of "
-                         "get_all_unique_colors and of merge_region_components_simple)")
-    _, leaf, m, new_keys = _cluster_device(be, keys, float(eps), int(max_colors_per_cluster), leaf_override,
-                                           quality=float(quality))
+    labels, leaf, m, new_keys = _cluster_device(be, keys, float(eps), int(max_colors_per_cluster), leaf_override,
+                                                quality=float(quality))
     new_palette = _keys_to_rgb(new_keys)
+    if len(np.unique(keys)) != n_orig and leaf_override is None:
+        # A palette handed on unmerged (merging.py:16-21) can hold a colour twice.  Rows of clusters that were
+        # split go back to palette rows through find_color_index (:803-808), which finds the FIRST row of a
+        # colour: that row takes the entry of the last split holding the colour (equal colours always share a
+        # split), every later duplicate row keeps the table's initial 0 (:373).
+        sizes = np.bincount(labels[labels >= 0], minlength=max(int(labels.max()) + 1, 1))
+        in_split = (labels >= 0) & (sizes[np.maximum(labels, 0)] > int(max_colors_per_cluster)) & (keys != 0)
+        _, first = np.unique(keys, return_index=True)
+        dup = np.ones(n_orig, dtype=bool)
+        dup[first] = False
+        leaf = np.where(in_split & dup, 0, leaf)
     lut = leaf.astype(np.uint16)                                                       # :373 (uint16 table)
     new_indices = lut[indices.astype(np.int64).ravel()].astype(np.int64)              # :377
     total = h * w

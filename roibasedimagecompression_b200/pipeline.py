@@ -160,6 +160,29 @@ def _dev(be: Backend, a, dtype=torch.int32):
     return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(be.device)
 
 
+def _refuse_duplicate_rows(keys, off: int, cnt: int, what: str) -> None:
+    """A palette that reaches the next clustering unmerged (merging.py:16-21 copies a single component) may
+    hold the same colour in two rows, when two clusters truncate to the same mean.  The reference then maps
+    only the first row of a colour (find_color_index, clustering.py:803-808) and leaves the other at index 0;
+    the entry tables of this pipeline hold one entry per colour, so that case is refused, never approximated."""
+    k = keys[off:off + cnt].cpu().numpy()
+    if np.unique(k).size != k.size:
+        raise RhccqError(f"{what}: the palette passed on unmerged holds a colour twice "
+                         "(reference behaviour: clustering.py:803-808 maps the first row only); not supported")
+
+
+def _single_component_groups(table: SegmentTable):
+    """Groups (image, class) whose only region has a single segment: [(group, segment index)]."""
+    seg_per_region = np.bincount(table.seg_region, minlength=table.R)
+    reg_per_group = np.bincount(table.region_group, minlength=table.B * table.K)
+    out = []
+    for r in np.flatnonzero(seg_per_region == 1):
+        g = int(table.region_group[r])
+        if reg_per_group[g] == 1:
+            out.append((g, int(np.flatnonzero(table.seg_region == r)[0])))
+    return out
+
+
 def stage1(be: Backend, images, labels, table: SegmentTable) -> dict:
     """Stage 1 for every segment of the batch and the per-region merge
     (encoder/compression/subregions.py:315-449, :634-683)."""
@@ -189,6 +212,8 @@ def stage1(be: Backend, images, labels, table: SegmentTable) -> dict:
                               params=table.dev(be, "q1", lambda: ops.quality_params(be, q1[cls_h], max_valid + 1)))
     nl1_h = s1["n_leaves"][:P].cpu().numpy()                        # the one host synchronisation
     ops.check_counts("stage 1", torch.from_numpy(nl1_h))
+    for _, p in table.__dict__.setdefault("_single_groups", _single_component_groups(table)):
+        _refuse_duplicate_rows(s1["new_keys"], int(pal_off_h[p]), int(nl1_h[p]), f"stage 1, segment {p}")
     ent_off_h = np.zeros(P + 1, dtype=np.int64)
     np.cumsum(nl1_h, out=ent_off_h[1:])
     E = int(ent_off_h[-1])
@@ -233,6 +258,13 @@ def encode_batch(be: Backend, images, labels, table: SegmentTable, *, keep_stage
     s2 = ops.cluster_palettes(be, Bm["color"], Bm["off"][:G], Bm["cnt"], None, max_rows=mr2,
                               params=ops.quality_params(be, np.tile(q2, B), mr2))
     fpos2 = ops.first_min(be, Bm["off"], Bm["cnt"], s2["n_leaves"], s2["leaf"], Bm["fpos"])
+    # an image with a single non-empty class hands its stage-2 palette to stage 3 unmerged (image.py:246-256)
+    grp_regions = np.diff(grp_first).reshape(B, K)
+    lone = [(b, int(np.flatnonzero(grp_regions[b])[0])) for b in range(B) if np.count_nonzero(grp_regions[b]) == 1]
+    if lone:
+        nl2_h, off2_h = s2["n_leaves"].cpu().numpy(), Bm["off"].cpu().numpy()
+        for b, k in lone:
+            _refuse_duplicate_rows(s2["new_keys"], int(off2_h[b * K + k]), int(nl2_h[b * K + k]), f"stage 2, image {b}")
     # ---- merge level C: classes -> image (image.py:246-256)
     img_first = (np.arange(B + 1) * K).astype(np.int32)
     ent_per_image = (ent_per_group + 1).reshape(B, K).sum(axis=1)
@@ -279,12 +311,12 @@ class HostEncoder:
         self.cuda = be.device.type == "cuda"
         self.d_img = [be.empty((B, H, W, 3), torch.uint8) for _ in range(2)]
         self.d_lab = [be.empty((K, B, H, W), torch.int32) for _ in range(2)]
-        self.h_idx = [torch.empty((B, H, W), dtype=torch.int16, pin_memory=self.cuda) for _ in range(2)]
+        self.h_idx = [torch.empty((B, H, W), dtype=torch.int16, pin_memory=self.cuda) for _ in range(3)]   # results: three slots
         self.h2d_bytes = self.d_img[0].numel() + 4 * self.d_lab[0].numel()
         self.d2h_bytes = 2 * self.h_idx[0].numel()
-        self.h_off = [torch.empty((B + 1,), dtype=torch.int32, pin_memory=self.cuda) for _ in range(2)]
-        self.h_cnt = [torch.empty((B,), dtype=torch.int32, pin_memory=self.cuda) for _ in range(2)]
-        self.h_keys = [torch.empty((B * 4096,), dtype=torch.int32, pin_memory=self.cuda) for _ in range(2)]   # palettes are ~10^2 rows
+        self.h_off = [torch.empty((B + 1,), dtype=torch.int32, pin_memory=self.cuda) for _ in range(3)]
+        self.h_cnt = [torch.empty((B,), dtype=torch.int32, pin_memory=self.cuda) for _ in range(3)]
+        self.h_keys = [torch.empty((B * 4096,), dtype=torch.int32, pin_memory=self.cuda) for _ in range(3)]   # palettes are ~10^2 rows
         if self.cuda:
             self.out_stream = torch.cuda.Stream(device=be.device)
             self.copy_stream = torch.cuda.Stream(device=be.device)
@@ -302,29 +334,30 @@ class HostEncoder:
             self.d_lab[slot].copy_(labels_host, non_blocking=True)
             self.ev_ready[slot].record(self.copy_stream)
 
-    def _launch(self, slot: int):
-        """Queue the encode of the batch in `slot` and the device->host copies of its results (on the copy-out
-        stream, so that they overlap the next batch's kernels).  Returns the handle `_finish` needs."""
+    def _launch(self, slot: int, out: int = 0):
+        """Queue the encode of the batch in device slot `slot` and the device->host copies of its results into
+        host slot `out` (on the copy-out stream, so that they overlap the next batch's kernels).  Returns the
+        handle `_finish` needs."""
         dev = self.be.device
         if self.cuda:
             torch.cuda.current_stream(dev).wait_event(self.ev_ready[slot])
         res = encode_batch(self.be, self.d_img[slot], self.d_lab[slot], self.table)
         B = self.table.B
         if not self.cuda:
-            self.h_idx[slot].copy_(res.indices)
-            return slot, res, res.palette_off.clone(), res.palette_cnt.clone(), res.palette_keys, None
+            self.h_idx[out].copy_(res.indices)
+            return out, res, res.palette_off.clone(), res.palette_cnt.clone(), res.palette_keys, None
         cur = torch.cuda.current_stream(dev)
         self.ev_free[slot].record(cur)
         done = torch.cuda.Event(); done.record(cur)
         with torch.cuda.stream(self.out_stream):
             self.out_stream.wait_event(done)
-            self.h_idx[slot].copy_(res.indices, non_blocking=True)
-            self.h_off[slot].copy_(res.palette_off[:B + 1], non_blocking=True)
-            self.h_cnt[slot].copy_(res.palette_cnt[:B], non_blocking=True)
-            n_cap = min(res.palette_keys.numel(), self.h_keys[slot].numel())
-            self.h_keys[slot][:n_cap].copy_(res.palette_keys[:n_cap], non_blocking=True)
+            self.h_idx[out].copy_(res.indices, non_blocking=True)
+            self.h_off[out].copy_(res.palette_off[:B + 1], non_blocking=True)
+            self.h_cnt[out].copy_(res.palette_cnt[:B], non_blocking=True)
+            n_cap = min(res.palette_keys.numel(), self.h_keys[out].numel())
+            self.h_keys[out][:n_cap].copy_(res.palette_keys[:n_cap], non_blocking=True)
             out_ev = torch.cuda.Event(); out_ev.record(self.out_stream)
-        return slot, res, self.h_off[slot], self.h_cnt[slot], self.h_keys[slot], out_ev
+        return out, res, self.h_off[out], self.h_cnt[out], self.h_keys[out], out_ev
 
     def _finish(self, handle):
         slot, res, off_t, cnt_t, keys_t, out_ev = handle
@@ -354,8 +387,9 @@ class HostEncoder:
     def encode_many(self, batches):
         """Generator over (palettes, indices) for an iterable of (images_host, labels_host) batches of the
         table's shape, in order.  Three things overlap: the host->device copy of batch i+1, the encode of batch
-        i, and the device->host copy of batch i-1's results; a result stays valid until two more batches have
-        been produced."""
+        i, and the device->host copy of batch i-1's results.  The index planes are views of three pinned result
+        slots used in turn: a result stays valid while the following one is consumed (until next() has been
+        called twice more)."""
         it = iter(batches)
         cur = next(it, None)
         if cur is None:
@@ -367,7 +401,7 @@ class HostEncoder:
             nxt = next(it, None)
             if nxt is not None:
                 self._upload((i + 1) & 1, nxt[0], nxt[1], first_use=(i == 0))
-            handle = self._launch(i & 1)                            # blocks the host until this batch's stage 1 is sized
+            handle = self._launch(i & 1, i % 3)                     # blocks the host until this batch's stage 1 is sized
             if pending is not None:
                 yield self._finish(pending)                         # batch i-1: its copies ran beside batch i's kernels
             pending = handle

@@ -134,6 +134,46 @@ def test_cluster_palette_equals_reference_when_sklearn_assignment_injected(backe
         assert np.array_equal(got["indices"], g[f"out_indices{c}"]), (c, q)
 
 
+def test_cluster_palette_with_duplicate_rows(backend):
+    """A palette passed on unmerged may hold a colour twice (two clusters truncating to one mean,
+    merging.py:16-21): the K-Means sees both rows, find_color_index (:803-808) maps only the first."""
+    rng = np.random.default_rng(9)
+    for trial in range(6):
+        base = np.unique(np.clip(rng.integers(60, 200, 3) + rng.integers(-12, 13, (int(rng.integers(30, 300)), 3)), 1, 255)
+                         .astype(np.uint8), axis=0)
+        pal = np.concatenate([base, base[rng.integers(0, len(base), int(rng.integers(1, 6)))]])
+        pal = pal[rng.permutation(len(pal))]
+        comp = {"palette": pal, "indices": rng.integers(0, len(pal), 64), "shape": (8, 8), "top_left": (0, 0)}
+        q = float(rng.choice([10, 20, 40]))
+        eps, _, m = O.compute_clustering_params(len(pal), q)
+        want = O.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m)
+        got = C.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m,
+                                                as_arrays=True)
+        assert np.array_equal(got["palette"], want["palette"]), trial
+        assert np.array_equal(got["indices"], want["indices"]), trial
+
+
+def test_pipeline_refuses_duplicate_rows_passed_on_unmerged(backend):
+    """One tile per class: stage 1's palette reaches stage 2 unmerged; when it holds a colour twice the entry
+    tables cannot follow the reference (first row only) and the pipeline must refuse, not approximate."""
+    from roibasedimagecompression_b200._lib import RhccqError
+    rng = np.random.default_rng(4)
+    refused = agreed = 0
+    for trial in range(40):
+        img = np.clip(rng.integers(1, 6, (8, 16, 1)) + rng.integers(0, 2, (8, 16, 3)), 1, 255).astype(np.uint8)   # near-grey
+        roi, non = tile_regions(8, 16, 8)
+        try:
+            pal, idx = _encode_device(backend, img, roi, non)
+        except RhccqError as e:
+            assert "holds a colour twice" in str(e)
+            refused += 1
+            continue
+        want = O.encode_image(img, roi, non)
+        assert np.array_equal(pal, want["palette"]) and np.array_equal(idx, want["indices"]), trial
+        agreed += 1
+    assert agreed > 0
+
+
 def test_cluster_palette_degenerate(backend):
     allblack = {"palette": [[0, 0, 0]], "indices": [0, 0, 0, 0], "shape": (2, 2), "top_left": (0, 0)}
     assert C.cluster_palette_colors_parallel(20, allblack, eps=102.4, min_samples=1) is allblack   # clustering.py:197-199
@@ -162,6 +202,21 @@ def test_merge_degenerate(backend):
     one = {"top_left": (0, 0), "shape": (1, 2), "palette": [[1, 2, 3]], "indices": [0, 0]}
     r = C.merge_region_components_simple([one], (0, 0, 4, 4))                   # :16-21
     assert r[0]["actual_colors"] == 1 and r[0]["palette"] == one["palette"] and r[0] is not one
+
+
+def test_merge_components_with_empty_palettes(backend):
+    """merging.py:52-82 with fewer than two components carrying palette rows: still a fresh canvas, palette =
+    black + the colours the paint sequence meets, unused rows dropped."""
+    rng = np.random.default_rng(31)
+    full = {"top_left": (1, 2), "shape": (4, 5), "palette": np.array([[0, 0, 0], [9, 9, 9], [200, 3, 3], [7, 7, 7]], np.uint8),
+            "indices": rng.integers(0, 3, 20)}                                   # row 3 is never used
+    empty = {"top_left": (0, 0), "shape": (2, 2), "palette": np.zeros((0, 3), np.uint8), "indices": np.zeros(4, int)}
+    for comps in ([full, empty], [empty, full], [empty, full, empty], [empty, empty]):
+        want = O.merge_region_components_simple(comps, (0, 0, 8, 8))[0]
+        got = C.merge_region_components_simple(comps, (0, 0, 8, 8), as_arrays=True)[0]
+        assert np.array_equal(np.asarray(got["palette"]).reshape(-1, 3), want["palette"])
+        assert np.array_equal(got["indices"], want["indices"])
+        assert got["actual_colors"] == want["actual_colors"]
 
 
 def test_merge_random_overlaps(backend):
@@ -462,7 +517,12 @@ def test_host_encoder_streaming_equals_single_batches(backend):
     if be.device.type == "cuda":
         labs, batches = labs.pin_memory(), [b.pin_memory() for b in batches]
     enc = pipeline.HostEncoder(be, tab)
-    outs = [(p, i.copy()) for p, i in enc.encode_many([(b, labs) for b in batches])]
+    outs = []
+    for p, i in enc.encode_many([(b, labs) for b in batches]):
+        outs.append((p, i))                                    # views: valid while the following batch is consumed
+        if len(outs) >= 2:
+            outs[-2] = (outs[-2][0], outs[-2][1].copy())
+    outs = [(p, i.copy()) for p, i in outs]                    # encode() below reuses the result slots
     assert len(outs) == 4
     for s, (p, i) in enumerate(outs):
         p2, i2 = enc.encode(batches[s], labs)
