@@ -267,10 +267,20 @@ int rhccq_dbscan_own_roots(const rhccq_dbscan_plan* host_plan, void* ws, size_t 
                            int32_t* out_ids, int32_t* out_count, void* stream);
 /* own_roots on a bare root array (global roots after rhccq_uf_lookup_roots); scratch: int32 [own_roots_scratch_ints(n)] */
 size_t rhccq_uf_own_roots_scratch_ints(int n);
+/* out_capacity > 0: ids beyond that many are dropped (out_count still holds the true number) */
 int rhccq_uf_own_roots(const int32_t* rootlab, int n, int own_lo, int own_hi, int g0, int32_t* scratch, int32_t* out_ids,
-                       int32_t* out_count, void* stream);
+                       int32_t* out_count, int out_capacity, void* stream);
 int rhccq_uf_rank_labels(const int32_t* sorted_roots, int n_roots, const int32_t* rootlab, int lo, int hi, int32_t* labels,
                          void* stream);
+/* The exchange step without the host in between: every rank contributes one block of stride_ints
+ * int32 — [0] = number of payload rows, payload from int 2 (edge rows of two ints, or root ids) — and `gathered`
+ * is the all-gather of the world's blocks in rank order.  merge: union-find over all edges (table_cap: a power of
+ * two >= 4 * world * cap_rows); rank_labels: label of every own point = rank of its global root among all roots
+ * (-2 everywhere when a block reports more rows than cap_rows: the caller must provide more room). */
+int rhccq_uf_merge_edges_gathered(const int32_t* gathered, int world, int stride_ints, int cap_rows, int32_t* table_keys,
+                                  int32_t* table_parent, int table_cap, void* stream);
+int rhccq_uf_rank_labels_gathered(const int32_t* gathered, int world, int stride_ints, int cap_rows, const int32_t* rootlab,
+                                  int lo, int hi, int32_t* labels, void* stream);
 /* labels int32 [n], original order */
 int rhccq_dbscan_relabel(const rhccq_dbscan_plan* host_plan, void* ws, size_t ws_bytes, int32_t* labels, void* stream);
 

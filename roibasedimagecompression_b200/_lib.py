@@ -72,7 +72,9 @@ SIGNATURES = {
     "rhccq_dbscan_lattice_attach": (_I, [_I, _I, _D, _I, _P, _Z, _P]),
     "rhccq_dbscan_lattice_ws_offset": (_Z, [_I, _I, _I]),
     "rhccq_uf_own_roots_scratch_ints": (_Z, [_I]),
-    "rhccq_uf_own_roots": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "rhccq_uf_own_roots": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "rhccq_uf_merge_edges_gathered": (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
+    "rhccq_uf_rank_labels_gathered": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "rhccq_uf_emit_edges": (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
     "rhccq_uf_merge_edges": (_I, [_P, _I, _P, _P, _I, _P]),
     "rhccq_uf_lookup_roots": (_I, [_P, _I, _I, _P, _P, _I, _P]),

@@ -473,9 +473,9 @@ rhccq_k_uf_root_flags(const int* __restrict__ rootlab, int n, int lo, int hi, in
 }
 __global__ void __launch_bounds__(RHCCQ_PT_THREADS)
 rhccq_k_uf_root_scatter(const int* __restrict__ rootlab, const int* __restrict__ rank, int lo, int hi, int g0,
-                        int* __restrict__ out_ids, int* __restrict__ out_count, int n) {
+                        int* __restrict__ out_ids, int* __restrict__ out_count, int n, int out_cap) {
     for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x)
-        if (rootlab[i] == g0 + (int)i) out_ids[rank[i]] = g0 + (int)i;
+        if (rootlab[i] == g0 + (int)i && rank[i] < out_cap) out_ids[rank[i]] = g0 + (int)i;
     if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = hi < n ? rank[hi] : rank[n - 1] + (rootlab[n - 1] == g0 + n - 1 && n - 1 >= lo ? 1 : 0);
 }
 __global__ void __launch_bounds__(RHCCQ_PT_THREADS)
@@ -486,6 +486,63 @@ rhccq_k_uf_rank(const int* __restrict__ sorted_roots, int n_roots, const int* __
         int a = 0, b = n_roots;
         while (a < b) { const int m = (a + b) >> 1; if (sorted_roots[m] < r) a = m + 1; else b = m; }
         labels[i - lo] = (r < 0 || a >= n_roots || sorted_roots[a] != r) ? -1 : a;
+    }
+}
+
+// The same on gathered buffers, without the host in between: every rank contributes one fixed-capacity block of
+// `stride` ints — [0] = number of payload rows, payload from int 2 — so that one all-gather of equal blocks
+// carries counts and rows together and nothing has to be sized on the host.
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_uf_tab_insert_g(const int* __restrict__ g, int world, int stride, int cap_rows, int* __restrict__ keys, int cap_mask) {
+    const long long per = 2LL * cap_rows, total = per * world;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / per);
+        const long long i = e - r * per;
+        const int* blk = g + (long long)r * stride;
+        if (i < 2LL * blk[0]) rhccq_tab_insert(keys, cap_mask, blk[2 + i]);
+    }
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_uf_tab_union_g(const int* __restrict__ g, int world, int stride, int cap_rows, const int* __restrict__ keys,
+                       int* __restrict__ parent, int cap_mask) {
+    const long long total = (long long)cap_rows * world;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / cap_rows);
+        const long long i = e - (long long)r * cap_rows;
+        const int* blk = g + (long long)r * stride;
+        if (i >= blk[0]) continue;
+        int a = rhccq_tab_find(keys, cap_mask, blk[2 + 2 * i]), b = rhccq_tab_find(keys, cap_mask, blk[2 + 2 * i + 1]);
+        while (true) {
+            a = rhccq_pt_find(parent, a);
+            b = rhccq_pt_find(parent, b);
+            if (a == b) break;
+            if (keys[a] < keys[b]) { const int t = a; a = b; b = t; }      // a: larger key
+            if (atomicCAS(&parent[a], a, b) == a) break;
+        }
+    }
+}
+// label = rank of the point's global root among the roots of all ranks; the blocks hold ascending ids and the
+// ranks own ascending index ranges, so the rank is (rows of the lower blocks) + (position inside its block).
+// A block whose count exceeds its capacity (more roots than the caller provided for) marks every label -2.
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_uf_rank_g(const int* __restrict__ g, int world, int stride, int cap_rows, const int* __restrict__ rootlab, int lo, int hi,
+                  int* __restrict__ labels) {
+    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+        const int r = rootlab[i];
+        int lab = -1, before = 0;
+        bool over = false;
+        for (int w = 0; w < world; ++w) {
+            const int* blk = g + (long long)w * stride;
+            const int c = blk[0];
+            if (c > cap_rows) over = true;
+            if (r >= 0 && lab < 0 && c > 0 && c <= cap_rows && blk[2] <= r && r <= blk[2 + c - 1]) {
+                int a = 0, b = c;
+                while (a < b) { const int m = (a + b) >> 1; if (blk[2 + m] < r) a = m + 1; else b = m; }
+                if (a < c && blk[2 + a] == r) lab = before + a;
+            }
+            before += c;
+        }
+        labels[i - lo] = over ? -2 : lab;
     }
 }
 
@@ -697,10 +754,36 @@ int rhccq_uf_lookup_roots(int32_t* rootlab, int n, int g0, const int32_t* table_
     return 0;
 }
 
+int rhccq_uf_merge_edges_gathered(const int32_t* gathered, int world, int stride_ints, int cap_rows, int32_t* table_keys,
+                                  int32_t* table_parent, int table_cap, void* stream) {
+    if (!gathered || world < 1 || cap_rows < 1 || stride_ints < 2 + 2 * cap_rows || table_cap < 2 ||
+        (table_cap & (table_cap - 1)) != 0 || (long long)table_cap < 4LL * world * cap_rows) {
+        rhccq_set_error("rhccq_uf_merge_edges_gathered: need blocks of 2 + 2 cap_rows ints and a power-of-two table >= 4 world cap_rows");
+        return -1;
+    }
+    RHCCQ_LAUNCH(rhccq_k_uf_tab_init, rhccq_pt_blocks(table_cap), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, table_keys, table_parent, table_cap);
+    RHCCQ_LAUNCH(rhccq_k_uf_tab_insert_g, rhccq_pt_blocks(2LL * world * cap_rows), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream,
+                 gathered, world, stride_ints, cap_rows, table_keys, table_cap - 1);
+    RHCCQ_LAUNCH(rhccq_k_uf_tab_union_g, rhccq_pt_blocks((long long)world * cap_rows), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream,
+                 gathered, world, stride_ints, cap_rows, table_keys, table_parent, table_cap - 1);
+    return 0;
+}
+
+int rhccq_uf_rank_labels_gathered(const int32_t* gathered, int world, int stride_ints, int cap_rows, const int32_t* rootlab,
+                                  int lo, int hi, int32_t* labels, void* stream) {
+    if (!gathered || world < 1 || cap_rows < 1 || stride_ints < 2 + cap_rows) {
+        rhccq_set_error("rhccq_uf_rank_labels_gathered: need blocks of 2 + cap_rows ints"); return -1;
+    }
+    if (hi <= lo) return 0;
+    RHCCQ_LAUNCH(rhccq_k_uf_rank_g, rhccq_pt_blocks(hi - lo), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, gathered, world,
+                 stride_ints, cap_rows, rootlab, lo, hi, labels);
+    return 0;
+}
+
 size_t rhccq_uf_own_roots_scratch_ints(int n) { return (size_t)(n > 0 ? n : 1) + rhccq_scan_scratch_ints(n) + 16; }
 
 int rhccq_uf_own_roots(const int32_t* rootlab, int n, int own_lo, int own_hi, int g0, int32_t* scratch, int32_t* out_ids,
-                       int32_t* out_count, void* stream) {
+                       int32_t* out_count, int out_capacity, void* stream) {
     if (!rootlab || !scratch || !out_ids || !out_count || n <= 0 || own_lo < 0 || own_hi > n || own_hi < own_lo) {
         rhccq_set_error("rhccq_uf_own_roots: bad arguments"); return -1;
     }
@@ -711,7 +794,7 @@ int rhccq_uf_own_roots(const int32_t* rootlab, int n, int own_lo, int own_hi, in
         RHCCQ_LAUNCH(rhccq_k_scan_small, 1, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, flags, n, (int*)nullptr);
     } else if (rhccq_scan_i32(flags, n, flags, scan, stream) != 0) return -1;
     RHCCQ_LAUNCH(rhccq_k_uf_root_scatter, rhccq_pt_blocks(own_hi - own_lo), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, rootlab,
-                 flags, own_lo, own_hi, g0, out_ids, out_count, n);
+                 flags, own_lo, own_hi, g0, out_ids, out_count, n, out_capacity > 0 ? out_capacity : 0x7fffffff);
     return 0;
 }
 
@@ -723,7 +806,7 @@ int rhccq_dbscan_own_roots(const rhccq_dbscan_plan* P, void* ws, size_t ws_bytes
         RHCCQ_LAUNCH(rhccq_k_scan_small, 1, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, W.is_root, P->n, (int*)nullptr);
     } else if (rhccq_scan_i32(W.is_root, P->n, W.is_root, W.scan, stream) != 0) return -1;
     RHCCQ_LAUNCH(rhccq_k_uf_root_scatter, rhccq_pt_blocks(own_hi - own_lo), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, W.rootlab,
-                 W.is_root, own_lo, own_hi, g0, out_ids, out_count, P->n);
+                 W.is_root, own_lo, own_hi, g0, out_ids, out_count, P->n, 0x7fffffff);
     return 0;
 }
 

@@ -178,56 +178,39 @@ class StripDbscan:
         self.rootlab = engine.ws[off:off + 4 * self.n_loc].view(torch.int32)
         self.cap = max(sum(b - a for a, b in self.zone), 1)
         n_own = self.own[1] - self.own[0]
-        # exchange buffers are sized for the largest rank, so that a gather never has to re-pad (one collective
-        # here, at construction, instead of one per call)
+        # The exchange buffers have one fixed capacity on every rank (the largest rank's: one collective here, at
+        # construction), their row count travels in the buffer itself, and the kernels skip the padding: a call
+        # needs no host synchronisation and allocates nothing.
         import torch.distributed as dist
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
-        caps = torch.tensor([self.cap, max(n_own, 1)], dtype=torch.int64, device=be.device)
+        # roots: a cluster has one root; clusters are a small fraction of the points (0.65 % on the synthetic
+        # images), room for a sixteenth of the own points + 64 Ki; a rank with more reports it (labels -2, `check`)
+        caps = torch.tensor([self.cap, max(n_own // 16 + 65536, 1)], dtype=torch.int64, device=be.device)
         if self.world > 1:
             dist.all_reduce(caps, op=dist.ReduceOp.MAX, group=group)
         self.cap_all, self.ids_all = (int(v) for v in caps.tolist())
-        self.edges = be.empty((self.cap_all, 2), torch.int32)
-        self.counter = be.zeros((1,), torch.int32)
-        self.ids = be.empty((self.ids_all,), torch.int32)
-        self.cnt = be.zeros((1,), torch.int32)
-        self.sizes = be.zeros((self.world,), torch.int32)
-        self._stage = {}
+        self.e_stride, self.i_stride = 2 + 2 * self.cap_all, 2 + self.ids_all
+        self.ebuf = be.zeros((self.e_stride,), torch.int32)          # [0] = edges, rows of (point, root) from int 2
+        self.ibuf = be.zeros((self.i_stride,), torch.int32)          # [0] = roots, ascending ids from int 2
+        self.eall = be.zeros((self.world, self.e_stride), torch.int32) if self.world > 1 else self.ebuf.view(1, -1)
+        self.iall = be.zeros((self.world, self.i_stride), torch.int32) if self.world > 1 else self.ibuf.view(1, -1)
+        self.tcap = 1 << max(4, int(np.ceil(np.log2(4 * self.world * self.cap_all))))
+        self.tk, self.tp = be.empty((self.tcap,), torch.int32), be.empty((self.tcap,), torch.int32)
         self.scratch = be.empty((int(be.cdll.rhccq_uf_own_roots_scratch_ints(self.n_loc)),), torch.int32)
         self.labels = be.empty((max(n_own, 1),), torch.int32)
 
-    def _gather(self, mine, counter, width):
-        """all_gather of variable-length int32 rows. `counter` is the device-side row count of this rank: the
-        counts travel first (one collective, one host synchronisation for all of them), then every rank's first
-        max(count) rows. Returns (rows of all ranks in rank order, this rank's count)."""
+    def _all_gather(self, out, mine):
         import torch.distributed as dist
-        be, world = self.be, self.world
-        if world == 1:
-            n = int(counter.item())
-            return mine[:n].contiguous(), n
+        if self.world == 1:
+            return
         if dist.get_backend(self.group) == "gloo":                   # CPU tests
-            parts = [torch.zeros_like(counter) for _ in range(world)]
-            dist.all_gather(parts, counter, group=self.group)
-            sizes = [int(t.item()) for t in parts]
+            dist.all_gather([out[r] for r in range(self.world)], mine, group=self.group)
         else:
-            dist.all_gather_into_tensor(self.sizes, counter, group=self.group)
-            sizes = self.sizes.tolist()
-        m = max(max(sizes), 1)
-        flat = self._stage.get(tuple(width))                          # grown on demand, reused across calls
-        need = world * m * (2 if width else 1)
-        if flat is None or flat.numel() < need:
-            flat = self._stage[tuple(width)] = be.empty((need + need // 4,), torch.int32)
-        out = flat[:need].view((world, m) + tuple(width))
-        if dist.get_backend(self.group) == "gloo":
-            dist.all_gather([out[r] for r in range(world)], mine[:m].contiguous(), group=self.group)
-        else:
-            dist.all_gather_into_tensor(out, mine[:m], group=self.group)
-        return torch.cat([out[r, :sizes[r]] for r in range(world)]), sizes[self.rank]
+            dist.all_gather_into_tensor(out, mine, group=self.group)
 
     def run(self, src, timings: dict | None = None):
-        import torch.distributed as dist
         be, eng = self.be, self.engine
-        world = self.world
         # ---- local phases up to the roots of the local components
         if self.lattice:
             eng.count(src); eng.union()
@@ -235,35 +218,42 @@ class StripDbscan:
         else:
             eng.bin(src); eng.count(); eng.union()
             be.call("rhccq_dbscan_flatten", eng._p(), be.ptr(eng.ws), eng.ws_bytes, be.ptr(eng.core), be.stream())
-        # ---- boundary edges of this rank, then the one exchange step
-        self.counter.zero_()
+        # ---- boundary edges of this rank (at most one per zone point: they fit by construction), then the one
+        # exchange step and the same union-find over all edges on every rank
+        self.ebuf[:1].zero_()
         for a, b in self.zone:
-            be.call("rhccq_uf_emit_edges", be.ptr(self.rootlab), a, b, self.g0, be.ptr(self.edges), be.ptr(self.counter),
-                    self.cap, be.stream())
-        all_edges, n_e = self._gather(self.edges, self.counter, (2,))      # n_e <= cap by construction (one edge per zone point)
-        E = int(all_edges.shape[0])
-        if E > 0:
-            tcap = 1 << max(4, int(np.ceil(np.log2(4 * E))))
-            tk, tp = be.empty((tcap,), torch.int32), be.empty((tcap,), torch.int32)
-            be.call("rhccq_uf_merge_edges", be.ptr(all_edges), E, be.ptr(tk), be.ptr(tp), tcap, be.stream(), launches=3)
-            be.call("rhccq_uf_lookup_roots", be.ptr(self.rootlab), self.n_loc, self.g0, be.ptr(tk), be.ptr(tp), tcap, be.stream())
-        else:
-            be.call("rhccq_uf_lookup_roots", be.ptr(self.rootlab), self.n_loc, self.g0, 0, 0, 0, be.stream())
+            be.call("rhccq_uf_emit_edges", be.ptr(self.rootlab), a, b, self.g0, be.ptr(self.ebuf[2:]), be.ptr(self.ebuf),
+                    self.cap_all, be.stream())
+        self._all_gather(self.eall, self.ebuf)
+        be.call("rhccq_uf_merge_edges_gathered", be.ptr(self.eall), self.world, self.e_stride, self.cap_all, be.ptr(self.tk),
+                be.ptr(self.tp), self.tcap, be.stream(), launches=3)
+        be.call("rhccq_uf_lookup_roots", be.ptr(self.rootlab), self.n_loc, self.g0, be.ptr(self.tk), be.ptr(self.tp), self.tcap,
+                be.stream())
         # ---- border points against global roots, then the global numbering of roots
         if self.lattice:
             be.call("rhccq_dbscan_lattice_attach", eng.H, eng.W, eng.eps, eng.min_pts, be.ptr(eng.ws), eng.ws_bytes, be.stream())
         else:
             be.call("rhccq_dbscan_attach", eng._p(), be.ptr(eng.ws), eng.ws_bytes, be.ptr(eng.core), be.stream())
-        self.cnt.zero_()
         be.call("rhccq_uf_own_roots", be.ptr(self.rootlab), self.n_loc, self.own[0], self.own[1], self.g0, be.ptr(self.scratch),
-                be.ptr(self.ids), be.ptr(self.cnt), be.stream(), launches=3)
-        roots, n_r = self._gather(self.ids, self.cnt, ())            # ascending: strips are ordered
-        be.call("rhccq_uf_rank_labels", be.ptr(roots), int(roots.numel()), be.ptr(self.rootlab), self.own[0], self.own[1],
-                be.ptr(self.labels), be.stream())
-        if timings is not None:
-            timings.update(edges_local=n_e, edges_total=E, roots_total=int(roots.numel()))
+                be.ptr(self.ibuf[2:]), be.ptr(self.ibuf), self.ids_all, be.stream(), launches=3)
+        self._all_gather(self.iall, self.ibuf)                       # ascending over the ranks: strips are ordered
+        be.call("rhccq_uf_rank_labels_gathered", be.ptr(self.iall), self.world, self.i_stride, self.ids_all, be.ptr(self.rootlab),
+                self.own[0], self.own[1], be.ptr(self.labels), be.stream())
+        if timings is not None:                                      # (reads counters back: one host synchronisation)
+            ne, nr = self.eall[:, 0].cpu(), self.iall[:, 0].cpu()
+            if int(nr.max()) > self.ids_all:
+                raise RhccqError(f"strip DBSCAN: a rank holds {int(nr.max())} cluster roots, more than the exchange "
+                                 f"buffer's {self.ids_all}")
+            timings.update(edges_local=int(ne[self.rank]), edges_total=int(ne.sum()), roots_total=int(nr.sum()))
         n_own = self.own[1] - self.own[0]
         return self.labels[:n_own], eng.core[self.own[0]:self.own[1]]
+
+    def check(self) -> None:
+        """Raise if the last run overflowed the root exchange buffer (its labels are -2 then)."""
+        nr = self.iall[:, 0].cpu()
+        if int(nr.max()) > self.ids_all:
+            raise RhccqError(f"strip DBSCAN: a rank holds {int(nr.max())} cluster roots, more than the exchange buffer's "
+                             f"{self.ids_all}")
 
 
 def dbscan_strips(be: Backend, pts_local, g0: int, own, zone, eps: float, min_pts: int, group=None, grid_dims: int = 2,
