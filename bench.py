@@ -406,6 +406,40 @@ def dbscan_probe(be, args, eps=None, min_pts=None):
                          "algorithmic_bytes_per_launch": DBSCAN_BYTES_PER_POINT * n, "avg_launch_ms": cms / cn}}
 
 
+def _write_frame(args):
+    import tempfile
+    from roibasedimagecompression_b200.encoder.compression import compression as CC
+    pal, idx = args
+    with tempfile.NamedTemporaryFile(suffix=".rhccq") as f:
+        return CC.save_encoded(pal, idx, f.name)
+
+
+def container_probe(pals, idx, e2e_ms):
+    """Time of the reference-format container writer on the frames of the last end-to-end step: one frame
+    single-threaded, and the whole batch over all host cores; `e2e_with_container` adds the latter to the step."""
+    import multiprocessing as mp
+    frames = [(np.asarray(pals[b]), np.ascontiguousarray(idx[b])) for b in range(len(pals))]
+    t0 = time.perf_counter()
+    size0 = _write_frame(frames[0])
+    one = time.perf_counter() - t0
+    cores = min(os.cpu_count() or 1, 64, len(frames))
+    t0 = time.perf_counter()
+    if cores > 1:
+        with mp.get_context("fork").Pool(cores) as pool:
+            sizes = pool.map(_write_frame, frames, chunksize=1)
+    else:
+        sizes = [_write_frame(f) for f in frames]
+    batch = time.perf_counter() - t0
+    px = sum(f[1].size for f in frames)
+    return {"format": "b'RHCCQ' + length + zlib9(pickle{s,l,p: zlib9(palette), i: zlib9(indices), d}) per frame "
+                      "(byte-identical to the reference's writer: tests/test_container.py)",
+            "frames": len(frames), "ms_one_frame_single_thread": one * 1e3, "ms_batch_all_cores": batch * 1e3, "cores": cores,
+            "bytes_out": int(sum(sizes)), "bits_per_pixel": 8.0 * sum(sizes) / px,
+            "e2e_with_container": {"value": px / 1e6 / ((e2e_ms + batch * 1e3) / 1e3), "unit": "MPx/s",
+                                   "ms_per_step": e2e_ms + batch * 1e3,
+                                   "note": "encode step from host buffers + the container writes of its frames, not overlapped"}}
+
+
 def encode_probe(be, B, H, W, tile, steps, warmup):
     """Device-resident and end-to-end encode of B synthetic HxW images (tile segmentation): ms, MPx/s, kernels."""
     import torch
@@ -553,6 +587,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     ap.add_argument("--no-dbscan", action="store_true", help="skip the short DBSCAN probe of the default line")
     ap.add_argument("--no-c3", action="store_true", help="skip the 3840x2160 legs of the default line")
+    ap.add_argument("--no-container", action="store_true", help="skip the .rhccq container leg of the default line")
     ap.add_argument("--no-strips", action="store_true", help="N > 1: skip the strip-sharded leg of the default line")
     ap.add_argument("--eps", type=float, default=3.0, help="c5 workloads: DBSCAN radius")
     ap.add_argument("--min-pts", type=int, default=8, help="c5 workloads: DBSCAN min_samples")
@@ -688,6 +723,12 @@ def main():
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "kernels": kernels,
         "last_step_launches_ms": last_step,
     }
+
+    # ---- the step after the path: every frame's final palette + index plane into the reference's
+    # .rhccq container (zlib level 9 twice + pickle: encoder/compression/compression.py:119-220).  A file per frame,
+    # so the frames of a batch are written by one process per host core; the bytes are the single-threaded writer's.
+    if rank == 0 and world == 1 and not args.no_container:
+        out["container"] = container_probe(pals, idx, e2e_ms)
 
     # ---- BASELINE configs[2]: one 3840x2160 image through the same three stages (and eight of them in one batch,
     # where the sequential MiniBatchKMeans chain of the stage-2 palettes amortises)

@@ -22,10 +22,18 @@
 
 #define RHCCQ_PAD_KEY 0xFFFFFFFFu
 
+#define RHCCQ_UQ_BUCKETS 2048           // buckets of the hashed path (key-ordered: by R, then by a slice of G)
+#define RHCCQ_UQ_MAXB 256               // largest bucket the hashed path ranks by counting; beyond: the sorting path
+#define RHCCQ_UQ_EMPTY 0xFFFFFFFFu
+
 size_t rhccq_unique_ws_bytes(int max_valid) {
     size_t np2 = 1;
     while (np2 < (size_t)(max_valid > 1 ? max_valid : 1)) np2 <<= 1;
-    return rhccq_carve_bytes(np2, 4) * 2;
+    const size_t sorting = rhccq_carve_bytes(np2, 4) * 2;
+    // hashed path: table of 2 np2 keys, a 16-bit rank per slot, the slots grouped by bucket, the bucket counters
+    const size_t hashed = rhccq_carve_bytes(2 * np2, 4) + rhccq_carve_bytes(2 * np2, 2) + rhccq_carve_bytes(np2, 2)
+                          + rhccq_carve_bytes(RHCCQ_UQ_BUCKETS, 4);
+    return np2 <= 16384 && hashed > sorting ? hashed : sorting;
 }
 
 __device__ __forceinline__ int rhccq_lower_bound_u32(const uint32_t* a, int n, uint32_t key) {
@@ -35,6 +43,175 @@ __device__ __forceinline__ int rhccq_lower_bound_u32(const uint32_t* a, int n, u
         if (a[mid] < key) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+__device__ __forceinline__ uint32_t rhccq_uq_hash(uint32_t key, uint32_t mask) { return (key * 2654435761u >> 7) & mask; }
+
+// Hashed form of the same result for segments of up to 16 384 pixels: the colours go into an open-addressing
+// table in shared memory (duplicates vanish there: ~45 % of the pixels), the distinct ones are grouped into
+// key-ordered buckets (R, then a slice of G scaled to the segment's range) and ranked inside their bucket by
+// counting — np.unique's lexicographic order without sorting every pixel — and a pixel's index is one table
+// lookup.  Returns false (nothing written) when a bucket is too large for counting: the caller then sorts.
+template <class IdxT>
+__device__ bool rhccq_unique_hashed(int p, const uint8_t* __restrict__ img, const int32_t* __restrict__ seg,
+                                    int B, int H, int W, const int32_t* __restrict__ crops,
+                                    const int* __restrict__ pal_off, uint32_t* __restrict__ pal_keys,
+                                    int* __restrict__ pal_cnt, IdxT* __restrict__ index_plane, int repaint_black,
+                                    int cap, unsigned char* wsbase) {
+    __shared__ int s_uniq, s_valid, s_black, s_rg[4], s_maxb;
+    __shared__ unsigned long long s_best;
+    __shared__ uint32_t s_repl;
+    __shared__ int s_scr[RHCCQ_MAX_WARPS + 2];
+    const int32_t* cr = crops + 8 * (size_t)p;
+    const int b = cr[0], r0 = cr[1], c0 = cr[2], h = cr[3], w = cr[4], sid = cr[5];
+    const int npx = h * w;
+    const size_t iplane = (size_t)b * H * W;
+    const size_t plane = ((size_t)cr[6] * B + b) * H * W;
+    int np2cap = 1;
+    while (np2cap < (cap > 1 ? cap : 1)) np2cap <<= 1;
+    const int nslots = 2 * np2cap;
+    const float inv_w = 1.0f / (float)w;                           // row of pixel q without an integer division (npx <= 16 384)
+    const uint32_t mask = (uint32_t)nslots - 1u;
+    rhccq_carver cv(wsbase);
+    uint32_t* hk = cv.take<uint32_t>(nslots);
+    uint16_t* rk = cv.take<uint16_t>(nslots);
+    uint16_t* bslot = cv.take<uint16_t>(np2cap);
+    int* hist = cv.take<int>(RHCCQ_UQ_BUCKETS);
+    if (threadIdx.x == 0) {
+        s_uniq = 0; s_valid = 0; s_black = 0; s_best = ~0ull; s_repl = 0u; s_maxb = 0;
+        s_rg[0] = 255; s_rg[1] = 0; s_rg[2] = 255; s_rg[3] = 0;
+    }
+    RHCCQ_PAR_FOR(j, nslots) hk[j] = RHCCQ_UQ_EMPTY;
+    RHCCQ_PAR_FOR(j, RHCCQ_UQ_BUCKETS) hist[j] = 0;
+    __syncthreads();
+    // pass A: the distinct non-black colours of the segment
+    unsigned long long best_local = ~0ull;
+    int rmin = 255, rmax = 0, gmin = 255, gmax = 0;
+    for (int q = (int)threadIdx.x; q - RHCCQ_LANE < npx; q += (int)blockDim.x) {          // warp-uniform trip count
+        bool valid = q < npx;
+        uint32_t key = 0u;
+        if (valid) {
+            int rq = (int)(((float)q + 0.5f) * inv_w), cq = q - rq * w;
+            if (cq < 0) { --rq; cq += w; } else if (cq >= w) { ++rq; cq -= w; }
+            const int r = r0 + rq, c = c0 + cq;
+            const size_t pos = plane + (size_t)r * W + c;
+            if (seg != nullptr && sid != 0 && seg[pos] != sid) valid = false;
+            else {
+                const uint8_t* px = img + 3 * (iplane + (size_t)r * W + c);
+                key = rhccq_pack_rgb(px[0], px[1], px[2]);
+            }
+        }
+        const bool nonblack = valid && key != 0u;
+        bool fresh = false;
+        if (nonblack) {
+            uint32_t hslot = rhccq_uq_hash(key, mask);
+            while (true) {
+                const uint32_t k = atomicCAS(&hk[hslot], RHCCQ_UQ_EMPTY, key);
+                if (k == RHCCQ_UQ_EMPTY) { fresh = true; break; }
+                if (k == key) break;
+                hslot = (hslot + 1u) & mask;
+            }
+            if (fresh) {
+                const int rr = rhccq_key_r(key), gg = rhccq_key_g(key);
+                rmin = rr < rmin ? rr : rmin; rmax = rr > rmax ? rr : rmax;
+                gmin = gg < gmin ? gg : gmin; gmax = gg > gmax ? gg : gmax;
+            }
+            if (repaint_black) {
+                const unsigned long long cand = ((unsigned long long)rhccq_d2(key, 0u) << 32) | (unsigned)q;
+                best_local = cand < best_local ? cand : best_local;
+            }
+        }
+        const unsigned mv = rhccq_ballot(valid), mnb = rhccq_ballot(nonblack), mf = rhccq_ballot(fresh);
+        if (RHCCQ_LANE == 0) {
+            if (mf) atomicAdd(&s_uniq, __popc(mf));
+            if (mv) atomicAdd(&s_valid, __popc(mv));
+            if (mv & ~mnb) atomicAdd(&s_black, __popc(mv & ~mnb));
+        }
+    }
+    for (int d = RHCCQ_WARP_SIZE >> 1; d > 0; d >>= 1) {
+        const unsigned long long o = rhccq_shfl_xor(best_local, d);
+        best_local = o < best_local ? o : best_local;
+        const int a0 = rhccq_shfl_xor(rmin, d), a1 = rhccq_shfl_xor(rmax, d), a2 = rhccq_shfl_xor(gmin, d), a3 = rhccq_shfl_xor(gmax, d);
+        rmin = a0 < rmin ? a0 : rmin; rmax = a1 > rmax ? a1 : rmax; gmin = a2 < gmin ? a2 : gmin; gmax = a3 > gmax ? a3 : gmax;
+    }
+    if (RHCCQ_LANE == 0) {
+        if (repaint_black && best_local != ~0ull) atomicMin(&s_best, best_local);
+        atomicMin(&s_rg[0], rmin); atomicMax(&s_rg[1], rmax); atomicMin(&s_rg[2], gmin); atomicMax(&s_rg[3], gmax);
+    }
+    __syncthreads();
+    const int nu = s_uniq, nvalid = s_valid, nblack = s_black;
+    if (nvalid > cap) {                                            // more pixels than the table was sized for: report
+        if (threadIdx.x == 0) pal_cnt[p] = -1;
+        return true;
+    }
+    const bool repaint = repaint_black && nblack > 0 && nu > 0;
+    if (repaint && threadIdx.x == 0) {
+        const int q = (int)(s_best & 0xffffffffu);
+        const uint8_t* px = img + 3 * (iplane + (size_t)(r0 + q / w) * W + (c0 + q % w));
+        s_repl = rhccq_pack_rgb(px[0], px[1], px[2]);
+    }
+    const int has_black = (nvalid < npx || (nblack > 0 && !repaint)) ? 1 : 0;
+    // key-ordered buckets: (R - Rmin) * gb + floor((G - Gmin) * gb / Grange)
+    const int Rmin = s_rg[0], Gmin = s_rg[2];
+    const int rrange = nu > 0 ? s_rg[1] - Rmin + 1 : 1, grange = nu > 0 ? s_rg[3] - Gmin + 1 : 1;
+    int gb = RHCCQ_UQ_BUCKETS / rrange;
+    gb = gb > 64 ? 64 : (gb < 1 ? 1 : gb);
+    const float gscale = (float)gb / (float)grange;
+    auto bucket = [&](uint32_t key) -> int {
+        int gs = (int)((float)(rhccq_key_g(key) - Gmin) * gscale);
+        gs = gs > gb - 1 ? gb - 1 : gs;
+        return (rhccq_key_r(key) - Rmin) * gb + gs;
+    };
+    RHCCQ_PAR_FOR(j, nslots) {
+        const uint32_t key = hk[j];
+        if (key != RHCCQ_UQ_EMPTY) atomicAdd(&hist[bucket(key)], 1);
+    }
+    __syncthreads();
+    RHCCQ_PAR_FOR(j, RHCCQ_UQ_BUCKETS) if (hist[j] > RHCCQ_UQ_MAXB) atomicMax(&s_maxb, hist[j]);
+    __syncthreads();
+    if (s_maxb > RHCCQ_UQ_MAXB) return false;                      // (uniform) a bucket too large to rank by counting
+    rhccq_block_excl_scan_array<int>(hist, RHCCQ_UQ_BUCKETS, s_scr);          // hist[b] = first position of bucket b
+    RHCCQ_PAR_FOR(j, nslots) {
+        const uint32_t key = hk[j];
+        if (key != RHCCQ_UQ_EMPTY) bslot[atomicAdd(&hist[bucket(key)], 1)] = (uint16_t)j;   // hist[b] ends as the end of b
+    }
+    __syncthreads();
+    uint32_t* pal = pal_keys + pal_off[p];
+    if (threadIdx.x == 0) {
+        if (has_black) pal[0] = 0u;
+        pal_cnt[p] = ((size_t)(has_black + nu) > (size_t)((IdxT)~(IdxT)0) + 1) ? -3 : has_black + nu;
+    }
+    RHCCQ_PAR_FOR(q, nu) {
+        const int slot = (int)bslot[q];
+        const uint32_t key = hk[slot];
+        const int bk = bucket(key);
+        const int lo = bk > 0 ? hist[bk - 1] : 0, hi = hist[bk];
+        int r = 0;
+        for (int t = lo; t < hi; ++t) r += hk[bslot[t]] < key ? 1 : 0;
+        rk[slot] = (uint16_t)(lo + r);
+        pal[has_black + lo + r] = key;
+    }
+    __syncthreads();
+    // pass B: index of every pixel of the segment
+    const uint32_t repl = s_repl;
+    RHCCQ_PAR_FOR(q, npx) {
+        int rq = (int)(((float)q + 0.5f) * inv_w), cq = q - rq * w;
+        if (cq < 0) { --rq; cq += w; } else if (cq >= w) { ++rq; cq -= w; }
+        const int r = r0 + rq, c = c0 + cq;
+        const size_t pos = plane + (size_t)r * W + c;
+        if (seg != nullptr && sid != 0 && seg[pos] != sid) continue;
+        const uint8_t* px = img + 3 * (iplane + (size_t)r * W + c);
+        uint32_t key = rhccq_pack_rgb(px[0], px[1], px[2]);
+        if (key == 0u && repaint) key = repl;
+        int idx = 0;
+        if (key != 0u) {
+            uint32_t hslot = rhccq_uq_hash(key, mask);
+            while (hk[hslot] != key) hslot = (hslot + 1u) & mask;
+            idx = has_black + (int)rk[hslot];
+        }
+        index_plane[pos] = (IdxT)idx;
+    }
+    return true;
 }
 
 template <class IdxT>
@@ -151,8 +328,14 @@ rhccq_k_unique(const uint8_t* __restrict__ img, const int32_t* __restrict__ seg,
     RHCCQ_DYN_SMEM(dyn);
     unsigned char* wsbase = gws ? gws + (size_t)blockIdx.x * gws_stride : dyn;
     for (int p = blockIdx.x; p < n_crops; p += gridDim.x) {
-        rhccq_unique_problem<IdxT>(p, img, seg, B, H, W, crops, pal_off, pal_keys, pal_cnt, index_plane,
-                                   repaint_black, cap, wsbase);
+        bool done = false;
+        if (cap <= 16384 && (size_t)((IdxT)~(IdxT)0) >= 0xffffu)   // 16-bit ranks in the table
+            done = rhccq_unique_hashed<IdxT>(p, img, seg, B, H, W, crops, pal_off, pal_keys, pal_cnt, index_plane,
+                                             repaint_black, cap, wsbase);
+        __syncthreads();
+        if (!done)
+            rhccq_unique_problem<IdxT>(p, img, seg, B, H, W, crops, pal_off, pal_keys, pal_cnt, index_plane,
+                                       repaint_black, cap, wsbase);
         __syncthreads();
     }
 }

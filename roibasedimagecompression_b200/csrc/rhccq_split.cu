@@ -40,7 +40,9 @@ __device__ unsigned long long rhccq_split_prof[16];
 #define RHCCQ_COUNT(slot, v) do {} while (0)
 #endif
 
+#ifndef RHCCQ_SPLIT_THREADS
 #define RHCCQ_SPLIT_THREADS 256
+#endif
 #define RHCCQ_KM_MAXT 12               // 2 + int(log(k)) for k < 22027
 #ifndef RHCCQ_PRUNE_MIN_K
 #define RHCCQ_PRUNE_MIN_K 10            // centres from which the E step prunes by the triangle inequality
@@ -720,6 +722,11 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
     for (int q = tid; q < 3; q += gsz)
         C.center[q] = __dsub_rn((double)((x[first] >> (16 - 8 * q)) & 255u), mean[q]);
     int ri = 1, prev_slot = -1;
+    // The distances to the centre chosen last are folded into `closest` lazily — by the next pass over the points
+    // (the potentials below; the cumulative sum of the warp-level form) and by the candidate search on the
+    // elements it looks at — instead of by a pass of their own: `pend` is that centre, pending the fold.
+    bool pending = false;
+    uint32_t pend = 0u;
     for (int c = 1; c < k; ++c) {
         // ---- candidates: searchsorted(cumsum(closest), r * pot), clipped (:247-252)
         // |float64 cumulative sum - integer one| <= n (1e-9 + ulp(pot)/2) and the same for r * pot, so the
@@ -757,7 +764,12 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                     const int j0 = cix * per < n ? cix * per : n, j1 = j0 + per < n ? j0 + per : n;
                     for (int base = j0; base < j1; base += RHCCQ_WARP_SIZE) {
                         const int j = base + RHCCQ_LANE;
-                        const unsigned long long own = j < j1 ? (unsigned long long)closest[j] : 0ull;
+                        unsigned long long own = 0ull;
+                        if (j < j1) {
+                            uint32_t o = closest[j];
+                            if (pending) { const uint32_t d = (uint32_t)rhccq_d2(x[j], pend); o = d < o ? d : o; }
+                            own = o;
+                        }
                         const unsigned long long inc = rhccq_warp_incl_scan_u64(own);
                         const unsigned mm = rhccq_ballot(j < j1 && (double)(pre + inc) >= rv);
                         if (mm != 0u) {
@@ -780,7 +792,11 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
             // inclusive cumulative sum of closest (exact integers)
             cum_t total;
             cum_t run = g.template excl_scan<cum_t>(chunk_sum, &total);
-            for (int j = c_lo; j < c_hi; ++j) { run += closest[j]; cum[j] = run; }
+            for (int j = c_lo; j < c_hi; ++j) {
+                uint32_t o = closest[j];
+                if (pending) { const uint32_t d = (uint32_t)rhccq_d2(x[j], pend); o = d < o ? d : o; closest[j] = o; }
+                run += o; cum[j] = run;
+            }
             g.sync();
             for (int t = tid; t < T; t += gsz) {
                 const double rv = __dmul_rn(rng[ri + t], (double)pot);
@@ -815,12 +831,16 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
         int cj[RHCCQ_KM_MAXT];
 #pragma unroll
         for (int t = 0; t < RHCCQ_KM_MAXT; ++t) { acc[t] = 0; cj[t] = t < T ? C.cand[t] : 0; xc[t] = t < T ? x[cj[t]] : 0u; }
+        cum_t part[RHCCQ_KM_MAXT];                                  // this thread's share of every candidate's potential
         if (per <= 20000) {                                         // 20 000 x 195 075 < 2^32: 32-bit partial sums
             uint32_t a32[RHCCQ_KM_MAXT];
 #pragma unroll
             for (int t = 0; t < RHCCQ_KM_MAXT; ++t) a32[t] = 0u;
+            const bool fold = pending && G::kCta;
             for (int j = c_lo; j < c_hi; ++j) {
-                const uint32_t cjx = x[j], o = closest[j];
+                const uint32_t cjx = x[j];
+                uint32_t o = closest[j];
+                if (fold) { const uint32_t d = (uint32_t)rhccq_d2(cjx, pend); o = d < o ? d : o; closest[j] = o; }
 #pragma unroll
                 for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {
                     if (t >= T) break;                              // uniform: no predicated-off slots are issued
@@ -829,10 +849,13 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                 }
             }
 #pragma unroll
-            for (int t = 0; t < RHCCQ_KM_MAXT; ++t) acc[t] = (long long)a32[t];
+            for (int t = 0; t < RHCCQ_KM_MAXT; ++t) { acc[t] = (long long)a32[t]; part[t] = (cum_t)a32[t]; }
         } else {
+            const bool fold = pending && G::kCta;
             for (int j = c_lo; j < c_hi; ++j) {
-                const uint32_t cjx = x[j], o = closest[j];
+                const uint32_t cjx = x[j];
+                uint32_t o = closest[j];
+                if (fold) { const uint32_t d = (uint32_t)rhccq_d2(cjx, pend); o = d < o ? d : o; closest[j] = o; }
 #pragma unroll
                 for (int t = 0; t < RHCCQ_KM_MAXT; ++t) {
                     if (t >= T) break;
@@ -840,6 +863,8 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
                     acc[t] += d < o ? d : o;
                 }
             }
+#pragma unroll
+            for (int t = 0; t < RHCCQ_KM_MAXT; ++t) part[t] = (cum_t)acc[t];
         }
         g.sum_vec(acc, T);
         int best = 0;
@@ -870,14 +895,11 @@ __device__ __forceinline__ void rhccq_kmeans(const G& g, const rhccq_km_arrays<C
         uint32_t cs = xc[0];
 #pragma unroll
         for (int t = 1; t < RHCCQ_KM_MAXT; ++t) if (t == best) cs = xc[t];
-        chunk_sum = 0;
-        for (int j = c_lo; j < c_hi; ++j) {
-            const uint32_t d = (uint32_t)rhccq_d2(x[j], cs);
-            const uint32_t o = closest[j];
-            const uint32_t m = d < o ? d : o;
-            closest[j] = m;
-            chunk_sum += m;
-        }
+        chunk_sum = part[0];                                        // sum over the chunk of min(closest, distance to the new centre)
+#pragma unroll
+        for (int t = 1; t < RHCCQ_KM_MAXT; ++t) if (t == best) chunk_sum = part[t];
+        pending = true;
+        pend = cs;
         for (int q = tid; q < 3; q += gsz) C.center[3 * c + q] = __dsub_rn((double)((cs >> (16 - 8 * q)) & 255u), mean[q]);
         pot = best_pot;
         prev_slot = best;

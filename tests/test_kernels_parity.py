@@ -40,6 +40,20 @@ def test_unique_colors_edge_cases(backend):
     r = C.get_all_unique_colors(wide, (0, 0), as_arrays=True)
     ref = O.get_all_unique_colors(wide, (0, 0))
     assert np.array_equal(r["palette"], ref["palette"]) and np.array_equal(r["indices"], ref["indices"])
+    # thousands of colours in one key-ordered bucket (one R, a narrow band of G) while R and G span their whole
+    # range: the hashed path hands the segment to the sorting path
+    skew = np.stack([np.full(4096, 10), rng.integers(0, 32, 4096), rng.integers(0, 256, 4096)], axis=1).astype(np.uint8)
+    skew[0], skew[1] = (0, 255, 7), (255, 0, 9)
+    skew = skew.reshape(64, 64, 3)
+    r = C.get_all_unique_colors(skew, (0, 0), as_arrays=True)
+    ref = O.get_all_unique_colors(skew, (0, 0))
+    assert np.array_equal(r["palette"], ref["palette"]) and np.array_equal(r["indices"], ref["indices"])
+    # a smooth segment: few values of R, many colours per value (large buckets that are still ranked by counting)
+    yy, xx = np.mgrid[0:64, 0:64]
+    smooth = np.stack([100 + xx // 16, 50 + (yy * 3 + rng.integers(0, 3, (64, 64))) % 200, rng.integers(0, 256, (64, 64))], axis=2).astype(np.uint8)
+    r = C.get_all_unique_colors(smooth, (0, 0), as_arrays=True)
+    ref = O.get_all_unique_colors(smooth, (0, 0))
+    assert np.array_equal(r["palette"], ref["palette"]) and np.array_equal(r["indices"], ref["indices"])
 
 
 # --------------------------------------------------------------------------- a2
