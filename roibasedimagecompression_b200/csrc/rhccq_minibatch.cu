@@ -13,11 +13,24 @@
 #include "rhccq_common.cuh"
 #include "rhccq_kernels.h"
 
+// Optional phase timers (cycles of rank 0 / thread 0 of every cluster, summed into rhccq_mb_prof[16]); compiled in
+// with -DRHCCQ_MB_PROFILE by tools/minibatch_phases.py only.
+#if defined(RHCCQ_MB_PROFILE) && !defined(RHCCQ_HOST_EMU)
+__device__ unsigned long long rhccq_mb_prof[16];
+#define RHCCQ_MBP_T0() long long mbp_t_ = clock64()
+#define RHCCQ_MBP(slot) do { if (rank == 0 && threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&rhccq_mb_prof[slot], (unsigned long long)(n_ - mbp_t_)); mbp_t_ = n_; } } while (0)
+#define RHCCQ_MBP_ADD(slot, v) do { if (rank == 0 && threadIdx.x == 0) atomicAdd(&rhccq_mb_prof[slot], (unsigned long long)(v)); } while (0)
+#else
+#define RHCCQ_MBP_T0() do {} while (0)
+#define RHCCQ_MBP(slot) do {} while (0)
+#define RHCCQ_MBP_ADD(slot, v) do {} while (0)
+#endif
 #define RHCCQ_MB_THREADS 512
 #define RHCCQ_MB_BATCH 1000
 #define RHCCQ_MB_MAXT 12
 #define RHCCQ_MB_SEED_GROUP 32       // seeding steps whose random numbers are drawn in one go
 #define RHCCQ_MB_SEED_CAP 3072      // subset sizes up to this are seeded out of shared memory (3 * batch = 3 000 is the usual one)
+#define RHCCQ_MB_GROUP_CAP 1024       // clusters per CTA up to which the centre update groups the batch in shared memory
 #define RHCCQ_MB_CLUSTER 8           // CTAs (SMs) that walk one palette together
 
 // ---------------------------------------------------------------- MT19937 as numpy.random.RandomState(42)
@@ -190,6 +203,7 @@ struct rhccq_mb_ws {
     int* flag;               // [k] to_reassign, then its exclusive scan
     int* perm;               // [batch]
     uint32_t* perm_xs;       // [init] colours of the init subset
+    float* cf;               // [cluster size][4k] per CTA: (-2 (c - 128), |c - 128|^2) in float32, first level of the batch labels
 };
 __host__ __device__ static inline size_t rhccq_mb_bytes(size_t n, size_t kmax, size_t init_max) {
     size_t k2 = 1;
@@ -197,7 +211,8 @@ __host__ __device__ static inline size_t rhccq_mb_bytes(size_t n, size_t kmax, s
     return rhccq_carve_bytes(n, 4) + rhccq_carve_bytes(n, 8) + rhccq_carve_bytes(init_max, 4) * 2 + rhccq_carve_bytes(init_max, 8)
            + rhccq_carve_bytes(3 * kmax, 8) * 2 + rhccq_carve_bytes(kmax, 8) + rhccq_carve_bytes(k2, 8)
            + rhccq_carve_bytes(kmax + 1, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 4) + rhccq_carve_bytes(init_max, 4)
-           + rhccq_carve_bytes(16, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 8);
+           + rhccq_carve_bytes(16, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 4) + rhccq_carve_bytes(RHCCQ_MB_BATCH, 8)
+           + rhccq_carve_bytes((size_t)RHCCQ_MB_CLUSTER * 4 * kmax, 4);
 }
 size_t rhccq_palette_minibatch_ws_bytes(int max_rows) {
     // k <= n / 10 (q <= 100); init subset <= max(3000, 3k)
@@ -281,9 +296,11 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         hdr = cv.take<int>(16);
         lab_g = cv.take<int>(RHCCQ_MB_BATCH);
         own_g = cv.take<double>(RHCCQ_MB_BATCH);
+        W.cf = cv.take<float>((size_t)RHCCQ_MB_CLUSTER * 4 * kmax);
     }
     const rhccq_mt mt = {s_mt, &s_mtpos};
     int status = 0, n = 0, k = 0, batch = 0;
+    RHCCQ_MBP_T0();
     if (rank == 0) {
         do {
             if (n_all > max_rows) { status = -1; break; }
@@ -325,6 +342,7 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         s_cand[0] = lo < ns - 1 ? lo : ns - 1;
     }
     __syncthreads();
+    RHCCQ_MBP(0);                                                   // setup: rows, random subset
     const int T = 2 + (k >= 3) + (k >= 8) + (k >= 21) + (k >= 55) + (k >= 149) + (k >= 404) + (k >= 1097) + (k >= 2981)
                   + (k >= 8104) + (k >= 22027);
     // every thread owns a contiguous chunk of the subset (the cumulative sum needs a fixed order)
@@ -339,6 +357,10 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         RHCCQ_PAR_FOR(q, 3) W.center[q] = (double)((cf >> (16 - 8 * q)) & 255u);
     }
     long long pot = rhccq_block_sum<long long>((long long)chunk_sum, s_ll);
+    // the distances to the centre chosen last are folded into `closest` by the next pass over the points (and by the
+    // search on the elements it looks at) instead of by a pass of their own
+    bool pending = false;
+    uint32_t pend = 0u;
     for (int c = 1; c < k; ++c) {
         unsigned long long total;
         const unsigned long long run0 = rhccq_block_excl_scan<unsigned long long>(chunk_sum, &total, reinterpret_cast<unsigned long long*>(s_ll));
@@ -365,7 +387,12 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
             if (lo < (int)blockDim.x) {
                 unsigned long long run = lo > 0 ? chunk_incl[lo - 1] : 0ull;
                 const int j_lo = lo * per < ns ? lo * per : ns, j_hi = j_lo + per < ns ? j_lo + per : ns;
-                for (j = j_lo; j < j_hi; ++j) { run += closest[j]; if (!((double)run < rv)) break; }
+                for (j = j_lo; j < j_hi; ++j) {
+                    uint32_t o = closest[j];
+                    if (pending) { const uint32_t d = (uint32_t)rhccq_d2(xs[j], pend); o = d < o ? d : o; }
+                    run += o;
+                    if (!((double)run < rv)) break;
+                }
                 if (j >= j_hi) j = ns;                              // (cannot happen: the chunk's sum reaches rv)
             }
             s_cand[t] = j < ns - 1 ? j : ns - 1;
@@ -374,12 +401,20 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         uint32_t xc[RHCCQ_MB_MAXT];
 #pragma unroll
         for (int t = 0; t < RHCCQ_MB_MAXT; ++t) { acc[t] = 0; xc[t] = t < T ? xs[s_cand[t]] : 0u; }
+        unsigned long long part[RHCCQ_MB_MAXT];                     // this thread's share of every candidate's potential
         for (int j = c_lo; j < c_hi; ++j) {
-            const uint32_t cj = xs[j], o = closest[j];
+            const uint32_t cj = xs[j];
+            uint32_t o = closest[j];
+            if (pending) { const uint32_t d = (uint32_t)rhccq_d2(cj, pend); o = d < o ? d : o; closest[j] = o; }
 #pragma unroll
-            for (int t = 0; t < RHCCQ_MB_MAXT; ++t)
-                if (t < T) { const uint32_t d = (uint32_t)rhccq_d2(cj, xc[t]); acc[t] += d < o ? d : o; }
+            for (int t = 0; t < RHCCQ_MB_MAXT; ++t) {
+                if (t >= T) break;                                  // uniform: no predicated-off slots are issued
+                const uint32_t d = (uint32_t)rhccq_d2(cj, xc[t]);
+                acc[t] += d < o ? d : o;
+            }
         }
+#pragma unroll
+        for (int t = 0; t < RHCCQ_MB_MAXT; ++t) part[t] = (unsigned long long)acc[t];
         rhccq_mb_sum_vec(acc, T, s_ll);
         int best = 0;
         long long best_pot = acc[0];
@@ -388,17 +423,16 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         uint32_t cs = xc[0];
 #pragma unroll
         for (int t = 1; t < RHCCQ_MB_MAXT; ++t) if (t == best) cs = xc[t];
-        chunk_sum = 0;
-        for (int j = c_lo; j < c_hi; ++j) {
-            const uint32_t d = (uint32_t)rhccq_d2(xs[j], cs), o = closest[j];
-            const uint32_t m = d < o ? d : o;
-            closest[j] = m;
-            chunk_sum += m;
-        }
+        chunk_sum = part[0];                                        // sum over the chunk of min(closest, distance to the new centre)
+#pragma unroll
+        for (int t = 1; t < RHCCQ_MB_MAXT; ++t) if (t == best) chunk_sum = part[t];
+        pending = true;
+        pend = cs;
         RHCCQ_PAR_FOR(q, 3) W.center[3 * c + q] = (double)((cs >> (16 - 8 * q)) & 255u);
         pot = best_pot;
     }
     __syncthreads();
+    RHCCQ_MBP(1);                                                   // seeding
             RHCCQ_PAR_FOR(q, k) W.counts[q] = 0.0;
             if (threadIdx.x == 0) {                                 // cdf of choice(n, batch, p=ones/n)
                 const double pi = __ddiv_rn(1.0, (double)n);
@@ -415,7 +449,9 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         __syncthreads();
         if (threadIdx.x == 0) { hdr[0] = status; hdr[1] = n; hdr[2] = k; hdr[3] = batch; hdr[4] = 0; }
     }
+    RHCCQ_MBP(2);                                                   // cumulative probabilities
     rhccq_cluster_sync();
+    RHCCQ_MBP_ADD(12, hdr[1]); RHCCQ_MBP_ADD(13, hdr[2]);
     status = hdr[0]; n = hdr[1]; k = hdr[2]; batch = hdr[3];
     if (status < 0) {                                               // cluster-uniform
         if (rank == 0 && threadIdx.x == 0) n_clusters[p] = status;
@@ -459,10 +495,24 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
             reassign = zero || n_since >= 10 * k;
             if (reassign) n_since = 0;
         }
+        RHCCQ_MBP(3);                                               // the batch's rows (rank 0)
         rhccq_cluster_sync();
+        RHCCQ_MBP(4);
         // labels and distances of this CTA's share of the batch: four threads per point, each a quarter of the
-        // centres (interleaved); the first minimum is kept by comparing (distance, index)
+        // centres (interleaved).  First level in float32 on this CTA's own table of (-2 (c - 128), |c - 128|^2): the
+        // score |c'|^2 - 2 x'.c' with x' = x - 128 differs from the float64 squared distance minus |x'|^2 by < 0.13
+        // (inputs exact or rounded by < 3.1e-5, |x'| <= 128, three fused steps at |score| < 1.4e5), so a point whose
+        // runner-up is more than 0.5 behind keeps the float32 winner; the others — ties of integer colours among
+        // them — take the float64 loop, whose first minimum by (distance, index) is the result either way.
         {
+            float* cf = W.cf + (size_t)rank * 4 * k;
+            RHCCQ_PAR_FOR(q, k) {
+                const double c0 = cen[3 * q] - 128.0, c1 = cen[3 * q + 1] - 128.0, c2 = cen[3 * q + 2] - 128.0;
+                cf[4 * q] = (float)(-2.0 * c0); cf[4 * q + 1] = (float)(-2.0 * c1); cf[4 * q + 2] = (float)(-2.0 * c2);
+                cf[4 * q + 3] = (float)(c0 * c0 + c1 * c1 + c2 * c2);
+            }
+            __syncthreads();
+            const float4* c4 = reinterpret_cast<const float4*>(cf);
             const int p_lo = rank * pts_per_cta, p_hi = p_lo + pts_per_cta < batch ? p_lo + pts_per_cta : batch;
             const int tpp = RHCCQ_WARP_SIZE >= 4 ? 4 : 1;           // threads per point
             for (int i0 = p_lo; i0 < p_hi; i0 += (int)blockDim.x / tpp) {
@@ -470,13 +520,37 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                 const bool have = i < p_hi;
                 const uint32_t c = keys[W.nb[bidx[have ? i : p_lo]]];
                 const double x0 = (double)rhccq_key_r(c), x1 = (double)rhccq_key_g(c), x2 = (double)rhccq_key_b(c);
-                double bd = 1.0e300;
-                int bq = 0x7fffffff;
+                const float f0 = (float)(rhccq_key_r(c) - 128), f1 = (float)(rhccq_key_g(c) - 128), f2 = (float)(rhccq_key_b(c) - 128);
+                float fb = 3.0e38f, fs = 3.0e38f;
+                int fq = 0x7fffffff;
                 for (int q = part; q < k; q += tpp) {
-                    const double d = rhccq_mb_dist(x0, x1, x2, cen + 3 * q);
-                    if (d < bd) { bd = d; bq = q; }
+                    const float4 cq = c4[q];
+                    const float d = fmaf(f0, cq.x, fmaf(f1, cq.y, fmaf(f2, cq.z, cq.w)));
+                    fs = fminf(fs, fmaxf(d, fb));
+                    const bool lt = d < fb;
+                    fb = lt ? d : fb;
+                    fq = lt ? q : fq;
                 }
                 __syncwarp();                                       // the four parts ran different trip counts
+                for (int m = 1; m < tpp; m <<= 1) {
+                    const float ob = rhccq_shfl_xor(fb, m), os = rhccq_shfl_xor(fs, m);
+                    const int oq = rhccq_shfl_xor(fq, m);
+                    fs = fminf(fminf(fs, os), fmaxf(fb, ob));       // runner-up of the union
+                    if (ob < fb || (ob == fb && oq < fq)) { fb = ob; fq = oq; }
+                }
+                const bool open_pt = !(fs - fb > 0.5f);             // (the same in the four lanes of a point)
+                double bd = 1.0e300;
+                int bq = 0x7fffffff;
+                if (open_pt) {
+                    for (int q = part; q < k; q += tpp) {
+                        const double d = rhccq_mb_dist(x0, x1, x2, cen + 3 * q);
+                        if (d < bd) { bd = d; bq = q; }
+                    }
+                } else if (part == 0) {
+                    bq = fq;
+                    bd = rhccq_mb_dist(x0, x1, x2, cen + 3 * fq);
+                }
+                __syncwarp();
                 for (int m = 1; m < tpp; m <<= 1) {
                     const double od = rhccq_shfl_xor(bd, m);
                     const int oq = rhccq_shfl_xor(bq, m);
@@ -485,21 +559,70 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                 if (have && part == 0) { lab_g[i] = bq; own_g[i] = bd; }
             }
         }
+        RHCCQ_MBP(5);                                               // labels of the batch
         rhccq_cluster_sync();
+        RHCCQ_MBP(6);
         // centre update of this CTA's share of the clusters, members in batch order (_k_means_minibatch.pyx:68-118)
         RHCCQ_PAR_FOR(i, batch) { s_lab[i] = lab_g[i]; s_col[i] = keys[W.nb[bidx[i]]]; }
         __syncthreads();
         {
             const int q_lo = rank * k_per_cta, q_hi = q_lo + k_per_cta < k ? q_lo + k_per_cta : k;
+            const int kpc = q_hi > q_lo ? q_hi - q_lo : 0;
+            // the batch grouped by cluster, batch order kept inside a group (the sums below are float64 additions in
+            // that order): counts, exclusive scan, then a stable scatter 32 elements at a time (rank among the equal
+            // labels of a tile by warp match).  Lives behind the batch's arrays in the shared buffer.
+            int* g_start = reinterpret_cast<int*>(s_raw + RHCCQ_MB_BATCH * 16);                // [kpc + 1]
+            int* g_cur = g_start + RHCCQ_MB_GROUP_CAP + 1;                                     // [kpc]
+            int* g_order = g_cur + RHCCQ_MB_GROUP_CAP;                                         // [batch]
+            const bool grouped = kpc <= RHCCQ_MB_GROUP_CAP;
+            if (grouped) {
+                RHCCQ_PAR_FOR(q, kpc + 1) g_start[q] = 0;
+                __syncthreads();
+                RHCCQ_PAR_FOR(i, batch) { const int L = s_lab[i] - q_lo; if (L >= 0 && L < kpc) atomicAdd(&g_start[L], 1); }
+                __syncthreads();
+                rhccq_block_excl_scan_array<int>(g_start, kpc + 1, s_i);
+                RHCCQ_PAR_FOR(q, kpc) g_cur[q] = g_start[q];
+                __syncthreads();
+                if (threadIdx.x < RHCCQ_WARP_SIZE) {
+                    for (int base = 0; base < batch; base += RHCCQ_WARP_SIZE) {
+                        const int i = base + RHCCQ_LANE;
+                        const int L = i < batch ? s_lab[i] - q_lo : -1;
+                        const bool mine = L >= 0 && L < kpc;
+#ifdef RHCCQ_HOST_EMU
+                        if (mine) g_order[g_cur[L]++] = i;
+#else
+                        const unsigned m = __match_any_sync(0xffffffffu, mine ? L : 0x40000000 + RHCCQ_LANE);
+                        const int rk = __popc(m & rhccq_lanemask_lt());
+                        int at = 0;
+                        if (mine) at = g_cur[L];
+                        __syncwarp();
+                        if (mine) {
+                            g_order[at + rk] = i;
+                            if (rk == __popc(m) - 1) g_cur[L] = at + __popc(m);
+                        }
+                        __syncwarp();
+#endif
+                    }
+                }
+                __syncthreads();
+            }
             for (int q = q_lo + (int)threadIdx.x; q < q_hi; q += (int)blockDim.x) {
                 int members = 0;
-                for (int i = 0; i < batch; ++i) members += s_lab[i] == q;
+                if (grouped) members = g_start[q - q_lo + 1] - g_start[q - q_lo];
+                else for (int i = 0; i < batch; ++i) members += s_lab[i] == q;
                 if (members > 0) {
                     const double w = W.counts[q];
                     double c0 = __dmul_rn(cen[3 * q], w), c1 = __dmul_rn(cen[3 * q + 1], w), c2 = __dmul_rn(cen[3 * q + 2], w);
-                    for (int i = 0; i < batch; ++i) if (s_lab[i] == q) {
-                        const uint32_t c = s_col[i];
-                        c0 = __dadd_rn(c0, (double)rhccq_key_r(c)); c1 = __dadd_rn(c1, (double)rhccq_key_g(c)); c2 = __dadd_rn(c2, (double)rhccq_key_b(c));
+                    if (grouped) {
+                        for (int t = g_start[q - q_lo]; t < g_start[q - q_lo + 1]; ++t) {
+                            const uint32_t c = s_col[g_order[t]];
+                            c0 = __dadd_rn(c0, (double)rhccq_key_r(c)); c1 = __dadd_rn(c1, (double)rhccq_key_g(c)); c2 = __dadd_rn(c2, (double)rhccq_key_b(c));
+                        }
+                    } else {
+                        for (int i = 0; i < batch; ++i) if (s_lab[i] == q) {
+                            const uint32_t c = s_col[i];
+                            c0 = __dadd_rn(c0, (double)rhccq_key_r(c)); c1 = __dadd_rn(c1, (double)rhccq_key_g(c)); c2 = __dadd_rn(c2, (double)rhccq_key_b(c));
+                        }
                     }
                     const double wn = __dadd_rn(w, (double)members);
                     const double alpha = __ddiv_rn(1.0, wn);
@@ -510,7 +633,9 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                 }
             }
         }
+        RHCCQ_MBP(7);                                               // centre update
         rhccq_cluster_sync();
+        RHCCQ_MBP(8);
         if (rank == 0) {
             RHCCQ_PAR_FOR(i, batch) s_own[i] = own_g[i];
             __syncthreads();
@@ -530,15 +655,41 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                 RHCCQ_PAR_FOR(q, k) { const int f = W.counts[q] < lim ? 1 : 0; W.flag[q] = f; cnt += f; }
                 cnt = rhccq_block_sum<int>(cnt, s_i);
                 if ((double)cnt > 0.5 * (double)batch) {
-                    // keep all but the int(0.5 * batch) smallest counts (stable order: ties by index)
-                    int k2 = 1;
-                    while (k2 < k) k2 <<= 1;
-                    for (int q = threadIdx.x; q < k2; q += blockDim.x)
-                        W.skey[q] = q < k ? (((unsigned long long)(long long)W.counts[q] << 24) | (unsigned)q) : ~0ull;
-                    __syncthreads();
-                    rhccq_block_bitonic_sort<unsigned long long>(W.skey, k2);
+                    // keep all but the int(0.5 * batch) smallest counts (stable order: ties by index).  The counts are
+                    // small integers while many clusters are still empty, which is when this branch is taken step after
+                    // step: then the cut falls inside the run of one small count value v, and the kept set is "count < v,
+                    // plus the first few clusters with count == v by index" — one scan instead of a sort of all k keys.
                     const int first_kept = (int)(0.5 * (double)batch);
-                    RHCCQ_PAR_FOR(r, k) if (r >= first_kept) W.flag[(int)(W.skey[r] & 0xffffffu)] = 0;
+                    int* rank_eq = reinterpret_cast<int*>(W.skey);
+                    bool selected = false;
+                    int below = 0;                                      // clusters with count < v
+                    for (int v = 0; v < 16 && !selected; ++v) {
+                        int eq = 0;
+                        RHCCQ_PAR_FOR(q, k) eq += W.counts[q] == (double)v ? 1 : 0;
+                        eq = rhccq_block_sum<int>(eq, s_i);
+                        if (below + eq >= first_kept) {
+                            // the cut is inside the clusters with count == v: the first (first_kept - below) of them stay flagged
+                            RHCCQ_PAR_FOR(q, k) rank_eq[q] = W.counts[q] == (double)v ? 1 : 0;
+                            __syncthreads();
+                            rhccq_block_excl_scan_array<int>(rank_eq, k, s_i);
+                            const int take = first_kept - below;
+                            RHCCQ_PAR_FOR(q, k) {
+                                const double c = W.counts[q];
+                                if (c > (double)v || (c == (double)v && rank_eq[q] >= take)) W.flag[q] = 0;
+                            }
+                            selected = true;
+                        }
+                        below += eq;
+                    }
+                    if (!selected) {
+                        int k2 = 1;
+                        while (k2 < k) k2 <<= 1;
+                        for (int q = threadIdx.x; q < k2; q += blockDim.x)
+                            W.skey[q] = q < k ? (((unsigned long long)(long long)W.counts[q] << 24) | (unsigned)q) : ~0ull;
+                        __syncthreads();
+                        rhccq_block_bitonic_sort<unsigned long long>(W.skey, k2);
+                        RHCCQ_PAR_FOR(r, k) if (r >= first_kept) W.flag[(int)(W.skey[r] & 0xffffffu)] = 0;
+                    }
                     __syncthreads();
                     cnt = 0;
                     RHCCQ_PAR_FOR(q, k) cnt += W.flag[q];
@@ -613,7 +764,11 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
             __syncthreads();
             if (threadIdx.x == 0) hdr[4] = done;
         }
+        RHCCQ_MBP(9);                                               // inertia, reassignment, convergence (rank 0)
+        RHCCQ_MBP_ADD(11, 1);
+        if (reassign) RHCCQ_MBP_ADD(14, 1);
         rhccq_cluster_sync();
+        RHCCQ_MBP(10);
         { double* t = cen; cen = cen_new; cen_new = t; }
         if (hdr[4]) break;                                          // cluster-uniform
     }
@@ -622,6 +777,13 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         if (threadIdx.x == 0) n_clusters[p] = k;
     }
 }
+
+#if defined(RHCCQ_MB_PROFILE) && !defined(RHCCQ_HOST_EMU)
+extern "C" int rhccq_mb_prof_read(unsigned long long* host_out, int reset) {
+    if (reset) { unsigned long long z[16] = {0}; return (int)cudaMemcpyToSymbol(rhccq_mb_prof, z, sizeof z); }
+    return (int)cudaMemcpyFromSymbol(host_out, rhccq_mb_prof, 16 * sizeof(unsigned long long));
+}
+#endif
 
 // status -4 (set by rhccq_k_palette_dbscan) selects the palettes of this branch; one cluster of CTAs per palette
 __global__ void __launch_bounds__(RHCCQ_MB_THREADS)
