@@ -45,6 +45,8 @@ def _lib():
         lib.km_first_seed.restype = ctypes.c_int
         lib.km_first_seed.argtypes = [ctypes.c_int, ctypes.c_double]
         lib.km_gemm_edge_rows.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        lib.km_estep_labels.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        lib.km_estep_labels.restype = None
         _LIB = lib
     return _LIB
 
@@ -108,3 +110,13 @@ def kmeans_labels(colors: np.ndarray, k: int, return_info: bool = False):
 def kmeans_pp_seeds(colors: np.ndarray, k: int) -> np.ndarray:
     """Indices of the k-means++ seeds (sklearn/cluster/_kmeans.py:216-282)."""
     return kmeans_labels(colors, k, return_info=True)[1]["seeds"]
+
+
+def estep_labels(x: np.ndarray, centers: np.ndarray) -> np.ndarray:
+    """Labels of float64 points x[n,3] against centers[k,3] by scikit-learn's chunked E step (_labels_inertia):
+    ``|c|^2 - 2 x.c`` through dgemm in chunks of 256 samples, first minimum."""
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
+    c = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3)
+    lab = np.empty(len(x), dtype=np.int32)
+    _lib().km_estep_labels(x.ctypes.data, len(x), c.ctypes.data, len(c), lab.ctypes.data)
+    return lab.astype(np.int64)

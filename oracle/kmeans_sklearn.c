@@ -209,6 +209,15 @@ static void e_step(const km_problem* p, const double* centers, int32_t* labels) 
     free(csn);
 }
 
+/* Labels of n points against k centres as sklearn's _labels_inertia computes them (the same chunked E step
+ * with update_centers == False): used by oracle/minibatch_restated.py, whose batches and final prediction
+ * go through it.  x[n,3] and centers[k,3] as given (MiniBatchKMeans does not centre the data). */
+void km_estep_labels(const double* x, int n, const double* centers, int k, int32_t* labels) {
+    km_problem P;
+    P.n = n; P.k = k; P.xc = (double*)x; P.xsn = 0; P.tol = 0.0;
+    e_step(&P, centers, labels);
+}
+
 static int cmp_far(const void* a, const void* b, void* ctx) {
     const double* d = (const double*)ctx;
     int ia = *(const int*)a, ib = *(const int*)b;

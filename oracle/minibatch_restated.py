@@ -10,21 +10,30 @@ n_init='auto').fit_predict(colours.astype(float))``
 :1566-1684 (_mini_batch_step), :1974-2037 (_mini_batch_convergence), :2039-2054 (_random_reassign),
 :964-1043 (_init_centroids), :180-282 (_kmeans_plusplus), _k_means_minibatch.pyx:68-118 (centre update).
 
-As with K-Means (oracle/kmeans_restated.py) scikit-learn's float evaluation (GEMM-based distances,
-OpenMP reductions, an unstable argsort) cannot be matched bit for bit, so this restatement keeps the
-algorithm, every parameter and the consumption of the ``RandomState(42)`` stream — it calls numpy's own
-``randint`` / ``choice`` / ``random_sample`` in the order scikit-learn does — and fixes the evaluation order:
+The float evaluation follows scikit-learn operation by operation, as oracle/kmeans_sklearn.c does for KMeans:
 
-* a point-to-centre distance is ``((x0-c0)^2 + (x1-c1)^2) + (x2-c2)^2`` in IEEE double, first minimum wins
-  (sklearn: ``|c|^2 - 2 x.c`` by GEMM);
-* the batch inertia is the sum of those distances in batch order (sklearn: an OpenMP reduction);
-* the k-means++ sums are exact integers;
-* the centre update is the scalar loop of _k_means_minibatch.pyx, in batch order (identical to sklearn);
-* when more than half a batch of centres would be reassigned, the ones kept are chosen by a STABLE sort of
-  the counts (sklearn: numpy's default, unstable, argsort).
+* labels (every batch, and the final prediction over the whole palette) are those of ``_labels_inertia``: the
+  chunked E step, ``|c|^2 - 2 x.c`` through dgemm in chunks of 256 samples, first minimum
+  (``kmeans_restated.estep_labels`` -> oracle/kmeans_sklearn.c: e_step; MiniBatchKMeans does not centre the data);
+* the distance of a point to its centre that enters the batch inertia is ``_inertia_dense``'s direct
+  ``((x0-c0)^2 + (x1-c1)^2) + (x2-c2)^2``; the inertia is their sum in batch order (sklearn: an OpenMP reduction
+  whose order depends on the thread count; it only feeds the early-stopping average);
+* the k-means++ sums are exact integers (uncentred uint8 data: every term of sklearn's float evaluation is an
+  integer below 2^53, so its results are the same integers);
+* the centre update is the scalar loop of _k_means_minibatch.pyx, in batch order;
+* ``RandomState(42)`` is consumed by numpy's own ``randint`` / ``choice`` / ``random_sample`` in sklearn's order.
 
-The CUDA kernel (csrc/rhccq_minibatch.cu) must match this file bit for bit; agreement with scikit-learn
-itself is measured in tests/test_oracle_golden.py.
+With these, labels AND final centres equal scikit-learn's bit for bit (tests/test_oracle_golden.py) on every
+palette on which one branch is not taken: when more than half a batch of centres would be reassigned
+(``to_reassign.sum() > 0.5 * batch_size``, which needs k > 500 and in practice k > ~1000), scikit-learn keeps the
+centres with the largest counts by ``np.argsort(weight_sums)``, numpy's default UNSTABLE sort, and the counts are
+small integers full of ties.  Which tied centres are kept then depends on numpy's CPU dispatch (x86-simd-sort's
+AVX-512 argsort, its AVX2 one and the scalar introsort order the ties differently: the same call gives three
+different answers under NPY_DISABLE_CPU_FEATURES), so the reference's own output is machine-dependent there.
+This restatement — and the CUDA kernel — keep the STABLE order (ties by index); ``info["unstable_cuts"]`` counts
+how often a call went through that branch.
+
+The CUDA kernel (csrc/rhccq_minibatch.cu) must match this file bit for bit.
 """
 from __future__ import annotations
 
@@ -74,21 +83,14 @@ def _kmeans_pp(xs: np.ndarray, k: int, rs: np.random.RandomState) -> np.ndarray:
 
 
 def _nearest(xf: np.ndarray, centers: np.ndarray):
-    """(labels, own distance): first minimum of ((d0^2 + d1^2) + d2^2) in IEEE double."""
-    n, k = xf.shape[0], centers.shape[0]
-    labels = np.empty(n, dtype=np.int64)
-    own = np.empty(n, dtype=np.float64)
-    step = max(1, (1 << 22) // max(k, 1))
-    for lo in range(0, n, step):
-        xs = xf[lo:lo + step]
-        d0 = xs[:, None, 0] - centers[None, :, 0]
-        d1 = xs[:, None, 1] - centers[None, :, 1]
-        d2 = xs[:, None, 2] - centers[None, :, 2]
-        dist = (d0 * d0 + d1 * d1) + d2 * d2
-        lab = np.argmin(dist, axis=1)
-        labels[lo:lo + step] = lab
-        own[lo:lo + step] = dist[np.arange(xs.shape[0]), lab]
-    return labels, own
+    """(labels, own distance) as sklearn's _labels_inertia returns them: the labels by the chunked E step
+    (``|c|^2 - 2 x.c`` through dgemm, first minimum: oracle/kmeans_sklearn.c), the distance of a point to its
+    centre by _inertia_dense's direct ``((d0^2 + d1^2) + d2^2)``."""
+    from . import kmeans_restated as K
+    lab = K.estep_labels(xf, centers)
+    d = xf - centers[lab]
+    own = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    return lab, own
 
 
 def minibatch_labels(colors: np.ndarray, k: int, return_info: bool = False):
@@ -118,6 +120,7 @@ def minibatch_labels(colors: np.ndarray, k: int, return_info: bool = False):
     n_steps = (MAX_ITER * n) // batch                        # :2163
     p = np.ones(n) / float(n)                                # :2164 normalized_sample_weight (sum of ones == n)
     steps_done = 0
+    unstable_cuts = 0
     for step in range(n_steps):
         idx = rs.choice(n, batch, p=p, replace=True)         # :2171-2176
         xb, xbf = x[idx], xf[idx]
@@ -142,6 +145,7 @@ def minibatch_labels(colors: np.ndarray, k: int, return_info: bool = False):
         if reassign:                                         # :1652-1682
             to_reassign = counts < REASSIGNMENT_RATIO * counts.max()
             if to_reassign.sum() > 0.5 * batch:
+                unstable_cuts += 1
                 keep = np.argsort(counts, kind="stable")[int(0.5 * batch):]
                 to_reassign[keep] = False
             n_re = int(to_reassign.sum())
@@ -170,5 +174,5 @@ def minibatch_labels(colors: np.ndarray, k: int, return_info: bool = False):
             break
     labels, _ = _nearest(xf, centers)
     if return_info:
-        return labels, {"steps": steps_done, "centers": centers, "counts": counts}
+        return labels, {"steps": steps_done, "centers": centers, "counts": counts, "unstable_cuts": unstable_cuts}
     return labels

@@ -11,17 +11,20 @@
 // numpy's randint / choice / shuffle and the inertia sum are sequential by definition and run on thread 0);
 // the final assignment, which is the only part proportional to n*k, is a separate kernel over all SMs.
 #include "rhccq_common.cuh"
+#include "rhccq_sklearn.cuh"
 #include "rhccq_kernels.h"
 
 // Optional phase timers (cycles of rank 0 / thread 0 of every cluster, summed into rhccq_mb_prof[16]); compiled in
 // with -DRHCCQ_MB_PROFILE by tools/minibatch_phases.py only.
 #if defined(RHCCQ_MB_PROFILE) && !defined(RHCCQ_HOST_EMU)
 __device__ unsigned long long rhccq_mb_prof[16];
-#define RHCCQ_MBP_T0() long long mbp_t_ = clock64()
+#define RHCCQ_MBP_T0() long long mbp_t_ = clock64(); const long long mbp_start_ = mbp_t_
+#define RHCCQ_MBP_END() do { if (rank == 0 && threadIdx.x == 0) atomicMax(&rhccq_mb_prof[15], (unsigned long long)(clock64() - mbp_start_)); } while (0)
 #define RHCCQ_MBP(slot) do { if (rank == 0 && threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&rhccq_mb_prof[slot], (unsigned long long)(n_ - mbp_t_)); mbp_t_ = n_; } } while (0)
 #define RHCCQ_MBP_ADD(slot, v) do { if (rank == 0 && threadIdx.x == 0) atomicAdd(&rhccq_mb_prof[slot], (unsigned long long)(v)); } while (0)
 #else
 #define RHCCQ_MBP_T0() do {} while (0)
+#define RHCCQ_MBP_END() do {} while (0)
 #define RHCCQ_MBP(slot) do {} while (0)
 #define RHCCQ_MBP_ADD(slot, v) do {} while (0)
 #endif
@@ -152,31 +155,20 @@ __device__ __forceinline__ double rhccq_mb_dist(double x0, double x1, double x2,
     return __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
 }
 
-// v[0..cnt) <- block sums (integers: the order of additions is immaterial); sll holds RHCCQ_MAX_WARPS * MAXT
-__device__ __forceinline__ void rhccq_mb_sum_vec(long long* v, int cnt, long long* sll) {
-#ifndef RHCCQ_HOST_EMU
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < RHCCQ_MB_MAXT; ++t) {
-        if (t < cnt) {
-            long long x = v[t];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-            if (lane == 0) sll[warp * RHCCQ_MB_MAXT + t] = x;
-        }
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < cnt) {                                  // one thread per entry adds the warps' partial sums
-        long long x = 0;
-        for (int w = 0; w < nwarp; ++w) x += sll[w * RHCCQ_MB_MAXT + threadIdx.x];
-        sll[RHCCQ_MAX_WARPS * RHCCQ_MB_MAXT - RHCCQ_MB_MAXT + threadIdx.x] = x;       // (the last warp slot is free: nwarp <= 16 here)
-    }
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < RHCCQ_MB_MAXT; ++t)
-        if (t < cnt) v[t] = sll[RHCCQ_MAX_WARPS * RHCCQ_MB_MAXT - RHCCQ_MB_MAXT + t];
+// sum over the lanes of a warp, in every lane
+__device__ __forceinline__ uint32_t rhccq_mb_warp_sum(uint32_t v) {
+#ifdef RHCCQ_HOST_EMU
+    return v;
+#else
+    return __reduce_add_sync(0xffffffffu, v);
 #endif
+}
+__device__ __forceinline__ unsigned long long rhccq_mb_warp_sum(unsigned long long v) {
+#ifndef RHCCQ_HOST_EMU
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+#endif
+    return v;
 }
 
 // number of clusters: ceil(n * (q / 100) / 10) as Python evaluates it (clustering.py:210)
@@ -248,7 +240,7 @@ __device__ __forceinline__ void rhccq_cluster_rank(int* rank, int* size, int* id
 // over all CTAs, exchanging through the global workspace between cluster barriers.
 __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batch& B, int p, const double* __restrict__ quality,
                                         int* __restrict__ n_clusters, int max_rows, unsigned char* wsbase,
-                                        double* __restrict__ centers_out, int rank, int csize) {
+                                        double* __restrict__ centers_out, int* __restrict__ labels, int rank, int csize) {
     __shared__ uint32_t s_mt[624];
     __shared__ int s_mtpos;
     __shared__ int s_i[RHCCQ_MAX_WARPS + 2 + 16];
@@ -265,11 +257,11 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
     uint32_t* s_xs = reinterpret_cast<uint32_t*>(s_raw + RHCCQ_MB_THREADS * 8);         // [RHCCQ_MB_SEED_CAP]
     uint32_t* s_closest = s_xs + RHCCQ_MB_SEED_CAP;                                     // [RHCCQ_MB_SEED_CAP]
     uint32_t* s_rbuf = reinterpret_cast<uint32_t*>(s_raw) + 1024;       // 624 raw generator outputs, beside a 1000-int array (never while the seeding arrays live)
-    __shared__ double s_rv[RHCCQ_MB_MAXT];
     __shared__ int s_prog;
     __shared__ uint32_t s_rvraw[2 * RHCCQ_MB_MAXT * RHCCQ_MB_SEED_GROUP];
     __shared__ int s_cand[RHCCQ_MB_MAXT];
     __shared__ double s_val;
+    __shared__ unsigned long long s_wtot[RHCCQ_MAX_WARPS];
     const int n_all = B.pal_cnt[p];
     const uint32_t* keys = B.pal_keys + B.pal_off[p];
     const size_t kmax = (size_t)max_rows / 10 + 2;
@@ -309,7 +301,9 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
     RHCCQ_PAR_FOR(i, n_all) mark[i] = keys[i] != 0u ? 1 : 0;
     __syncthreads();
     n = rhccq_block_excl_scan_array<int>(mark, n_all, s_i);
-    RHCCQ_PAR_FOR(i, n_all) if (keys[i] != 0u) W.nb[mark[i]] = i;
+    // (the label slot of a row carries its position among the non-black rows until rhccq_k_minibatch_assign
+    // replaces it: scikit-learn's E step depends on where in its chunk of 256 a sample sits)
+    RHCCQ_PAR_FOR(i, n_all) if (keys[i] != 0u) { W.nb[mark[i]] = i; labels[B.pal_off[p] + i] = mark[i]; }
     __syncthreads();
     k = rhccq_mb_k(n, quality[p]);
     if (k < 1 || k > n || (size_t)k > kmax - 1) { status = -1; break; }
@@ -349,88 +343,119 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
     const int per = (ns + (int)blockDim.x - 1) / (int)blockDim.x;
     const int c_lo = (int)threadIdx.x * per < ns ? (int)threadIdx.x * per : ns;
     const int c_hi = c_lo + per < ns ? c_lo + per : ns;
-    long long acc[RHCCQ_MB_MAXT];
     unsigned long long chunk_sum = 0;
     {
         const uint32_t cf = xs[s_cand[0]];
         for (int j = c_lo; j < c_hi; ++j) { const uint32_t d = (uint32_t)rhccq_d2(xs[j], cf); closest[j] = d; chunk_sum += d; }
         RHCCQ_PAR_FOR(q, 3) W.center[q] = (double)((cf >> (16 - 8 * q)) & 255u);
     }
-    long long pot = rhccq_block_sum<long long>((long long)chunk_sum, s_ll);
-    // the distances to the centre chosen last are folded into `closest` by the next pass over the points (and by the
-    // search on the elements it looks at) instead of by a pass of their own
-    bool pending = false;
-    uint32_t pend = 0u;
-    for (int c = 1; c < k; ++c) {
-        unsigned long long total;
-        const unsigned long long run0 = rhccq_block_excl_scan<unsigned long long>(chunk_sum, &total, reinterpret_cast<unsigned long long*>(s_ll));
-        chunk_incl[threadIdx.x] = run0 + chunk_sum;
-        // uniform(size=T) of this step: the raw outputs of RHCCQ_MB_SEED_GROUP steps are drawn together by the whole
-        // CTA (nothing else consumes the stream during the seeding), two per double, in order
-        const int gi = (c - 1) % RHCCQ_MB_SEED_GROUP;
-        if (gi == 0) {
-            const int steps = k - c < RHCCQ_MB_SEED_GROUP ? k - c : RHCCQ_MB_SEED_GROUP;
-            rhccq_mt_fill_raw(mt, s_rvraw, 2 * T * steps);
-        }
-        RHCCQ_PAR_FOR(t, T) {
-            const uint32_t a = s_rvraw[2 * (gi * T + t)] >> 5, b = s_rvraw[2 * (gi * T + t) + 1] >> 6;
-            s_rv[t] = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
-        }
-        __syncthreads();
-        RHCCQ_PAR_FOR(t, T) {                                      // the T searches side by side
-            // first j with cum[j] >= rv, cum = running sum of `closest`: first the chunk whose running sum gets
-            // there (the sums of whole chunks are non-decreasing), then the element inside it
-            const double rv = __dmul_rn(s_rv[t], (double)pot);
-            int lo = 0, hi = (int)blockDim.x;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)chunk_incl[mid] < rv) lo = mid + 1; else hi = mid; }
-            int j = ns;
-            if (lo < (int)blockDim.x) {
-                unsigned long long run = lo > 0 ? chunk_incl[lo - 1] : 0ull;
-                const int j_lo = lo * per < ns ? lo * per : ns, j_hi = j_lo + per < ns ? j_lo + per : ns;
-                for (j = j_lo; j < j_hi; ++j) {
-                    uint32_t o = closest[j];
-                    if (pending) { const uint32_t d = (uint32_t)rhccq_d2(xs[j], pend); o = d < o ? d : o; }
-                    run += o;
-                    if (!((double)run < rv)) break;
-                }
-                if (j >= j_hi) j = ns;                              // (cannot happen: the chunk's sum reaches rv)
-            }
-            s_cand[t] = j < ns - 1 ? j : ns - 1;
-        }
-        __syncthreads();
-        uint32_t xc[RHCCQ_MB_MAXT];
+    const unsigned long long pot0 = (unsigned long long)rhccq_block_sum<long long>((long long)chunk_sum, s_ll);
+    // Three block barriers per centre: [scan of the threads' chunk sums inside every warp] | [T threads search their
+    // candidate: warp totals, lanes of one warp, elements of one chunk] | [every thread's share of the T potentials,
+    // added up inside the warp] | [every warp adds the warps' shares and knows the winner].  S is the type the sums
+    // are carried in: 32 bits (one REDUX per warp sum) when the whole subset's potential fits, else 64.
+    auto seed_loop = [&](auto s_zero) {
+        using S = decltype(s_zero);
+        S* s_sv = reinterpret_cast<S*>(s_ll);                       // [warps][RHCCQ_MB_MAXT]
+        const int lane = RHCCQ_LANE, warp = RHCCQ_WARP, nw = RHCCQ_NWARPS;
+        unsigned long long pot = pot0;
+        // the distances to the centre chosen last are folded into `closest` by the next pass over the points (and by
+        // the search on the elements it looks at) instead of by a pass of their own
+        bool pending = false;
+        uint32_t pend = 0u;
+        for (int c = 1; c < k; ++c) {
+            unsigned long long incl = chunk_sum;
+#ifndef RHCCQ_HOST_EMU
 #pragma unroll
-        for (int t = 0; t < RHCCQ_MB_MAXT; ++t) { acc[t] = 0; xc[t] = t < T ? xs[s_cand[t]] : 0u; }
-        unsigned long long part[RHCCQ_MB_MAXT];                     // this thread's share of every candidate's potential
-        for (int j = c_lo; j < c_hi; ++j) {
-            const uint32_t cj = xs[j];
-            uint32_t o = closest[j];
-            if (pending) { const uint32_t d = (uint32_t)rhccq_d2(cj, pend); o = d < o ? d : o; closest[j] = o; }
+            for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = rhccq_shfl_up(incl, d); if (lane >= d) incl += o; }
+#endif
+            chunk_incl[threadIdx.x] = incl;                         // inclusive inside the warp
+            if (lane == RHCCQ_WARP_SIZE - 1) s_wtot[warp] = incl;
+            // uniform(size=T) of this step: the raw outputs of RHCCQ_MB_SEED_GROUP steps are drawn together by the
+            // whole CTA (nothing else consumes the stream during the seeding), two per double, in order
+            const int gi = (c - 1) % RHCCQ_MB_SEED_GROUP;
+            if (gi == 0) {
+                const int steps = k - c < RHCCQ_MB_SEED_GROUP ? k - c : RHCCQ_MB_SEED_GROUP;
+                rhccq_mt_fill_raw(mt, s_rvraw, 2 * T * steps);
+            }
+            __syncthreads();
+            RHCCQ_PAR_FOR(t, T) {                                   // the T searches side by side
+                const uint32_t a = s_rvraw[2 * (gi * T + t)] >> 5, b = s_rvraw[2 * (gi * T + t) + 1] >> 6;
+                const double u = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+                const double rv = __dmul_rn(u, (double)pot);
+                // first j with cum[j] >= rv, cum = running sum of `closest`: the warp whose running total gets there
+                // (totals are non-decreasing: count those below), the chunk inside it, the element inside the chunk
+                unsigned long long base = 0, run = 0;
+                int w = 0;
+                for (int i = 0; i < nw; ++i) {
+                    run += s_wtot[i];
+                    const bool lt = (double)run < rv;
+                    w += lt ? 1 : 0;
+                    base = lt ? run : base;
+                }
+                int j = ns;
+                if (w < nw) {
+                    const unsigned long long* wi = chunk_incl + w * RHCCQ_WARP_SIZE;
+                    int lo = 0, hi = RHCCQ_WARP_SIZE;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)(base + wi[mid]) < rv) lo = mid + 1; else hi = mid; }
+                    if (lo < RHCCQ_WARP_SIZE) {
+                        const int ci = w * RHCCQ_WARP_SIZE + lo;
+                        run = base + (lo > 0 ? wi[lo - 1] : 0ull);
+                        const int j_lo = ci * per < ns ? ci * per : ns, j_hi = j_lo + per < ns ? j_lo + per : ns;
+                        for (j = j_lo; j < j_hi; ++j) {
+                            uint32_t o = closest[j];
+                            if (pending) { const uint32_t d = (uint32_t)rhccq_d2(xs[j], pend); o = d < o ? d : o; }
+                            run += o;
+                            if (!((double)run < rv)) break;
+                        }
+                        if (j >= j_hi) j = ns;                      // (cannot happen: the chunk's sum reaches rv)
+                    }
+                }
+                s_cand[t] = j < ns - 1 ? j : ns - 1;
+            }
+            __syncthreads();
+            uint32_t xc[RHCCQ_MB_MAXT];
+            S part[RHCCQ_MB_MAXT];                                  // this thread's share of every candidate's potential
+#pragma unroll
+            for (int t = 0; t < RHCCQ_MB_MAXT; ++t) { part[t] = 0; xc[t] = t < T ? xs[s_cand[t]] : 0u; }
+            for (int j = c_lo; j < c_hi; ++j) {
+                const uint32_t cj = xs[j];
+                uint32_t o = closest[j];
+                if (pending) { const uint32_t d = (uint32_t)rhccq_d2(cj, pend); o = d < o ? d : o; closest[j] = o; }
+#pragma unroll
+                for (int t = 0; t < RHCCQ_MB_MAXT; ++t) {
+                    if (t >= T) break;                              // uniform: no predicated-off slots are issued
+                    const uint32_t d = (uint32_t)rhccq_d2(cj, xc[t]);
+                    part[t] += (S)(d < o ? d : o);
+                }
+            }
 #pragma unroll
             for (int t = 0; t < RHCCQ_MB_MAXT; ++t) {
-                if (t >= T) break;                                  // uniform: no predicated-off slots are issued
-                const uint32_t d = (uint32_t)rhccq_d2(cj, xc[t]);
-                acc[t] += d < o ? d : o;
+                if (t >= T) break;
+                const S x = rhccq_mb_warp_sum(part[t]);
+                if (lane == 0) s_sv[warp * RHCCQ_MB_MAXT + t] = x;
             }
+            __syncthreads();
+            int best = 0;
+            S best_pot = 0;
+#pragma unroll
+            for (int t = 0; t < RHCCQ_MB_MAXT; ++t) {
+                if (t >= T) break;
+                const S x = rhccq_mb_warp_sum(lane < nw ? s_sv[lane * RHCCQ_MB_MAXT + t] : (S)0);
+                if (t == 0 || x < best_pot) { best_pot = x; best = t; }
+            }
+            uint32_t cs = xc[0];
+            chunk_sum = part[0];                                    // sum over the chunk of min(closest, distance to the new centre)
+#pragma unroll
+            for (int t = 1; t < RHCCQ_MB_MAXT; ++t) if (t == best) { cs = xc[t]; chunk_sum = part[t]; }
+            pending = true;
+            pend = cs;
+            RHCCQ_PAR_FOR(q, 3) W.center[3 * c + q] = (double)((cs >> (16 - 8 * q)) & 255u);
+            pot = best_pot;
         }
-#pragma unroll
-        for (int t = 0; t < RHCCQ_MB_MAXT; ++t) part[t] = (unsigned long long)acc[t];
-        rhccq_mb_sum_vec(acc, T, s_ll);
-        int best = 0;
-        long long best_pot = acc[0];
-#pragma unroll
-        for (int t = 1; t < RHCCQ_MB_MAXT; ++t) if (t < T && acc[t] < best_pot) { best_pot = acc[t]; best = t; }
-        uint32_t cs = xc[0];
-#pragma unroll
-        for (int t = 1; t < RHCCQ_MB_MAXT; ++t) if (t == best) cs = xc[t];
-        chunk_sum = part[0];                                        // sum over the chunk of min(closest, distance to the new centre)
-#pragma unroll
-        for (int t = 1; t < RHCCQ_MB_MAXT; ++t) if (t == best) chunk_sum = part[t];
-        pending = true;
-        pend = cs;
-        RHCCQ_PAR_FOR(q, 3) W.center[3 * c + q] = (double)((cs >> (16 - 8 * q)) & 255u);
-        pot = best_pot;
-    }
+    };
+    if ((unsigned long long)ns * 195075ull < 4294967296ull) seed_loop((uint32_t)0);
+    else seed_loop((unsigned long long)0);
     __syncthreads();
     RHCCQ_MBP(1);                                                   // seeding
             RHCCQ_PAR_FOR(q, k) W.counts[q] = 0.0;
@@ -467,6 +492,8 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
     double* cen_new = W.center_new;
     const int pts_per_cta = (batch + csize - 1) / csize;
     const int k_per_cta = (k + csize - 1) / csize;
+    int e_lo, e_hi;
+    rhccq_sk_edge_rows(k, e_lo, e_hi);
     for (long long step = 0; step < n_steps; ++step) {
         bool reassign = false;
         if (rank == 0) {
@@ -540,23 +567,26 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                 }
                 const bool open_pt = !(fs - fb > 0.5f);             // (the same in the four lanes of a point)
                 double bd = 1.0e300;
-                int bq = 0x7fffffff;
+                int bq = open_pt ? 0x7fffffff : fq;
                 if (open_pt) {
+                    // scikit-learn's own evaluation (_labels_inertia -> the chunked E step): |c|^2 - 2 x.c through
+                    // dgemm, first minimum; the sample's place in its chunk of 256 selects the dgemm kernel
+                    const rhccq_sk_pt pt = {x0, x1, x2};
+                    const bool es = rhccq_sk_edge_sample(have ? i : p_lo, batch);
                     for (int q = part; q < k; q += tpp) {
-                        const double d = rhccq_mb_dist(x0, x1, x2, cen + 3 * q);
+                        const double* cq = cen + 3 * q;
+                        const double d = rhccq_sk_score(pt, cq, rhccq_sk_norm3(cq[0], cq[1], cq[2]), es && q >= e_lo && q < e_hi);
                         if (d < bd) { bd = d; bq = q; }
                     }
-                } else if (part == 0) {
-                    bq = fq;
-                    bd = rhccq_mb_dist(x0, x1, x2, cen + 3 * fq);
                 }
-                __syncwarp();
+                __syncwarp();                                       // (every lane: the four lanes of a closed point agree already)
                 for (int m = 1; m < tpp; m <<= 1) {
                     const double od = rhccq_shfl_xor(bd, m);
                     const int oq = rhccq_shfl_xor(bq, m);
                     if (od < bd || (od == bd && oq < bq)) { bd = od; bq = oq; }
                 }
-                if (have && part == 0) { lab_g[i] = bq; own_g[i] = bd; }
+                // the distance that enters the batch inertia is the direct one (_inertia_dense)
+                if (have && part == 0) { lab_g[i] = bq; own_g[i] = rhccq_mb_dist(x0, x1, x2, cen + 3 * bq); }
             }
         }
         RHCCQ_MBP(5);                                               // labels of the batch
@@ -772,9 +802,10 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         { double* t = cen; cen = cen_new; cen_new = t; }
         if (hdr[4]) break;                                          // cluster-uniform
     }
+    RHCCQ_MBP_END();
     if (rank == 0) {
         RHCCQ_PAR_FOR(q, 3 * k) centers_out[q] = cen[q];
-        if (threadIdx.x == 0) n_clusters[p] = k;
+        if (threadIdx.x == 0) { n_clusters[p] = k; centers_out[3 * k] = (double)n; }   // (k <= kmax - 1: the slot exists)
     }
 }
 
@@ -789,7 +820,7 @@ extern "C" int rhccq_mb_prof_read(unsigned long long* host_out, int reset) {
 __global__ void __launch_bounds__(RHCCQ_MB_THREADS)
 rhccq_k_palette_minibatch(rhccq_palette_batch B, const double* __restrict__ quality, int* __restrict__ n_clusters,
                           int max_rows, unsigned char* gws, size_t gws_stride, double* __restrict__ centers,
-                          size_t centers_stride, int* __restrict__ todo, int* __restrict__ claim) {
+                          size_t centers_stride, int* __restrict__ todo, int* __restrict__ claim, int* __restrict__ labels) {
     int rank, csize, cid;
     rhccq_cluster_rank(&rank, &csize, &cid);
     while (true) {
@@ -804,12 +835,13 @@ rhccq_k_palette_minibatch(rhccq_palette_batch B, const double* __restrict__ qual
         rhccq_cluster_sync();
         if (p >= B.n_problems) return;
         rhccq_minibatch_problem(B, p, quality, n_clusters, max_rows, gws + (size_t)cid * gws_stride,
-                                centers + (size_t)p * centers_stride, rank, csize);
+                                centers + (size_t)p * centers_stride, labels, rank, csize);
         rhccq_cluster_sync();
     }
 }
 
-// labels of all non-black rows: nearest of the palette's k centres, first minimum
+// labels of all non-black rows: scikit-learn's final _labels_inertia over the whole palette (chunked E step as in
+// the batches: |c|^2 - 2 x.c, first minimum, dgemm kernel by the row's place in its chunk)
 __global__ void __launch_bounds__(RHCCQ_PIXEL_THREADS)
 rhccq_k_minibatch_assign(rhccq_palette_batch B, const int* __restrict__ n_clusters_before, const int* __restrict__ n_clusters,
                          const double* __restrict__ centers, size_t centers_stride, int* __restrict__ labels, int chunks) {
@@ -820,15 +852,23 @@ rhccq_k_minibatch_assign(rhccq_palette_batch B, const int* __restrict__ n_cluste
         const uint32_t* keys = B.pal_keys + B.pal_off[p];
         int* lab = labels + B.pal_off[p];
         const double* C = centers + (size_t)p * centers_stride;
+        const int n_rows = (int)C[3 * k];                           // non-black rows
+        int e_lo, e_hi;
+        rhccq_sk_edge_rows(k, e_lo, e_hi);
         const int per = (n + chunks - 1) / chunks;
         const int lo = ch * per, hi = lo + per < n ? lo + per : n;
         for (int i = lo + (int)threadIdx.x; i < hi; i += (int)blockDim.x) {
             const uint32_t c = keys[i];
             if (c == 0u) { lab[i] = -2; continue; }
-            const double x0 = (double)rhccq_key_r(c), x1 = (double)rhccq_key_g(c), x2 = (double)rhccq_key_b(c);
-            double bd = rhccq_mb_dist(x0, x1, x2, C);
+            const rhccq_sk_pt pt = {(double)rhccq_key_r(c), (double)rhccq_key_g(c), (double)rhccq_key_b(c)};
+            const bool es = rhccq_sk_edge_sample(lab[i], n_rows);   // (the slot holds the row's position, see above)
+            double bd = 1.0e300;
             int bi = 0;
-            for (int q = 1; q < k; ++q) { const double d = rhccq_mb_dist(x0, x1, x2, C + 3 * q); if (d < bd) { bd = d; bi = q; } }
+            for (int q = 0; q < k; ++q) {
+                const double* cq = C + 3 * q;
+                const double d = rhccq_sk_score(pt, cq, rhccq_sk_norm3(cq[0], cq[1], cq[2]), es && q >= e_lo && q < e_hi);
+                if (d < bd) { bd = d; bi = q; }
+            }
             lab[i] = bi;
         }
     }
@@ -862,7 +902,7 @@ int rhccq_launch_palette_minibatch(const rhccq_palette_batch& B, const double* q
     memset(todo, 0, 16);
     memcpy(before, n_clusters, (size_t)B.n_problems * 4);
     RHCCQ_LAUNCH(rhccq_k_palette_minibatch, workers, RHCCQ_MB_THREADS, 0, (cudaStream_t)stream, B, quality, n_clusters, max_rows,
-                 slices, slice, centers, cstride, todo, claim);
+                 slices, slice, centers, cstride, todo, claim, labels);
 #else
     cudaMemsetAsync(todo, 0, 16, (cudaStream_t)stream);
     cudaMemcpyAsync(before, n_clusters, (size_t)B.n_problems * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
@@ -877,7 +917,7 @@ int rhccq_launch_palette_minibatch(const rhccq_palette_batch& B, const double* q
         attr[0].val.clusterDim.x = RHCCQ_MB_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         cudaError_t e = cudaLaunchKernelEx(&cfg, rhccq_k_palette_minibatch, B, quality, n_clusters, max_rows, slices, slice,
-                                           centers, cstride, todo, claim);
+                                           centers, cstride, todo, claim, labels);
         if (e != cudaSuccess) { rhccq_set_error("rhccq_palette_minibatch: cluster launch failed: %s", cudaGetErrorString(e)); return -1; }
     }
 #endif

@@ -38,3 +38,4 @@ tot = sum(buf[i] for i in range(11)) or 1
 for i, nm in enumerate(names):
     print(f"{nm:50s} {100.0 * buf[i] / tot:5.1f} %   {buf[i] / 1.965e6:8.2f} ms summed over the clusters")
 print("steps", buf[11], "of which with a reassignment", buf[14], "; sum of n", buf[12], "sum of k", buf[13])
+print(f"longest palette: {buf[15] / 1.965e6:.2f} ms (the kernel lasts as long as its longest palette)")
