@@ -492,6 +492,21 @@ def test_minibatch_branch_equals_restated_oracle(backend, n, q, black):
     assert np.array_equal(got["indices"], want["indices"])
 
 
+def test_minibatch_branch_equals_reference_output(backend):
+    """The reference itself (tests/golden/make_golden.py minibatch: its cluster_palette_colors_parallel with
+    scikit-learn's MiniBatchKMeans and KMeans underneath) on a 10 500-colour palette at two qualities: the
+    kernels reproduce its palette, order included, and its indices — nothing injected."""
+    g = golden("minibatch_palette.npz")
+    pal = g["in_palette"]
+    for c in range(int(g["n_cases"])):
+        q = int(g[f"q{c}"])
+        comp = {"palette": pal, "indices": np.arange(len(pal)), "shape": (1, len(pal)), "top_left": (0, 0)}
+        eps, _, m = O.compute_clustering_params(len(pal), q, "lab")
+        got = C.cluster_palette_colors_parallel(q, comp, eps=eps, min_samples=1, max_colors_per_cluster=m, as_arrays=True)
+        assert np.array_equal(got["palette"], g[f"out_palette{c}"]), c
+        assert np.array_equal(got["indices"], g[f"out_indices{c}"]), c
+
+
 def test_pipeline_with_large_segments_minibatch_in_stage1(backend):
     """Segments of more than 10 000 colours (natural 128 px tiles hit this): stage 1 itself takes the
     MiniBatchKMeans branch, and the index plane needs no more than 16 bits."""
