@@ -21,6 +21,7 @@
 #include "rhccq_kernels.h"
 
 #define RHCCQ_EMPTY_KEY 0xFFFFFFFFu
+#define RHCCQ_MERGE_COUNT_CAP 1024     // colours one component may own for the counting rank (else: sort)
 
 __host__ __device__ static inline size_t rhccq_pow2_sz(size_t v) { size_t p = 1; while (p < v) p <<= 1; return p; }
 
@@ -30,9 +31,9 @@ __host__ __device__ static inline size_t rhccq_merge_hcap(int max_entries) {
 
 size_t rhccq_merge_level_ws_bytes(int max_entries, int max_comps) {
     const size_t hcap = rhccq_merge_hcap(max_entries);
-    return rhccq_carve_bytes(hcap, 4) * 2 + rhccq_carve_bytes(hcap, 8)
+    return rhccq_carve_bytes(hcap, 4) * 2 + rhccq_carve_bytes(hcap, 8) + rhccq_carve_bytes(hcap, 4)
            + rhccq_carve_bytes(rhccq_pow2_sz(max_entries > 1 ? max_entries : 1), 8)
-           + rhccq_carve_bytes((size_t)max_comps + 1, 4);
+           + rhccq_carve_bytes((size_t)max_comps + 1, 4) * 2;
 }
 
 __device__ __forceinline__ int rhccq_lower_bound_u64(const unsigned long long* a, int n, unsigned long long key) {
@@ -61,8 +62,10 @@ __device__ void rhccq_merge_level_group(const rhccq_merge_args& M, int g, int ma
     uint32_t* hcol = cv.take<uint32_t>(hcap);
     uint32_t* hpos = cv.take<uint32_t>(hcap);
     unsigned long long* hkey = cv.take<unsigned long long>(hcap);
+    uint32_t* hrank = cv.take<uint32_t>(hcap);                       // slot -> rank of its colour
     unsigned long long* sortbuf = cv.take<unsigned long long>(rhccq_pow2_sz(max_entries > 1 ? max_entries : 1));
     int* prank = cv.take<int>((size_t)max_comps + 1);
+    int* ownc = cv.take<int>((size_t)max_comps + 1);
 
     // components that hold at least one entry take part (regions.py:18-29 drops empty ones)
     if (threadIdx.x == 0) s_single = -1;
@@ -119,20 +122,92 @@ __device__ void rhccq_merge_level_group(const rhccq_merge_args& M, int g, int ma
         }
     }
     __syncthreads();
-    for (size_t s = threadIdx.x; s < hcap; s += blockDim.x)
-        if (hcol[s] != RHCCQ_EMPTY_KEY) sortbuf[atomicAdd(&s_cnt, 1)] = hkey[s];
-    __syncthreads();
-    const int U = s_cnt;
-    const int np2 = rhccq_next_pow2(U > 1 ? U : 1);
-    for (int j = U + (int)threadIdx.x; j < np2; j += (int)blockDim.x) sortbuf[j] = ~0ull;
-    __syncthreads();
-    rhccq_block_bitonic_sort<unsigned long long>(sortbuf, np2);
-    for (size_t s = threadIdx.x; s < hcap; s += blockDim.x) {
-        if (hcol[s] == RHCCQ_EMPTY_KEY) continue;
-        const int rank = rhccq_lower_bound_u64(sortbuf, U, hkey[s]);
-        M.color_out[out0 + 1 + rank] = hcol[s];
-        M.fpos_out[out0 + 1 + rank] = hpos[s];
-        hkey[s] = (unsigned long long)rank;
+    // Rank of every colour's okey among the group's.  The okeys order first by component (last listed first), then by
+    // raster position inside it, and every colour has one owner entry — the one whose (component, position) is the
+    // colour's okey.  So: owners per component (one warp per component), a scan over the components in paint order,
+    // and the rank of an owner among its component's owners by counting.  A component that owns more than
+    // RHCCQ_MERGE_COUNT_CAP colours makes the group take the general way instead: sort all okeys.
+    int over = 0;
+    for (int i = RHCCQ_WARP; i < ncomp; i += RHCCQ_NWARPS) {
+        const int st = M.comp_start[c0 + i], cn = M.comp_cnt[c0 + i];
+        const unsigned long long hi = (unsigned long long)(n_present - 1 - prank[i]) << 32;
+        int owned = 0;
+        for (int j0 = 0; j0 < cn; j0 += RHCCQ_WARP_SIZE) {
+            const int j = j0 + RHCCQ_LANE;
+            bool owner = false;
+            if (j < cn) {
+                const uint32_t col = M.color_in[st + j], fp = M.fpos_in[st + j];
+                if (col != 0u && fp != 0xFFFFFFFFu) {
+                    uint32_t h = (col * 2654435761u) & hmask;
+                    while (hcol[h] != col) h = (h + 1) & hmask;
+                    owner = hkey[h] == (hi | fp);
+                }
+            }
+            owned += __popc(rhccq_ballot(owner));
+        }
+        if (RHCCQ_LANE == 0) ownc[i] = owned;
+        over |= owned > RHCCQ_MERGE_COUNT_CAP;
+    }
+    over = rhccq_block_or(over, s_scr);
+    int U;
+    if (!over) {
+        U = rhccq_block_excl_scan_array<int>(ownc, ncomp, s_scr);    // ownc[i] <- owners in the components listed before i
+        if (threadIdx.x == 0) ownc[ncomp] = U;
+        __syncthreads();
+        for (int i = RHCCQ_WARP; i < ncomp; i += RHCCQ_NWARPS) {
+            const int st = M.comp_start[c0 + i], cn = M.comp_cnt[c0 + i];
+            const int owned = ownc[i + 1] - ownc[i];
+            if (owned == 0) continue;
+            const int base = U - ownc[i + 1];                         // owners in the components painted before this one
+            const unsigned long long hi = (unsigned long long)(n_present - 1 - prank[i]) << 32;
+            unsigned long long* seg = sortbuf + base;                 // (position << 32) | table slot of this component's owners
+            int filled = 0;
+            for (int j0 = 0; j0 < cn; j0 += RHCCQ_WARP_SIZE) {
+                const int j = j0 + RHCCQ_LANE;
+                bool owner = false;
+                uint32_t h = 0, fp = 0;
+                if (j < cn) {
+                    const uint32_t col = M.color_in[st + j];
+                    fp = M.fpos_in[st + j];
+                    if (col != 0u && fp != 0xFFFFFFFFu) {
+                        h = (col * 2654435761u) & hmask;
+                        while (hcol[h] != col) h = (h + 1) & hmask;
+                        owner = hkey[h] == (hi | fp);
+                    }
+                }
+                const unsigned m = rhccq_ballot(owner);
+                if (owner) seg[filled + __popc(m & rhccq_lanemask_lt())] = ((unsigned long long)fp << 32) | h;
+                filled += __popc(m);
+            }
+#ifndef RHCCQ_HOST_EMU
+            __syncwarp();
+#endif
+            for (int e = RHCCQ_LANE; e < owned; e += RHCCQ_WARP_SIZE) {
+                const unsigned long long mine = seg[e];
+                int rank = base;
+                for (int o = 0; o < owned; ++o) rank += seg[o] < mine ? 1 : 0;      // (positions of one component are distinct)
+                const uint32_t h = (uint32_t)mine;
+                M.color_out[out0 + 1 + rank] = hcol[h];
+                M.fpos_out[out0 + 1 + rank] = hpos[h];
+                hrank[h] = (uint32_t)rank;
+            }
+        }
+    } else {
+        for (size_t s = threadIdx.x; s < hcap; s += blockDim.x)
+            if (hcol[s] != RHCCQ_EMPTY_KEY) sortbuf[atomicAdd(&s_cnt, 1)] = hkey[s];
+        __syncthreads();
+        U = s_cnt;
+        const int np2 = rhccq_next_pow2(U > 1 ? U : 1);
+        for (int j = U + (int)threadIdx.x; j < np2; j += (int)blockDim.x) sortbuf[j] = ~0ull;
+        __syncthreads();
+        rhccq_block_bitonic_sort<unsigned long long>(sortbuf, np2);
+        for (size_t s = threadIdx.x; s < hcap; s += blockDim.x) {
+            if (hcol[s] == RHCCQ_EMPTY_KEY) continue;
+            const int rank = rhccq_lower_bound_u64(sortbuf, U, hkey[s]);
+            M.color_out[out0 + 1 + rank] = hcol[s];
+            M.fpos_out[out0 + 1 + rank] = hpos[s];
+            hrank[s] = (uint32_t)rank;
+        }
     }
     if (threadIdx.x == 0) {
         M.color_out[out0] = 0u;                                    // merging.py:42-44
@@ -148,7 +223,7 @@ __device__ void rhccq_merge_level_group(const rhccq_merge_args& M, int g, int ma
             if (col != 0u && fp != 0xFFFFFFFFu) {
                 uint32_t h = (col * 2654435761u) & hmask;
                 while (hcol[h] != col) h = (h + 1) & hmask;
-                out = 1 + (int)hkey[h];
+                out = 1 + (int)hrank[h];
             }
             M.map[st + j] = out;
         }

@@ -17,16 +17,22 @@
 // Optional phase timers (cycles of rank 0 / thread 0 of every cluster, summed into rhccq_mb_prof[16]); compiled in
 // with -DRHCCQ_MB_PROFILE by tools/minibatch_phases.py only.
 #if defined(RHCCQ_MB_PROFILE) && !defined(RHCCQ_HOST_EMU)
-__device__ unsigned long long rhccq_mb_prof[16];
+__device__ unsigned long long rhccq_mb_prof[40];
 #define RHCCQ_MBP_T0() long long mbp_t_ = clock64(); const long long mbp_start_ = mbp_t_
 #define RHCCQ_MBP_END() do { if (rank == 0 && threadIdx.x == 0) atomicMax(&rhccq_mb_prof[15], (unsigned long long)(clock64() - mbp_start_)); } while (0)
 #define RHCCQ_MBP(slot) do { if (rank == 0 && threadIdx.x == 0) { const long long n_ = clock64(); atomicAdd(&rhccq_mb_prof[slot], (unsigned long long)(n_ - mbp_t_)); mbp_t_ = n_; } } while (0)
 #define RHCCQ_MBP_ADD(slot, v) do { if (rank == 0 && threadIdx.x == 0) atomicAdd(&rhccq_mb_prof[slot], (unsigned long long)(v)); } while (0)
+#define RHCCQ_MBP_ANY(slot, v) atomicAdd(&rhccq_mb_prof[slot], (unsigned long long)(v))
+#define RHCCQ_MBP_RANK_T0() const long long mbr_t_ = clock64()
+#define RHCCQ_MBP_RANK(slot0) do { if (threadIdx.x == 0) atomicAdd(&rhccq_mb_prof[(slot0) + rank], (unsigned long long)(clock64() - mbr_t_)); } while (0)
 #else
 #define RHCCQ_MBP_T0() do {} while (0)
 #define RHCCQ_MBP_END() do {} while (0)
 #define RHCCQ_MBP(slot) do {} while (0)
 #define RHCCQ_MBP_ADD(slot, v) do {} while (0)
+#define RHCCQ_MBP_ANY(slot, v) do {} while (0)
+#define RHCCQ_MBP_RANK_T0() do {} while (0)
+#define RHCCQ_MBP_RANK(slot0) do {} while (0)
 #endif
 #define RHCCQ_MB_THREADS 512
 #define RHCCQ_MB_BATCH 1000
@@ -532,6 +538,7 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         // runner-up is more than 0.5 behind keeps the float32 winner; the others — ties of integer colours among
         // them — take the float64 loop, whose first minimum by (distance, index) is the result either way.
         {
+            RHCCQ_MBP_RANK_T0();
             float* cf = W.cf + (size_t)rank * 4 * k;
             RHCCQ_PAR_FOR(q, k) {
                 const double c0 = cen[3 * q] - 128.0, c1 = cen[3 * q + 1] - 128.0, c2 = cen[3 * q + 2] - 128.0;
@@ -573,11 +580,28 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                     // dgemm, first minimum; the sample's place in its chunk of 256 selects the dgemm kernel
                     const rhccq_sk_pt pt = {x0, x1, x2};
                     const bool es = rhccq_sk_edge_sample(have ? i : p_lo, batch);
-                    for (int q = part; q < k; q += tpp) {
-                        const double* cq = cen + 3 * q;
-                        const double d = rhccq_sk_score(pt, cq, rhccq_sk_norm3(cq[0], cq[1], cq[2]), es && q >= e_lo && q < e_hi);
-                        if (d < bd) { bd = d; bq = q; }
+                    // ... of the centres whose float32 score is within the margin of the best one: any other centre's
+                    // float64 score is above the best centre's by more than 0.5 - 2 * 0.13
+                    const float lim = fb + 0.5f;
+                    for (int q0 = part; q0 < k; q0 += 8 * tpp) {     // eight scores at a time: the loads are in flight together
+                        float dd[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int q = q0 + u * tpp;
+                            const float4 c4q = c4[q < k ? q : k - 1];
+                            dd[u] = q < k ? fmaf(f0, c4q.x, fmaf(f1, c4q.y, fmaf(f2, c4q.z, c4q.w))) : 3.0e38f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (dd[u] > lim) continue;
+                            const int q = q0 + u * tpp;
+                            const double* cq = cen + 3 * q;
+                            const double d = rhccq_sk_score(pt, cq, rhccq_sk_norm3(cq[0], cq[1], cq[2]), es && q >= e_lo && q < e_hi);
+                            if (d < bd) { bd = d; bq = q; }
+                            RHCCQ_MBP_ANY(17, 1);
+                        }
                     }
+                    if (part == 0 && have) RHCCQ_MBP_ANY(16, 1);
                 }
                 __syncwarp();                                       // (every lane: the four lanes of a closed point agree already)
                 for (int m = 1; m < tpp; m <<= 1) {
@@ -588,6 +612,8 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                 // the distance that enters the batch inertia is the direct one (_inertia_dense)
                 if (have && part == 0) { lab_g[i] = bq; own_g[i] = rhccq_mb_dist(x0, x1, x2, cen + 3 * bq); }
             }
+            __syncthreads();
+            RHCCQ_MBP_RANK(18);
         }
         RHCCQ_MBP(5);                                               // labels of the batch
         rhccq_cluster_sync();
@@ -811,8 +837,8 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
 
 #if defined(RHCCQ_MB_PROFILE) && !defined(RHCCQ_HOST_EMU)
 extern "C" int rhccq_mb_prof_read(unsigned long long* host_out, int reset) {
-    if (reset) { unsigned long long z[16] = {0}; return (int)cudaMemcpyToSymbol(rhccq_mb_prof, z, sizeof z); }
-    return (int)cudaMemcpyFromSymbol(host_out, rhccq_mb_prof, 16 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[40] = {0}; return (int)cudaMemcpyToSymbol(rhccq_mb_prof, z, sizeof z); }
+    return (int)cudaMemcpyFromSymbol(host_out, rhccq_mb_prof, 40 * sizeof(unsigned long long));
 }
 #endif
 

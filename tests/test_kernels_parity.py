@@ -250,6 +250,21 @@ def test_merge_random_overlaps(backend):
         assert np.array_equal(got["indices"], want["indices"]), trial
 
 
+def test_merge_large_component_palettes(backend):
+    """Components that own thousands of colours each (the rank of a colour is then found by sorting all colours
+    of the group rather than by counting inside its component), next to many small ones."""
+    rng = np.random.default_rng(5)
+    comps = []
+    for h, w, ncol in ((60, 70, 3000), (50, 64, 2500), (8, 8, 40), (70, 60, 1500), (5, 9, 20)):
+        pal = np.unique(rng.integers(0, 32, size=(ncol, 3)).astype(np.uint8) * 8, axis=0)
+        comps.append({"top_left": (int(rng.integers(0, 20)), int(rng.integers(0, 20))), "shape": (h, w),
+                      "palette": pal, "indices": rng.integers(0, len(pal), size=h * w)})
+    want = O.merge_region_components_simple(comps, (0, 0, 96, 96))[0]
+    got = C.merge_region_components_simple(comps, (0, 0, 96, 96), as_arrays=True)[0]
+    assert np.array_equal(got["palette"], want["palette"])
+    assert np.array_equal(got["indices"], want["indices"])
+
+
 # --------------------------------------------------------------------------- a6 / a7: the three stages
 def _encode_device(be, img, roi, non, qualities=(20, 10)):
     H, W, _ = img.shape

@@ -28,7 +28,7 @@ imgs = torch.from_numpy(synth(H, W, 1234)[None]).cuda()
 labs = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(lab, (2, 1, H, W)))).cuda()
 pipeline.encode_batch(be, imgs, labs, tab); torch.cuda.synchronize()
 be.cdll.rhccq_mb_prof_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
-buf = (ctypes.c_ulonglong * 16)()
+buf = (ctypes.c_ulonglong * 40)()
 be.cdll.rhccq_mb_prof_read(buf, 1)
 pipeline.encode_batch(be, imgs, labs, tab); torch.cuda.synchronize()
 be.cdll.rhccq_mb_prof_read(buf, 0)
@@ -39,3 +39,5 @@ for i, nm in enumerate(names):
     print(f"{nm:50s} {100.0 * buf[i] / tot:5.1f} %   {buf[i] / 1.965e6:8.2f} ms summed over the clusters")
 print("steps", buf[11], "of which with a reassignment", buf[14], "; sum of n", buf[12], "sum of k", buf[13])
 print(f"longest palette: {buf[15] / 1.965e6:.2f} ms (the kernel lasts as long as its longest palette)")
+print(f"batch points that needed the float64 level: {buf[16]} of {buf[11] * 1000} ; float64 scores evaluated for them: {buf[17]}")
+print("batch labels per rank of the cluster, ms summed:", [round(buf[18 + r] / 1.965e6, 2) for r in range(8)])
