@@ -1344,6 +1344,95 @@ rhccq_k_lt_union_rows(const uint32_t* __restrict__ packed, rhccq_lt_args A, int*
     }
 }
 
+// Border attachment for small radii (R <= 4), in the sliding-window form of the count pass: a thread owns 8 adjacent
+// pixels; the tile holds the colours re-encoded as in the union pass (core: top byte 0x00, everything else 0xFF, so
+// one byte-wise distance covers "is a core pixel" as well) and, beside it, the root labels of the same pixels.  A
+// non-core pixel takes the smallest root label among the core pixels within eps (what rhccq_k_lt_sweep<2> computes
+// over a compacted list with one global load per qualifying neighbour).
+template <int RT>
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_lt_attach_rows(const uint32_t* __restrict__ packed, rhccq_lt_args A, int* __restrict__ rootlab) {
+    RHCCQ_DYN_SMEM(dyn);
+    constexpr int TH = RHCCQ_LTT_TH, TW = RHCCQ_LTT_TW, PAD = RHCCQ_LTT_PAD, THH = TH + 2 * RT, NTASK = TH * (RHCCQ_LT_W / 8);
+    uint32_t* tile = reinterpret_cast<uint32_t*>(dyn);                  // [THH][TW]
+    int* rl = reinterpret_cast<int*>(tile + THH * TW);                  // [THH][TW] root labels
+    const int thr = A.thr;
+    const int tiles_x = (A.W + RHCCQ_LT_W - 1) / RHCCQ_LT_W, tiles_y = (A.H + TH - 1) / TH;
+    for (int tI = blockIdx.x; tI < tiles_x * tiles_y; tI += gridDim.x) {
+        const int ty0 = (tI / tiles_x) * TH, tx0 = (tI % tiles_x) * RHCCQ_LT_W;
+        RHCCQ_PAR_FOR(t, THH * (TW / 4)) {
+            const int r = t / (TW / 4), q = t % (TW / 4);
+            const int y = ty0 + r - RT, x = tx0 + 4 * q - PAD;
+            uint32_t w[4];
+            int l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t v = RHCCQ_LT_INVALID;
+                int lab = 0x7fffffff;
+                if (y >= 0 && y < A.H && x + j >= 0 && x + j < A.W) {
+                    const size_t id = (size_t)y * A.W + x + j;
+                    const uint32_t pk = packed[id];
+                    const bool is_core = (pk >> 24) == 1u;
+                    v = is_core ? (pk & 0x00ffffffu) : (0xFE000000u | (pk & 0x00ffffffu));     // 0xFE: a pixel of the image, not core
+                    if (is_core) lab = rootlab[id];
+                }
+                w[j] = v; l[j] = lab;
+            }
+            const int i0 = r * TW + 4 * q;
+            *reinterpret_cast<uint4*>(tile + i0) = uint4{w[0], w[1], w[2], w[3]};
+            *reinterpret_cast<uint4*>(rl + i0) = uint4{(unsigned)l[0], (unsigned)l[1], (unsigned)l[2], (unsigned)l[3]};
+        }
+        __syncthreads();
+        RHCCQ_PAR_FOR(task, NTASK) {
+            const int ly = task / (RHCCQ_LT_W / 8), lx0 = (task % (RHCCQ_LT_W / 8)) * 8;
+            const int y = ty0 + ly, x0 = tx0 + lx0;
+            uint32_t c[8];
+            {
+                const uint4* ctr = reinterpret_cast<const uint4*>(tile + (ly + RT) * TW + lx0 + PAD);
+                const uint4 a = ctr[0], b = ctr[1];
+                c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+            }
+            unsigned want = 0u;                                         // the non-core pixels of the image among my eight
+#pragma unroll
+            for (int u = 0; u < 8; ++u) want |= ((c[u] >> 24) == 0xFEu ? 1u : 0u) << u;
+            if (!want || y >= A.H) continue;
+            int best[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { best[u] = 0x7fffffff; c[u] &= 0x00ffffffu; }   // as a core pixel's word: top byte 0
+#pragma unroll
+            for (int dy = -RT; dy <= RT; ++dy) {
+                if (dy * dy > thr) continue;                            // (block-uniform)
+                uint32_t win[16];
+                int wl[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(tile + (ly + RT + dy) * TW + lx0 + 4 * j);
+                    win[4 * j] = v.x; win[4 * j + 1] = v.y; win[4 * j + 2] = v.z; win[4 * j + 3] = v.w;
+                    const uint4 r = *reinterpret_cast<const uint4*>(rl + (ly + RT + dy) * TW + lx0 + 4 * j);
+                    wl[4 * j] = (int)r.x; wl[4 * j + 1] = (int)r.y; wl[4 * j + 2] = (int)r.z; wl[4 * j + 3] = (int)r.w;
+                }
+#pragma unroll
+                for (int dx = -RT; dx <= RT; ++dx) {
+                    if (dy == 0 && dx == 0) continue;
+                    const int budget = thr - dy * dy - dx * dx;
+                    if (budget < 0) continue;
+                    const unsigned start = (unsigned)(-(budget + 1));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {                       // a neighbour that is not core is at least 254^2 away
+                        const unsigned d = __vabsdiffu4(c[u], win[u + dx + PAD]);
+                        const int cand = (int)__dp4a(d, d, start) < 0 ? wl[u + dx + PAD] : 0x7fffffff;
+                        best[u] = cand < best[u] ? cand : best[u];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (((want >> u) & 1u) && x0 + u < A.W) rootlab[(size_t)y * A.W + x0 + u] = best[u] == 0x7fffffff ? -1 : best[u];
+        }
+        __syncthreads();
+    }
+}
+
 #ifndef RHCCQ_HOST_EMU
 // One colour channel of a float32 point -> 0..255 without the conversion unit: v + 2^23 holds round(v) in its low
 // mantissa bits. `eor` collects the bits of every "must be exactly zero" difference, `uor` every channel value.
@@ -1438,6 +1527,33 @@ rhccq_k_lt_count_tma(const float* __restrict__ pts, rhccq_lt_args A, int* __rest
     if (tid == 0 && s_bad) *status = 1;
 }
 #endif
+
+// relabel without a scan over every pixel: root flags -> bit mask + word populations; label = rank of the root
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_lt_root_bits(const int* __restrict__ is_root, long long n, uint32_t* __restrict__ bits, int* __restrict__ wcount) {
+#ifdef RHCCQ_HOST_EMU
+    for (long long w = (long long)blockIdx.x; w < (n + 31) / 32; w += (long long)gridDim.x) {
+        uint32_t word = 0u;
+        for (int b = 0; b < 32; ++b) if (32 * w + b < n && is_root[32 * w + b]) word |= 1u << b;
+        bits[w] = word; wcount[w] = __builtin_popcount(word);
+    }
+#else
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {      // (block-uniform trip count)
+        const long long i = i0 + threadIdx.x;
+        const unsigned word = __ballot_sync(0xffffffffu, i < n && is_root[i] != 0);
+        if ((threadIdx.x & 31) == 0 && i < n) { bits[i >> 5] = word; wcount[i >> 5] = __popc(word); }
+    }
+#endif
+}
+__global__ void __launch_bounds__(RHCCQ_PT_THREADS)
+rhccq_k_lt_labels_bits(long long n, const int* __restrict__ rootlab, const uint32_t* __restrict__ bits,
+                       const int* __restrict__ wprefix, int* __restrict__ labels) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = rootlab[i];
+        labels[i] = r < 0 ? -1 : wprefix[r >> 5] + __popc(bits[r >> 5] & ((1u << (r & 31)) - 1u));
+    }
+}
 
 #define RHCCQ_LT_H 16         // tile height of the count and attachment passes
 #define RHCCQ_LT_UH 32        // tile height of the union passes: fewer edges cross tile borders
@@ -1594,6 +1710,16 @@ int rhccq_dbscan_lattice_border(int H, int W, double eps, int min_pts, const uin
 
 int rhccq_dbscan_lattice_attach(int H, int W, double eps, int min_pts, void* ws, size_t ws_bytes, void* stream) {
     RHCCQ_LT_PROLOGUE("rhccq_dbscan_lattice_attach")
+    if (A.R >= 1 && A.R <= 4) {                                    // sliding-window form
+        const size_t rsmem = (size_t)RHCCQ_LTT_TW * (RHCCQ_LTT_TH + 2 * A.R) * 8;
+        const long long tiles = (long long)((W + RHCCQ_LT_W - 1) / RHCCQ_LT_W) * ((H + RHCCQ_LTT_TH - 1) / RHCCQ_LTT_TH);
+        const long long cap = (long long)rhccq_sm_count() * 32;
+        const int rgrid = (int)(tiles < cap ? tiles : cap);
+#define RHCCQ_LT_AROWS(RT) RHCCQ_LAUNCH((rhccq_k_lt_attach_rows<RT>), rgrid, RHCCQ_PT_THREADS, rsmem, (cudaStream_t)stream, L.packed, A, L.rootlab)
+        if (A.R == 1) RHCCQ_LT_AROWS(1); else if (A.R == 2) RHCCQ_LT_AROWS(2); else if (A.R == 3) RHCCQ_LT_AROWS(3); else RHCCQ_LT_AROWS(4);
+#undef RHCCQ_LT_AROWS
+        return 0;
+    }
     if (rhccq_smem_optin((const void*)rhccq_k_lt_sweep<2, 2, RHCCQ_LT_H>, smem) != 0) return -1;
     RHCCQ_LAUNCH((rhccq_k_lt_sweep<2, 2, RHCCQ_LT_H>), grid, RHCCQ_PT_THREADS, smem, (cudaStream_t)stream, (const void*)L.packed, A, (int*)nullptr, L.packed,
                  (uint8_t*)nullptr, L.parent, L.rootlab, (int*)nullptr);
@@ -1604,10 +1730,24 @@ int rhccq_dbscan_lattice_relabel(int H, int W, void* ws, size_t ws_bytes, int32_
     if (!ws || ws_bytes < rhccq_dbscan_lattice_workspace_bytes(H, W) || !labels) { rhccq_set_error("rhccq_dbscan_lattice_relabel: bad arguments"); return -1; }
     rhccq_lt_ws L; rhccq_lt_carve(H, W, ws, &L);
     const long long n = (long long)H * W;
-    if (n <= RHCCQ_SCAN_TILE) {
-        RHCCQ_LAUNCH(rhccq_k_scan_small, 1, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, L.is_root, (int)n, (int*)nullptr);
-    } else if (rhccq_scan_i32(L.is_root, n, L.is_root, L.scan, stream) != 0) return -1;
-    RHCCQ_LAUNCH(rhccq_k_pt_labels, rhccq_pt_blocks(n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, (int)n, L.rootlab, L.is_root, labels);
+    // The rank of a root among the roots, without a scan over all n flags: the flags as a bit mask (one word per 32
+    // pixels), an exclusive scan over the n / 32 word populations, and rank(r) = prefix[r / 32] + the bits below r
+    // in its word.  Both tables live in the parent array, which is dead once the forest has been flattened.
+    const long long m = (n + 31) / 32;
+    uint32_t* bits = reinterpret_cast<uint32_t*>(L.parent);
+    int* wpre = L.parent + ((m + 63) & ~63LL);
+    if (2 * ((m + 63) & ~63LL) > n) {                              // (tiny images: the plain way)
+        if (n <= RHCCQ_SCAN_TILE) {
+            RHCCQ_LAUNCH(rhccq_k_scan_small, 1, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, L.is_root, (int)n, (int*)nullptr);
+        } else if (rhccq_scan_i32(L.is_root, n, L.is_root, L.scan, stream) != 0) return -1;
+        RHCCQ_LAUNCH(rhccq_k_pt_labels, rhccq_pt_blocks(n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, (int)n, L.rootlab, L.is_root, labels);
+        return 0;
+    }
+    RHCCQ_LAUNCH(rhccq_k_lt_root_bits, rhccq_pt_blocks(n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, L.is_root, n, bits, wpre);
+    if (m <= RHCCQ_SCAN_TILE) {
+        RHCCQ_LAUNCH(rhccq_k_scan_small, 1, RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, wpre, (int)m, (int*)nullptr);
+    } else if (rhccq_scan_i32(wpre, m, wpre, L.scan, stream) != 0) return -1;
+    RHCCQ_LAUNCH(rhccq_k_lt_labels_bits, rhccq_pt_blocks(n), RHCCQ_PT_THREADS, 0, (cudaStream_t)stream, n, L.rootlab, bits, wpre, labels);
     return 0;
 }
 
