@@ -1319,11 +1319,25 @@ rhccq_k_lt_union_rows(const uint32_t* __restrict__ packed, rhccq_lt_args A, int*
                 RHCCQ_PAR_FOR(task, NTASK) {
                     const int ly = task / (RHCCQ_LT_W / 8), lx0 = (task % (RHCCQ_LT_W / 8)) * 8;
                     int* mine = lpar + (ly + RT) * TW + lx0 + PAD;
+                    // (no link is made during this pass: plain loads, the eight walks side by side)
+                    int p0[8], g[8];
+                    {
+                        const uint4 a = *reinterpret_cast<const uint4*>(mine), b = *reinterpret_cast<const uint4*>(mine + 4);
+                        p0[0] = (int)a.x; p0[1] = (int)a.y; p0[2] = (int)a.z; p0[3] = (int)a.w;
+                        p0[4] = (int)b.x; p0[5] = (int)b.y; p0[6] = (int)b.z; p0[7] = (int)b.w;
+                    }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int p0 = ((volatile int*)mine)[u];
-                        const int r = rhccq_pt_find_ro(lpar, p0);
-                        if (r != p0) mine[u] = r;                       // (non-roots only, with an ancestor)
+                    for (int u = 0; u < 8; ++u) g[u] = lpar[p0[u]];
+                    bool deep = false;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) deep |= g[u] != p0[u];
+                    if (deep) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (g[u] == p0[u]) continue;
+                            const int r = rhccq_pt_find_ro(lpar, g[u]);
+                            mine[u] = r;                                // (non-roots only, with an ancestor)
+                        }
                     }
                 }
                 __syncthreads();
