@@ -133,6 +133,10 @@ def test_lattice_rejects_non_lattice_points_and_ragged_sizes(backend):
     for eps, mp in ((1.0, 2), (2.5, 5), (4.0, 30)):
         lab, core = D.dbscan_image(be, torch.from_numpy(img.copy()).to(be.device), eps, mp)
         assert np.array_equal(lab.cpu().numpy().reshape(-1), O.dbscan_labels(pts, eps, mp)), (eps, mp)
+    tiny = synth(5, 9, 3)                                               # fewer pixels than the relabel's bit tables need
+    tiny[:, :4] = tiny[0, 0]
+    lab, _ = D.dbscan_image(be, torch.from_numpy(tiny.copy()).to(be.device), 2.0, 3)
+    assert np.array_equal(lab.cpu().numpy().reshape(-1), O.dbscan_labels(pixel_features(tiny), 2.0, 3))
     bad = pts.copy()
     bad[100, 2] += 0.5
     plan = D.LatticeDbscan(be, 19, 67, 2.0, 3)
