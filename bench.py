@@ -49,7 +49,7 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of the same command
 # (summaries under profiles/): (workload, entry point) -> (bytes, source)
 NCU_TRAFFIC = {
-    ("c2", "rhccq_palette_split"): (832561152 + 379788544, "profiles/r01_split_c2_v6.txt (the stage-1 launch)"),
+    ("c2", "rhccq_palette_split"): (836914176 + 401633792, "profiles/r02_split_c2_v4.txt (the stage-1 launch)"),
     ("c5l", "rhccq_dbscan_lattice_count"): (352404736 + 126816000, "profiles/r01_lattice_count_v3.txt"),
 }
 DBSCAN_BYTES_PER_POINT = 24       # 20 B read + 4 B written, both for the count kernel and the whole
