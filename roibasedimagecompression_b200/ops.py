@@ -123,6 +123,27 @@ def kmeans_labels(be: Backend, colors, k: int):
     return leaf.cpu().numpy().astype(np.int64)
 
 
+def minibatch_labels(be: Backend, colors, quality: float):
+    """``MiniBatchKMeans(n_clusters=ceil(n*quality/100/10), batch_size=1000, random_state=42,
+    n_init='auto').fit_predict(colors.astype(float))`` — the operator the reference calls at
+    clustering.py:207-218 for palettes of 10 000 colours and more — through rhccq_palette_minibatch on one
+    palette.  Returns (int64 labels, k)."""
+    import numpy as np
+    c = np.ascontiguousarray(np.asarray(colors).astype(np.uint8).reshape(-1, 3)).astype(np.int64)
+    n = int(c.shape[0])
+    if (c == 0).all(axis=1).any():
+        raise NotImplementedError("black rows never reach MiniBatchKMeans in the reference (clustering.py:185-192)")
+    keys = _as_dev(be, ((c[:, 0] << 16) | (c[:, 1] << 8) | c[:, 2]).astype(np.int32), I32)
+    off = _as_dev(be, np.zeros(1, np.int32), I32)
+    cnt = _as_dev(be, np.full(1, n, np.int32), I32)
+    lab = be.zeros((n,), I32)
+    ncl = _as_dev(be, np.full(1, -4, np.int32), I32)               # the status rhccq_palette_dbscan gives such a palette
+    q = _as_dev(be, np.full(1, float(quality), np.float64), torch.float64)
+    palette_minibatch(be, keys, off, cnt, q, lab, ncl, max_rows=n)
+    check_counts("rhccq_palette_minibatch", ncl)
+    return lab.cpu().numpy().astype(np.int64), int(ncl.cpu().numpy()[0])
+
+
 def palette_finish(be: Backend, pal_keys, pal_off, pal_cnt, leaf, n_leaves, *, max_rows: int):
     """Truncated means — rhccq_palette_finish.  Returns new_keys (same layout as pal_keys)."""
     P = pal_cnt.numel()

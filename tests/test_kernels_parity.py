@@ -522,6 +522,24 @@ def test_minibatch_branch_equals_reference_output(backend):
         assert np.array_equal(got["indices"], g[f"out_indices{c}"]), c
 
 
+def test_minibatch_kernel_equals_sklearn_labels(backend):
+    """rhccq_palette_minibatch on one palette is MiniBatchKMeans(...).fit_predict: labels recorded from scikit-learn
+    itself (tests/golden/make_minibatch_sklearn.py) on five palettes of 10 000 - 15 739 colours, k = 126 ... 630;
+    the oracle reproduces them too (it is what the other tests of this branch compare the kernel with)."""
+    from oracle import minibatch_restated as MB
+    g = golden("minibatch_sklearn.npz")
+    n_cases = int(g["n_cases"])
+    assert n_cases >= 4
+    for c in range(n_cases if backend.device.type == "cuda" else 2):
+        col, q, k = g[f"colors{c}"], float(g[f"q{c}"]), int(g[f"k{c}"])
+        want = g[f"labels{c}"].astype(np.int64)
+        lab, k_dev = ops.minibatch_labels(backend, col, q)
+        assert k_dev == k
+        assert np.array_equal(lab, want), (c, len(col), k, float((lab == want).mean()))
+        if c < 2:
+            assert np.array_equal(MB.minibatch_labels(col, k), want)
+
+
 def test_pipeline_with_large_segments_minibatch_in_stage1(backend):
     """Segments of more than 10 000 colours (natural 128 px tiles hit this): stage 1 itself takes the
     MiniBatchKMeans branch, and the index plane needs no more than 16 bits."""
