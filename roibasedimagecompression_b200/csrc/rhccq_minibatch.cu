@@ -494,32 +494,45 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
     bool have_ewa = false, have_min = false;
     double ewa = 0.0, ewa_min = 0.0;
     int* bidx = W.sub;                                              // the batch's rows (nb order); the subset is dead
+    int* bidx_next = W.perm;                                        // ... of the step after, when they are drawn ahead
     double* cen = W.center;
     double* cen_new = W.center_new;
+    // With more than one CTA, rank 0 leaves the centre update to the others: while they update, it adds up the batch
+    // inertia, takes the stopping decision and draws the next batch's rows.  A step that may reassign centres (its
+    // random draws come between the two batches', and it edits the centres after the update) keeps the serial order.
+    const bool overlap = csize > 1;
+    const int workers = overlap ? csize - 1 : 1, wrank = overlap ? rank - 1 : 0;      // of the centre update
+    const bool worker = !overlap || rank > 0;
     const int pts_per_cta = (batch + csize - 1) / csize;
-    const int k_per_cta = (k + csize - 1) / csize;
+    const int k_per_cta = (k + workers - 1) / workers;
+    bool have_next = false;                                         // rank 0: `bidx` already holds this step's rows
+    auto draw_batch = [&](int* dst) {
+        // uniform_samples = random_sample(batch): two raw outputs per double, converted in place
+        rhccq_mt_fill_raw(mt, reinterpret_cast<uint32_t*>(s_own), 2 * batch);
+        RHCCQ_PAR_FOR(i, batch) {
+            const uint32_t a = reinterpret_cast<uint32_t*>(s_own)[2 * i] >> 5, b = reinterpret_cast<uint32_t*>(s_own)[2 * i + 1] >> 6;
+            s_own[i] = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
+        }
+        __syncthreads();
+        RHCCQ_PAR_FOR(i, batch) {
+            // searchsorted(cdf / last, u, side='right'): first g with cdf[g] > u. The cdf is that of n equal
+            // weights, so u * n is at most a step or two off; the walk makes the answer exact wherever it starts
+            const double u = s_own[i];
+            int g = (int)(u * (double)n);
+            g = g < 0 ? 0 : (g > n - 1 ? n - 1 : g);
+            while (g > 0 && W.cdf[g - 1] > u) --g;
+            while (g < n && W.cdf[g] <= u) ++g;
+            dst[i] = g < n ? g : n - 1;
+        }
+        __syncthreads();
+    };
     int e_lo, e_hi;
     rhccq_sk_edge_rows(k, e_lo, e_hi);
     for (long long step = 0; step < n_steps; ++step) {
         bool reassign = false;
         if (rank == 0) {
-            // uniform_samples = random_sample(batch): two raw outputs per double, converted in place
-            rhccq_mt_fill_raw(mt, reinterpret_cast<uint32_t*>(s_own), 2 * batch);
-            RHCCQ_PAR_FOR(i, batch) {
-                const uint32_t a = reinterpret_cast<uint32_t*>(s_own)[2 * i] >> 5, b = reinterpret_cast<uint32_t*>(s_own)[2 * i + 1] >> 6;
-                s_own[i] = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
-            }
-            __syncthreads();
-            RHCCQ_PAR_FOR(i, batch) {
-                // searchsorted(cdf / last, u, side='right'): first g with cdf[g] > u. The cdf is that of n equal
-                // weights, so u * n is at most a step or two off; the walk makes the answer exact wherever it starts
-                const double u = s_own[i];
-                int g = (int)(u * (double)n);
-                g = g < 0 ? 0 : (g > n - 1 ? n - 1 : g);
-                while (g > 0 && W.cdf[g - 1] > u) --g;
-                while (g < n && W.cdf[g] <= u) ++g;
-                bidx[i] = g < n ? g : n - 1;
-            }
+            if (!have_next) draw_batch(bidx);
+            have_next = false;
             // _random_reassign (:2039-2054)
             n_since += batch;
             int zero = 0;
@@ -527,10 +540,12 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
             zero = rhccq_block_or(zero, s_i);
             reassign = zero || n_since >= 10 * k;
             if (reassign) n_since = 0;
+            if (threadIdx.x == 0) hdr[5] = reassign ? 1 : 0;
         }
         RHCCQ_MBP(3);                                               // the batch's rows (rank 0)
         rhccq_cluster_sync();
         RHCCQ_MBP(4);
+        const bool serial = !overlap || hdr[5] != 0;                // (cluster-uniform)
         // labels and distances of this CTA's share of the batch: four threads per point, each a quarter of the
         // centres (interleaved).  First level in float32 on this CTA's own table of (-2 (c - 128), |c - 128|^2): the
         // score |c'|^2 - 2 x'.c' with x' = x - 128 differs from the float64 squared distance minus |x'|^2 by < 0.13
@@ -547,7 +562,8 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
             }
             __syncthreads();
             const float4* c4 = reinterpret_cast<const float4*>(cf);
-            const int p_lo = rank * pts_per_cta, p_hi = p_lo + pts_per_cta < batch ? p_lo + pts_per_cta : batch;
+            const int p_lo = rank * pts_per_cta < batch ? rank * pts_per_cta : batch;
+            const int p_hi = p_lo + pts_per_cta < batch ? p_lo + pts_per_cta : batch;
             const int tpp = RHCCQ_WARP_SIZE >= 4 ? 4 : 1;           // threads per point
             for (int i0 = p_lo; i0 < p_hi; i0 += (int)blockDim.x / tpp) {
                 const int i = i0 + (int)threadIdx.x / tpp, part = (int)threadIdx.x % tpp;
@@ -619,10 +635,11 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         rhccq_cluster_sync();
         RHCCQ_MBP(6);
         // centre update of this CTA's share of the clusters, members in batch order (_k_means_minibatch.pyx:68-118)
+        if (worker) {
         RHCCQ_PAR_FOR(i, batch) { s_lab[i] = lab_g[i]; s_col[i] = keys[W.nb[bidx[i]]]; }
         __syncthreads();
         {
-            const int q_lo = rank * k_per_cta, q_hi = q_lo + k_per_cta < k ? q_lo + k_per_cta : k;
+            const int q_lo = wrank * k_per_cta < k ? wrank * k_per_cta : k, q_hi = q_lo + k_per_cta < k ? q_lo + k_per_cta : k;
             const int kpc = q_hi > q_lo ? q_hi - q_lo : 0;
             // the batch grouped by cluster, batch order kept inside a group (the sums below are float64 additions in
             // that order): counts, exclusive scan, then a stable scatter 32 elements at a time (rank among the equal
@@ -689,10 +706,10 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                 }
             }
         }
-        RHCCQ_MBP(7);                                               // centre update
-        rhccq_cluster_sync();
-        RHCCQ_MBP(8);
-        if (rank == 0) {
+        }
+        // inertia of the batch, reassignment of starved centres, stopping rule: rank 0, after the update — or beside it
+        // when the step cannot reassign (nothing it does then touches what the update reads or writes)
+        auto after_update = [&]() {
             RHCCQ_PAR_FOR(i, batch) s_own[i] = own_g[i];
             __syncthreads();
             if (threadIdx.x == 0) {                                 // inertia in batch order
@@ -819,13 +836,21 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
             } while (0);
             __syncthreads();
             if (threadIdx.x == 0) hdr[4] = done;
+        };
+        if (rank == 0 && !serial) { after_update(); draw_batch(bidx_next); have_next = true; }
+        RHCCQ_MBP(7);                                               // centre update
+        rhccq_cluster_sync();
+        RHCCQ_MBP(8);
+        if (serial) {
+            if (rank == 0) after_update();
+            RHCCQ_MBP(9);                                           // inertia, reassignment, convergence (rank 0)
+            rhccq_cluster_sync();
+            RHCCQ_MBP(10);
         }
-        RHCCQ_MBP(9);                                               // inertia, reassignment, convergence (rank 0)
         RHCCQ_MBP_ADD(11, 1);
         if (reassign) RHCCQ_MBP_ADD(14, 1);
-        rhccq_cluster_sync();
-        RHCCQ_MBP(10);
         { double* t = cen; cen = cen_new; cen_new = t; }
+        if (!serial) { int* t = bidx; bidx = bidx_next; bidx_next = t; }     // the rows drawn ahead are the next step's
         if (hdr[4]) break;                                          // cluster-uniform
     }
     RHCCQ_MBP_END();
