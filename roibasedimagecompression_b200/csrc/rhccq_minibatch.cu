@@ -588,42 +588,39 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                     fs = fminf(fminf(fs, os), fmaxf(fb, ob));       // runner-up of the union
                     if (ob < fb || (ob == fb && oq < fq)) { fb = ob; fq = oq; }
                 }
-                const bool open_pt = !(fs - fb > 0.5f);             // (the same in the four lanes of a point)
-                double bd = 1.0e300;
-                int bq = open_pt ? 0x7fffffff : fq;
-                if (open_pt) {
-                    // scikit-learn's own evaluation (_labels_inertia -> the chunked E step): |c|^2 - 2 x.c through
-                    // dgemm, first minimum; the sample's place in its chunk of 256 selects the dgemm kernel
-                    const rhccq_sk_pt pt = {x0, x1, x2};
-                    const bool es = rhccq_sk_edge_sample(have ? i : p_lo, batch);
-                    // ... of the centres whose float32 score is within the margin of the best one: any other centre's
-                    // float64 score is above the best centre's by more than 0.5 - 2 * 0.13
-                    const float lim = fb + 0.5f;
-                    for (int q0 = part; q0 < k; q0 += 8 * tpp) {     // eight scores at a time: the loads are in flight together
-                        float dd[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int q = q0 + u * tpp;
-                            const float4 c4q = c4[q < k ? q : k - 1];
-                            dd[u] = q < k ? fmaf(f0, c4q.x, fmaf(f1, c4q.y, fmaf(f2, c4q.z, c4q.w))) : 3.0e38f;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            if (dd[u] > lim) continue;
-                            const int q = q0 + u * tpp;
-                            const double* cq = cen + 3 * q;
-                            const double d = rhccq_sk_score(pt, cq, rhccq_sk_norm3(cq[0], cq[1], cq[2]), es && q >= e_lo && q < e_hi);
-                            if (d < bd) { bd = d; bq = q; }
-                            RHCCQ_MBP_ANY(17, 1);
-                        }
+                // A point whose float32 runner-up is within 0.5 of its best ("open": 0.6 % of them) is decided by
+                // scikit-learn's own evaluation (_labels_inertia -> the chunked E step): |c|^2 - 2 x.c through dgemm in
+                // float64, first minimum, the sample's place in its chunk of 256 selecting the dgemm kernel — taken
+                // over the centres whose float32 score is within the margin of the best one (any other centre's
+                // float64 score is above the best centre's by more than 0.5 - 2 * 0.13).  The whole warp serves one
+                // open point at a time, a lane every 32nd centre.
+                const bool open_pt = have && !(fs - fb > 0.5f);     // (the same in the four lanes of a point)
+                int bq = fq;
+                unsigned open_mask = rhccq_ballot(open_pt && part == 0);
+                while (open_mask) {                                 // (warp-uniform)
+                    const int src = __ffs((int)open_mask) - 1;
+                    open_mask &= open_mask - 1u;
+                    const float g0 = rhccq_shfl(f0, src), g1 = rhccq_shfl(f1, src), g2 = rhccq_shfl(f2, src);
+                    const float lim = rhccq_shfl(fb, src) + 0.5f;
+                    const rhccq_sk_pt pt = {rhccq_shfl(x0, src), rhccq_shfl(x1, src), rhccq_shfl(x2, src)};
+                    const bool es = rhccq_sk_edge_sample(rhccq_shfl(i, src), batch);
+                    double cd = 1.0e300;
+                    int cq = 0x7fffffff;
+                    for (int q = RHCCQ_LANE; q < k; q += RHCCQ_WARP_SIZE) {
+                        const float4 c4q = c4[q];
+                        if (fmaf(g0, c4q.x, fmaf(g1, c4q.y, fmaf(g2, c4q.z, c4q.w))) > lim) continue;
+                        const double* cq3 = cen + 3 * q;
+                        const double d = rhccq_sk_score(pt, cq3, rhccq_sk_norm3(cq3[0], cq3[1], cq3[2]), es && q >= e_lo && q < e_hi);
+                        if (d < cd) { cd = d; cq = q; }
+                        RHCCQ_MBP_ANY(17, 1);
                     }
-                    if (part == 0 && have) RHCCQ_MBP_ANY(16, 1);
-                }
-                __syncwarp();                                       // (every lane: the four lanes of a closed point agree already)
-                for (int m = 1; m < tpp; m <<= 1) {
-                    const double od = rhccq_shfl_xor(bd, m);
-                    const int oq = rhccq_shfl_xor(bq, m);
-                    if (od < bd || (od == bd && oq < bq)) { bd = od; bq = oq; }
+                    for (int m = RHCCQ_WARP_SIZE >> 1; m > 0; m >>= 1) {
+                        const double od = rhccq_shfl_xor(cd, m);
+                        const int oq = rhccq_shfl_xor(cq, m);
+                        if (od < cd || (od == cd && oq < cq)) { cd = od; cq = oq; }
+                    }
+                    if (RHCCQ_LANE / tpp == src / tpp) bq = cq;     // the lanes of that point
+                    if (RHCCQ_LANE == src) RHCCQ_MBP_ANY(16, 1);
                 }
                 // the distance that enters the batch inertia is the direct one (_inertia_dense)
                 if (have && part == 0) { lab_g[i] = bq; own_g[i] = rhccq_mb_dist(x0, x1, x2, cen + 3 * bq); }

@@ -12,7 +12,7 @@ if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(os.path.j
     nvcc = "/usr/local/cuda/bin/nvcc"
     objdir = os.path.join(B.HERE, "build")
     flags = [f for f in B.NVCC_FLAGS if f != "-shared"]
-    subprocess.run([nvcc] + flags + ["-DRHCCQ_MB_PROFILE", "-c", os.path.join(B.CSRC, "rhccq_minibatch.cu"), "-o",
+    subprocess.run([nvcc] + flags + ["-DRHCCQ_MB_PROFILE"] + [a for a in sys.argv[1:] if a.startswith("-D")] + ["-c", os.path.join(B.CSRC, "rhccq_minibatch.cu"), "-o",
                     os.path.join(objdir, "rhccq_minibatch_prof.o")], check=True)
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in B.SOURCES if s != "rhccq_minibatch.cu"]
     subprocess.run([nvcc, "-shared", "-Xcompiler", "-fPIC"] + objs + [os.path.join(objdir, "rhccq_minibatch_prof.o"), "-o", out], check=True)
