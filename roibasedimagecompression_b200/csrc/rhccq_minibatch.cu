@@ -161,6 +161,15 @@ __device__ __forceinline__ double rhccq_mb_dist(double x0, double x1, double x2,
     return __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
 }
 
+// inclusive running sum along the lanes of a warp
+__device__ __forceinline__ unsigned long long rhccq_mb_warp_incl_scan(unsigned long long v) {
+#ifndef RHCCQ_HOST_EMU
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += o; }
+#endif
+    return v;
+}
 // sum over the lanes of a warp, in every lane
 __device__ __forceinline__ uint32_t rhccq_mb_warp_sum(uint32_t v) {
 #ifdef RHCCQ_HOST_EMU
@@ -370,11 +379,7 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
         bool pending = false;
         uint32_t pend = 0u;
         for (int c = 1; c < k; ++c) {
-            unsigned long long incl = chunk_sum;
-#ifndef RHCCQ_HOST_EMU
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = rhccq_shfl_up(incl, d); if (lane >= d) incl += o; }
-#endif
+            const unsigned long long incl = rhccq_mb_warp_incl_scan(chunk_sum);
             chunk_incl[threadIdx.x] = incl;                         // inclusive inside the warp
             if (lane == RHCCQ_WARP_SIZE - 1) s_wtot[warp] = incl;
             // uniform(size=T) of this step: the raw outputs of RHCCQ_MB_SEED_GROUP steps are drawn together by the
@@ -385,39 +390,42 @@ __device__ __forceinline__ void rhccq_minibatch_problem(const rhccq_palette_batc
                 rhccq_mt_fill_raw(mt, s_rvraw, 2 * T * steps);
             }
             __syncthreads();
-            RHCCQ_PAR_FOR(t, T) {                                   // the T searches side by side
+            for (int t = warp; t < T; t += nw) {                    // the T searches side by side, a warp each
                 const uint32_t a = s_rvraw[2 * (gi * T + t)] >> 5, b = s_rvraw[2 * (gi * T + t) + 1] >> 6;
                 const double u = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 9007199254740992.0);
                 const double rv = __dmul_rn(u, (double)pot);
-                // first j with cum[j] >= rv, cum = running sum of `closest`: the warp whose running total gets there
-                // (totals are non-decreasing: count those below), the chunk inside it, the element inside the chunk
-                unsigned long long base = 0, run = 0;
-                int w = 0;
-                for (int i = 0; i < nw; ++i) {
-                    run += s_wtot[i];
-                    const bool lt = (double)run < rv;
-                    w += lt ? 1 : 0;
-                    base = lt ? run : base;
-                }
+                // first j with cum[j] >= rv, cum = running sum of `closest`, in three warp-wide steps (every running sum
+                // below is non-decreasing along the lanes, so "how many are below rv" is the index looked for):
+                // the warp whose running total gets there, the chunk inside it, the element inside the chunk
+                const unsigned long long run = rhccq_mb_warp_incl_scan(lane < nw ? s_wtot[lane] : 0ull);
+                const int w = __popc(rhccq_ballot(lane < nw && (double)run < rv));
+                unsigned long long base = rhccq_shfl(run, w > 0 ? w - 1 : 0);
+                if (w == 0) base = 0ull;
                 int j = ns;
-                if (w < nw) {
-                    const unsigned long long* wi = chunk_incl + w * RHCCQ_WARP_SIZE;
-                    int lo = 0, hi = RHCCQ_WARP_SIZE;
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((double)(base + wi[mid]) < rv) lo = mid + 1; else hi = mid; }
+                if (w < nw) {                                       // (warp-uniform; always, while pot > 0)
+                    const unsigned long long ci = base + chunk_incl[w * RHCCQ_WARP_SIZE + lane];
+                    const int lo = __popc(rhccq_ballot((double)ci < rv));
                     if (lo < RHCCQ_WARP_SIZE) {
-                        const int ci = w * RHCCQ_WARP_SIZE + lo;
-                        run = base + (lo > 0 ? wi[lo - 1] : 0ull);
-                        const int j_lo = ci * per < ns ? ci * per : ns, j_hi = j_lo + per < ns ? j_lo + per : ns;
-                        for (j = j_lo; j < j_hi; ++j) {
-                            uint32_t o = closest[j];
-                            if (pending) { const uint32_t d = (uint32_t)rhccq_d2(xs[j], pend); o = d < o ? d : o; }
-                            run += o;
-                            if (!((double)run < rv)) break;
+                        unsigned long long run0 = rhccq_shfl(ci, lo > 0 ? lo - 1 : 0);
+                        if (lo == 0) run0 = base;
+                        const int chunk = w * RHCCQ_WARP_SIZE + lo;
+                        const int j_lo = chunk * per < ns ? chunk * per : ns, j_hi = j_lo + per < ns ? j_lo + per : ns;
+                        for (int j0 = j_lo; j0 < j_hi; j0 += RHCCQ_WARP_SIZE) {
+                            const int jj = j0 + lane;
+                            unsigned long long o = 0ull;
+                            if (jj < j_hi) {
+                                uint32_t cl = closest[jj];
+                                if (pending) { const uint32_t d = (uint32_t)rhccq_d2(xs[jj], pend); cl = d < cl ? d : cl; }
+                                o = cl;
+                            }
+                            const unsigned long long e = rhccq_mb_warp_incl_scan(o);
+                            const unsigned reach = rhccq_ballot(jj < j_hi && !((double)(run0 + e) < rv));
+                            if (reach) { j = j0 + __ffs((int)reach) - 1; break; }
+                            run0 += rhccq_shfl(e, RHCCQ_WARP_SIZE - 1);
                         }
-                        if (j >= j_hi) j = ns;                      // (cannot happen: the chunk's sum reaches rv)
                     }
                 }
-                s_cand[t] = j < ns - 1 ? j : ns - 1;
+                if (lane == 0) s_cand[t] = j < ns - 1 ? j : ns - 1;
             }
             __syncthreads();
             uint32_t xc[RHCCQ_MB_MAXT];
