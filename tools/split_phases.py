@@ -35,7 +35,10 @@ torch.cuda.synchronize()
 be.cdll.rhccq_split_prof_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
 buf = (ctypes.c_ulonglong * 16)()
 be.cdll.rhccq_split_prof_read(buf, 1)           # reset
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 pipeline.stage1(be, imgs, labs, tab)
+e1.record()
 torch.cuda.synchronize()
 be.cdll.rhccq_split_prof_read(buf, 0)
 names = ["prologue", "top-level seeding (CTA)", "top-level Lloyd (CTA)", "CTA-level rest (partition, queue)",
@@ -48,3 +51,6 @@ for n, x in zip(names, v):
 print("E steps", buf[8], "; points through the bound test", buf[7], ", failing it", buf[9], ", still failing with the tightened bound", buf[10])
 print("points to the second level", buf[14], "; E steps with third-level decisions", buf[15])
 print("tolerance decisions in float64", buf[11], " seeding: draws re-evaluated", buf[12], " candidate ties", buf[13])
+busy_ms = tot / 1.965e6
+print(f"sum of the CTAs' phase times {busy_ms:.0f} ms; stage 1 took {e0.elapsed_time(e1):.1f} ms in all (split kernel ~85 % of it): "
+      f"{busy_ms / 296:.1f} ms per resident CTA slot (296 = 2 per SM) -> what is missing to the kernel's time is the tail")
