@@ -29,6 +29,20 @@ def test_writer_is_byte_identical_to_the_reference(tmp_path):
     assert open(fn2, "rb").read() == want
 
 
+def test_writer_at_another_zlib_level_is_read_back(tmp_path):
+    """``level`` trades size for host time; the reader (and the reference's: it only calls zlib.decompress) gets the
+    same palette and indices from any level, only level 9 gives the reference's bytes."""
+    g = golden("pipeline_small.npz")
+    pal, idx, shape = g["palette"], g["indices"], tuple(int(v) for v in g["shape"])
+    want = open(os.path.join(GOLDEN, "container_small.rhccq"), "rb").read()
+    for level in (1, 6):
+        fn = tmp_path / f"l{level}.rhccq"
+        C.save_encoded(pal, idx.reshape(shape), fn, level=level)
+        assert open(fn, "rb").read() != want
+        p2, i2, s2 = U.lossless_decompress(U.load_compressed(fn))
+        assert np.array_equal(p2, pal) and np.array_equal(np.asarray(i2).reshape(shape), idx.reshape(shape)) and tuple(s2) == shape
+
+
 def test_reader_reads_a_file_shipped_by_the_reference():
     d = U.load_compressed(os.path.join(GOLDEN, "reference_Lenna_compressed.rhccq"))
     assert set(d) == {"s", "l", "p", "i", "d"} and tuple(d["s"]) == (512, 512) and d["l"] == 147 and d["d"] == "uint8"
