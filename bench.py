@@ -456,6 +456,31 @@ def container_probe(pals, idx, e2e_ms):
                                    "note": "encode step from host buffers + the container writes of its frames, not overlapped"}}
 
 
+def device_container_probe(be, res, e2e_ms, pals, idx):
+    """The same frames with the index streams built on the device (csrc/rhccq_deflate.cu; palette stream, pickle and
+    the outer zlib on host threads): valid .rhccq files the reference's reader opens, not the reference's bytes."""
+    import tempfile
+    import torch
+    from roibasedimagecompression_b200.encoder.compression import device_deflate as DD
+    from roibasedimagecompression_b200.decoder.uncompression import uncompression as U
+    B = int(res.indices.shape[0])
+    with tempfile.TemporaryDirectory() as d:
+        names = [os.path.join(d, f"f{b}.rhccq") for b in range(B)]
+        DD.save_batch(be, res, names)                                   # warm-up (allocations)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sizes = DD.save_batch(be, res, names)
+        dt = time.perf_counter() - t0
+        p0, i0, s0 = U.lossless_decompress(U.load_compressed(names[0]))
+        ok = bool(np.array_equal(p0, np.asarray(pals[0])) and np.array_equal(np.asarray(i0).reshape(s0), np.asarray(idx[0])))
+    px = int(res.indices.numel())
+    return {"what": "index streams by rhccq_deflate_chunks / rhccq_deflate_pack (fixed-Huffman blocks, run and row-above matches), "
+                    "palette stream + pickle + outer zlib (level 1) on host threads",
+            "ms_batch": dt * 1e3, "bytes_out": int(sum(sizes)), "bits_per_pixel": 8.0 * sum(sizes) / px,
+            "frame0_read_back_equal": ok,
+            "e2e_with_container": {"value": px / 1e6 / ((e2e_ms + dt * 1e3) / 1e3), "unit": "MPx/s", "ms_per_step": e2e_ms + dt * 1e3}}
+
+
 def encode_probe(be, B, H, W, tile, steps, warmup):
     """Device-resident and end-to-end encode of B synthetic HxW images (tile segmentation): ms, MPx/s, kernels."""
     import torch
@@ -745,6 +770,7 @@ def main():
     # so the frames of a batch are written by one process per host core; the bytes are the single-threaded writer's.
     if rank == 0 and world == 1 and not args.no_container:
         out["container"] = container_probe(pals, idx, e2e_ms)
+        out["container"]["device"] = device_container_probe(be, res, e2e_ms, pals, idx)
 
     # ---- BASELINE configs[2]: one 3840x2160 image through the same three stages (and eight of them in one batch,
     # where the sequential MiniBatchKMeans chain of the stage-2 palettes amortises)

@@ -293,6 +293,21 @@ int rhccq_decode_gather(const void* indices, int idx_bytes, long long n, const u
                         uint8_t* out_rgb, int32_t* bad, void* stream);
 int rhccq_sq_abs_err(const uint8_t* a, const uint8_t* b, long long n, long long* acc2, void* stream);
 
+/* ------------------------------------------------------------------ container side
+ * The 'i' entry of the .rhccq package is zlib(index bytes) (/root/reference/encoder/compression/compression.py:204-220,
+ * read back by zlib.decompress, decoder/uncompression/uncompression.py:58-92).  rhccq_deflate_chunks turns every
+ * rhccq_deflate_chunk_bytes() bytes of n_frames index planes (frame f at src + f * frame_stride, frame_bytes each;
+ * elem_bytes per index, row_bytes per image row) into one fixed-Huffman deflate block followed by an empty stored
+ * block, in the chunk's slot of rhccq_deflate_slot_bytes() bytes; slot_len[c] = bytes used, sums[2c], sums[2c+1] =
+ * (sum of the chunk's bytes, sum of position-in-chunk * byte) for the Adler-32.  rhccq_deflate_pack copies slot c to
+ * out + offsets[c].  The stream of a frame is 78 01 | its chunks | 03 00 | Adler-32 (big-endian). */
+int rhccq_deflate_chunk_bytes(void);
+int rhccq_deflate_slot_bytes(void);
+int rhccq_deflate_chunks(const uint8_t* src, long long frame_stride, int frame_bytes, int n_frames, int elem_bytes,
+                         int row_bytes, uint8_t* slots, int32_t* slot_len, unsigned long long* sums, void* stream);
+int rhccq_deflate_pack(const uint8_t* slots, const int32_t* slot_len, const long long* offsets, long long n_slots,
+                       uint8_t* out, void* stream);
+
 /* out[i] = sum_{j<i} max(in[j],0), out[n] = total. */
 int rhccq_excl_scan(const int32_t* in, int n, int32_t* out, void* stream);
 

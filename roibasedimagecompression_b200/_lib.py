@@ -52,6 +52,10 @@ SIGNATURES = {
     "rhccq_excl_scan": (_I, [_P, _I, _P, _P]),
     "rhccq_decode_gather": (_I, [_P, _I, ctypes.c_longlong, _P, _I, _P, _P, _P]),
     "rhccq_sq_abs_err": (_I, [_P, _P, ctypes.c_longlong, _P, _P]),
+    "rhccq_deflate_chunk_bytes": (_I, []),
+    "rhccq_deflate_slot_bytes": (_I, []),
+    "rhccq_deflate_chunks": (_I, [_P, ctypes.c_longlong, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "rhccq_deflate_pack": (_I, [_P, _P, _P, ctypes.c_longlong, _P, _P]),
     "rhccq_dbscan_plan_make": (_I, [_I, _I, _I, _D, _I, _P, _P, _P]),
     "rhccq_dbscan_workspace_bytes": (_Z, [_P]),
     "rhccq_dbscan_bounds": (_I, [_P, _I, _I, _I, _P, _P, _Z, _P]),

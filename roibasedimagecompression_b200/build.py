@@ -7,7 +7,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["rhccq_api.cu", "rhccq_palette.cu", "rhccq_split.cu", "rhccq_minibatch.cu", "rhccq_points.cu", "rhccq_pixels.cu", "rhccq_merge.cu"]
+SOURCES = ["rhccq_api.cu", "rhccq_palette.cu", "rhccq_split.cu", "rhccq_minibatch.cu", "rhccq_points.cu", "rhccq_pixels.cu", "rhccq_merge.cu", "rhccq_deflate.cu"]
 OUT = os.path.join(HERE, "librhccq.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

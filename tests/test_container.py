@@ -43,6 +43,58 @@ def test_writer_at_another_zlib_level_is_read_back(tmp_path):
         assert np.array_equal(p2, pal) and np.array_equal(np.asarray(i2).reshape(shape), idx.reshape(shape)) and tuple(s2) == shape
 
 
+def test_device_zlib_streams_decompress_to_the_index_bytes(backend):
+    """csrc/rhccq_deflate.cu: whatever the plane holds — runs, rows repeating the row above, noise with bytes on both
+    sides of the 8 / 9-bit literal codes, one or two bytes per index, sizes that are not multiples of the 4 KiB
+    chunk, planes shorter than a match — zlib.decompress returns the bytes (and checks the Adler-32)."""
+    import zlib
+    from roibasedimagecompression_b200.encoder.compression import device_deflate as DD
+    rng = np.random.default_rng(8)
+    cases = []
+    g = golden("pipeline_small.npz")
+    shape = tuple(int(v) for v in g["shape"])
+    cases.append((g["indices"].astype(np.uint8).reshape(1, -1), 1, shape[1]))
+    cases.append((np.ascontiguousarray(g["indices"].astype(np.uint16).reshape(1, -1)).view(np.uint8), 2, 2 * shape[1]))
+    cases.append((rng.integers(0, 256, (3, 9000), dtype=np.uint8), 1, 300))                    # incompressible
+    smooth = np.repeat(np.repeat(rng.integers(0, 200, (2, 20, 30), dtype=np.uint8), 7, axis=1), 11, axis=2)
+    cases.append((smooth.reshape(2, -1), 1, smooth.shape[2]))                                  # runs and repeated rows
+    cases.append((np.zeros((1, 70000), np.uint8), 1, 40000))                                   # row longer than the window
+    cases.append((np.full((2, 2), 255, np.uint8), 1, 2))
+    cases.append((np.arange(1, dtype=np.uint8).reshape(1, 1), 1, 1))
+    wide = (np.arange(5000) // 37 % 700).astype(np.uint16)
+    cases.append((np.ascontiguousarray(wide.reshape(1, -1)).view(np.uint8), 2, 200))
+    for planes, elem, row in cases:
+        planes = np.ascontiguousarray(planes)
+        got = DD.zlib_streams(backend, torch.from_numpy(planes).to(backend.device), elem, row)
+        assert len(got) == planes.shape[0]
+        for f, st in enumerate(got):
+            assert zlib.decompress(st) == planes[f].tobytes(), (planes.shape, elem, row)
+    empty = DD.zlib_streams(backend, torch.zeros((2, 0), dtype=torch.uint8, device=backend.device), 1, 1)
+    assert empty == [b"\x78\x01\x03\x00\x00\x00\x00\x01"] * 2 and zlib.decompress(empty[0]) == b""
+
+
+def test_device_container_is_read_by_the_reader(backend, tmp_path):
+    """save_batch: index streams from the device inside the reference's package; the reader returns the pipeline's
+    palette and indices."""
+    from roibasedimagecompression_b200 import pipeline
+    from roibasedimagecompression_b200.encoder.compression import device_deflate as DD
+    from roibasedimagecompression_b200.synth import synth
+    H, W = 64, 96
+    imgs = np.stack([synth(H, W, 5 + i) for i in range(2)])
+    tab, lab = pipeline.table_from_tiles(2, H, W, 32)
+    labs = np.ascontiguousarray(np.broadcast_to(lab, (2, 2, H, W)))
+    res = pipeline.encode_batch(backend, torch.from_numpy(imgs).to(backend.device), torch.from_numpy(labs).to(backend.device), tab)
+    pipeline.finish_checks(res)
+    names = [tmp_path / f"f{b}.rhccq" for b in range(2)]
+    sizes = DD.save_batch(backend, res, names)
+    for b in range(2):
+        assert sizes[b] == os.path.getsize(names[b])
+        p2, i2, s2 = U.lossless_decompress(U.load_compressed(names[b]))
+        assert tuple(s2) == (H, W)
+        assert np.array_equal(p2, res.palette(b))
+        assert np.array_equal(np.asarray(i2).reshape(H, W), res.index_image(b))
+
+
 def test_reader_reads_a_file_shipped_by_the_reference():
     d = U.load_compressed(os.path.join(GOLDEN, "reference_Lenna_compressed.rhccq"))
     assert set(d) == {"s", "l", "p", "i", "d"} and tuple(d["s"]) == (512, 512) and d["l"] == 147 and d["d"] == "uint8"
