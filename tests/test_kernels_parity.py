@@ -484,6 +484,33 @@ def test_split_kernel_stress_equals_oracle(backend, kind):
         assert np.array_equal(got["indices"], want["indices"]), (kind, trial, n, q, m)
 
 
+def test_pipeline_random_images_equal_oracle(backend):
+    """A slice of tools/pipeline_fuzz.py in the suite: random small images, tile sizes and quality pairs through the
+    three stages, palette and every index equal to the oracle's (the duplicate-rows refusal of DESIGN.md section 2
+    is the only accepted alternative)."""
+    from roibasedimagecompression_b200._lib import RhccqError
+    rng = np.random.default_rng(606)
+    equal = 0
+    for c in range(40 if backend.device.type == "cuda" else 8):
+        H, W = int(rng.integers(3, 8)) * 16, int(rng.integers(3, 10)) * 16
+        tile = int(rng.choice([16, 32, 48, 64]))
+        img = synth(H, W, int(rng.integers(0, 10 ** 6)), sigma=float(rng.choice([1.0, 3.0, 6.0])))
+        if rng.random() < 0.3:
+            img = np.clip((img // int(rng.integers(2, 9))) * int(rng.integers(1, 5)), 0, 255).astype(np.uint8)
+        quals = (int(rng.choice([10, 20, 30, 50])), int(rng.choice([5, 10, 20])))
+        roi, non = tile_regions(H, W, tile)
+        want = O.encode_image(img, roi, non, roi_quality=quals[0], nonroi_quality=quals[1])
+        try:
+            pal, idx = _encode_device(backend, img, roi, non, quals)
+        except RhccqError as e:
+            assert "holds a colour twice" in str(e)
+            continue
+        assert np.array_equal(pal, want["palette"]), (c, H, W, tile, quals)
+        assert np.array_equal(idx, np.asarray(want["indices"]).reshape(-1)), (c, H, W, tile, quals)
+        equal += 1
+    assert equal >= 6
+
+
 # --------------------------------------------------------------------------- >= 10 000 colours
 def _big_palette(seed, n):
     img = synth(256, 256, seed, sigma=3.0)
