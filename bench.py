@@ -479,7 +479,7 @@ def device_container_probe(be, res, e2e_ms, pals, idx):
         ok = bool(np.array_equal(p0, np.asarray(pals[0])) and np.array_equal(np.asarray(i0).reshape(s0), np.asarray(idx[0])))
     px = int(res.indices.numel())
     return {"what": "index streams by rhccq_deflate_chunks / rhccq_deflate_pack (fixed-Huffman blocks, run and row-above matches), "
-                    "palette stream + pickle + outer zlib (stored) on host threads",
+                    "palette stream + pickle + outer zlib (level 1) on host threads",
             "ms_batch": dt * 1e3, "kernels_ms": kt, "bytes_out": int(sum(sizes)), "bits_per_pixel": 8.0 * sum(sizes) / px,
             "frame0_read_back_equal": ok,
             "e2e_with_container": {"value": px / 1e6 / ((e2e_ms + dt * 1e3) / 1e3), "unit": "MPx/s", "ms_per_step": e2e_ms + dt * 1e3}}

@@ -67,6 +67,31 @@ __device__ __forceinline__ void rhccq_df_distance(rhccq_bitw& w, int dist) {    
     rhccq_df_put(w, (unsigned)((d - (2 << e)) & ((1 << e) - 1)), e);
 }
 
+// Length of the common prefix of a[0..) and a[-d..), at most `room` bytes.  Four bytes per step while eight bytes
+// from both positions are inside the buffer (`left` bytes remain from a): two aligned words and a funnel shift give
+// the word at any byte address.  `wide` is false when the buffer's base is not word-aligned.
+__device__ __forceinline__ uint32_t rhccq_df_word(const uint8_t* a) {
+#ifdef RHCCQ_HOST_EMU
+    uint32_t v; memcpy(&v, a, 4); return v;
+#else
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(a);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (unsigned)(ad & 3) * 8u);
+#endif
+}
+__device__ __forceinline__ int rhccq_df_match(const uint8_t* a, int d, int room, long long left, bool wide) {
+    int l = 0;
+    if (wide) {
+        while (l + 4 <= room && (long long)l + 8 <= left) {
+            const uint32_t x = rhccq_df_word(a + l) ^ rhccq_df_word(a + l - d);
+            if (x != 0u) return l + ((__ffs((int)x) - 1) >> 3);
+            l += 4;
+        }
+    }
+    while (l < room && a[l] == a[l - d]) ++l;
+    return l;
+}
+
 // One thread per chunk.  frames: n_frames planes of frame_bytes bytes each, frame f at src + f * frame_stride.
 // slots: n_frames * chunks_per_frame slots of RHCCQ_DF_SLOT bytes; slot_len: bytes written; sums: (sum of the
 // chunk's bytes, sum of j * byte_j) for Adler-32.
@@ -84,12 +109,15 @@ rhccq_k_deflate_chunks(const uint8_t* __restrict__ src, long long frame_stride, 
         rhccq_df_put(w, 2u, 3);                                       // BFINAL = 0, BTYPE = 01
         unsigned long long s1 = 0, s2 = 0;
         const bool use_row = row_bytes >= 1 && row_bytes <= 32768;
+        const long long src_bytes = (long long)(n_frames - 1) * frame_stride + frame_bytes;
+        const bool wide = (reinterpret_cast<uintptr_t>(src) & 3) == 0;
         int i = s;
         while (i < e) {
             const int room = e - i < 258 ? e - i : 258;
             int l1 = 0, l2 = 0;
-            if (i >= elem) while (l1 < room && p[i + l1] == p[i + l1 - elem]) ++l1;
-            if (use_row && i >= row_bytes && row_bytes != elem) while (l2 < room && p[i + l2] == p[i + l2 - row_bytes]) ++l2;
+            const long long left = src_bytes - ((long long)f * frame_stride + i);
+            if (i >= elem) l1 = rhccq_df_match(p + i, elem, room, left, wide);
+            if (use_row && i >= row_bytes && row_bytes != elem) l2 = rhccq_df_match(p + i, row_bytes, room, left, wide);
             int len = l1, dist = elem;
             if (l2 > l1) { len = l2; dist = row_bytes; }
             if (len >= 3) {

@@ -62,17 +62,18 @@ def zlib_streams(be, planes: torch.Tensor, elem_bytes: int, row_bytes: int) -> l
     return res
 
 
-def package(palette_u8: np.ndarray, i_stream: bytes, shape, dtype_name: str, *, level: int = 0) -> bytes:
+def package(palette_u8: np.ndarray, i_stream: bytes, shape, dtype_name: str, *, level: int = 1) -> bytes:
     """The bytes of one .rhccq file around a ready 'i' stream (compression.py:119-142, :151-202).  ``level`` is that
-    of the outer zlib over the pickle: its content is the already compressed index stream, so the default stores it
-    (level 0 is a valid zlib stream; the palette's few hundred bytes get level 9 as in the reference)."""
+    of the outer zlib over the pickle.  Its content is the device's index stream, whose fixed Huffman code leaves
+    redundancy: level 1 takes another 15 % off the file for ~0.2 ms per full-HD frame and thread (level 0 stores
+    it: 0.99 instead of 0.84 bits per pixel on the bench frames).  The palette's few hundred bytes get level 9."""
     d = {"s": (int(shape[0]), int(shape[1])), "l": int(len(palette_u8)),
          "p": _C.compress_palette([tuple(int(v) for v in c) for c in palette_u8], 9), "i": i_stream, "d": dtype_name}
     body = zlib.compress(pickle.dumps(d, protocol=5), level)
     return _C.MAGIC + struct.pack("<I", len(body)) + body
 
 
-def save_batch(be, result, filenames, *, level: int = 0, threads: int = 16) -> list:
+def save_batch(be, result, filenames, *, level: int = 1, threads: int = 16) -> list:
     """Write every frame of an `EncodeResult` (pipeline.encode_batch) as a .rhccq file, the index streams built on
     the device.  Returns the file sizes.  Index dtype per frame as the reference chooses it (uint8 below 256
     palette rows, else uint16; compression.py:160-170)."""
