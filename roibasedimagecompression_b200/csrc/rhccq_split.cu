@@ -51,7 +51,9 @@ __device__ unsigned long long rhccq_split_prof[16];
 #define RHCCQ_KM_CAND 16               // ints per candidate table: RHCCQ_KM_MAXT candidates + 2 flags
 #define RHCCQ_KC 128                   // centres of a CTA-level K-Means kept in shared memory
 #define RHCCQ_KW 8                     // centres of a warp-level K-Means
+#ifndef RHCCQ_WARP_RANGE
 #define RHCCQ_WARP_RANGE 1024          // largest range a single warp splits
+#endif
 #define RHCCQ_KPRIV 32                 // k up to which the CTA-level M step uses per-warp histograms
 #define RHCCQ_SPLIT_THREADS_BIG 512     // few, large palettes (stage 2): one CTA per SM, twice the warps
 #define RHCCQ_SPLIT_MAX_WARPS (RHCCQ_SPLIT_THREADS_BIG / 32)
