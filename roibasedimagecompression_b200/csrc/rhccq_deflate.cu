@@ -11,9 +11,10 @@
 // Format produced (RFC 1950 / 1951): 78 01 | per 4 KiB chunk of the input: one block with the fixed Huffman
 // code, then an empty stored block (00 00 00 FF FF after padding: zlib's "sync flush"), which leaves every chunk's
 // output byte-aligned and independent of its neighbours | 03 00 (empty final block) | Adler-32, big-endian.
-// Inside a chunk one thread walks the bytes: at each position the longer of two matches — against the previous
-// index (distance = bytes per index) and against the index one row up (distance = bytes per row; index planes
-// repeat vertically) — of at least 3 bytes becomes a length/distance pair, anything else a literal.  Matches
+// Inside a chunk one thread walks the bytes: at each position the longest of five matches — against the previous
+// index (distance = bytes per index), the index one row up (distance = bytes per row; index planes repeat
+// vertically), its two neighbours (row -/+ one index) and the index two rows up — of at least 3 bytes becomes a
+// length/distance pair, anything else a literal.  Matches
 // may reach back across chunk borders (the window is the stream), never forward across them.
 // A second kernel packs the chunks' outputs into one run per frame; the chunk sums for Adler-32 are combined on
 // the host (two integers per chunk).
@@ -120,6 +121,11 @@ rhccq_k_deflate_chunks(const uint8_t* __restrict__ src, long long frame_stride, 
             if (use_row && i >= row_bytes && row_bytes != elem) l2 = rhccq_df_match(p + i, row_bytes, room, left, wide);
             int len = l1, dist = elem;
             if (l2 > l1) { len = l2; dist = row_bytes; }
+            if (use_row && row_bytes > 2 * elem && row_bytes + elem <= 32768) {
+                if (i >= row_bytes - elem) { const int l3 = rhccq_df_match(p + i, row_bytes - elem, room, left, wide); if (l3 > len) { len = l3; dist = row_bytes - elem; } }
+                if (i >= row_bytes + elem) { const int l4 = rhccq_df_match(p + i, row_bytes + elem, room, left, wide); if (l4 > len) { len = l4; dist = row_bytes + elem; } }
+            }
+            if (use_row && 2 * row_bytes <= 32768 && i >= 2 * row_bytes) { const int l5 = rhccq_df_match(p + i, 2 * row_bytes, room, left, wide); if (l5 > len) { len = l5; dist = 2 * row_bytes; } }
             if (len >= 3) {
                 rhccq_df_length(w, len);
                 rhccq_df_distance(w, dist);
